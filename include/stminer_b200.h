@@ -1,0 +1,112 @@
+/*
+ * stminer_b200.h — C ABI of the B200-native STMiner spatial-pattern hot path.
+ *
+ * The reference (xjtu-omics/STMiner v1.1.4) has no FFI layer: its boundary is the
+ * Python API.  Each entry point below replaces the arithmetic of
+ * one reference function and is what a reference-side ctypes binding would call
+ * (INTEGRATION.md shows those stubs).
+ *
+ * Conventions
+ *   - all array arguments are caller-owned DEVICE pointers unless the name ends
+ *     in `_host`; nothing is allocated, freed or retained by the library,
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream),
+ *   - calls only enqueue work on `stream`; there is no host synchronisation inside,
+ *   - return value: 0 on success, <0 on error (STM_ERR_*); the message of the
+ *     last error of the calling thread is available from stm_last_error_string(),
+ *   - the library is stateless and thread-compatible (one caller thread per GPU rank).
+ */
+#ifndef STMINER_B200_H_
+#define STMINER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STM_OK 0
+#define STM_ERR_INVALID_ARG (-1)
+#define STM_ERR_CUDA (-2)
+#define STM_ERR_UNSUPPORTED (-3)
+
+/* per-gene status written by stm_gmm_fit_batched */
+#define STM_GENE_OK 0
+#define STM_GENE_DROPPED 1          /* fewer than K distinct positive spots: reference returns None
+                                       (STMiner/Algorithm/distribution.py:125,129-130) */
+#define STM_GENE_ILL_CONDITIONED 2  /* a covariance lost positive-definiteness: sklearn raises ValueError
+                                       (_gaussian_mixture.py:361-367 -> distribution.py:200-202) */
+
+/* flags of stm_gmm_fit_batched */
+#define STM_FIT_REMOVE_LOW_EXP_SPOTS 1u /* AlgUtils.py:16-17: w <- round(max(w - mean(nonzero w), 0)) */
+#define STM_FIT_DEVICE_INIT 2u          /* ignore init_*; run the on-device weighted k-means++/Lloyd init
+                                           (replaces sklearn KMeans inside GaussianMixture, _base.py:119-128) */
+
+/* Library / build identification. */
+int stm_version(void);
+const char* stm_last_error_string(void);
+
+/*
+ * Batched count-weighted 2-D Gaussian-mixture EM fit — one CTA per gene, whole EM loop on chip.
+ *
+ * Replaces: fit_gmms / fit_gmm        STMiner/Algorithm/distribution.py:148-205, :87-130
+ *           get_exp_array             STMiner/Algorithm/AlgUtils.py:8-36       (int16 truncation of the column)
+ *           array_to_list             STMiner/Algorithm/distribution.py:369-373 (count-replicated list == integer weights)
+ *           GaussianMixture.fit       scikit-learn 1.3.0 mixture/_base.py:203-312 (E/M loop, tol on the lower bound)
+ *
+ * Input is the expression matrix in CSC form over DISTINCT spots:
+ *   col_ptr[G+1]   int64   column (gene) pointers
+ *   row_idx[nnz]   int32   spot index of each stored value
+ *   val[nnz]       float   expression value; truncated toward zero to int16 inside (AlgUtils.py:35);
+ *                          entries whose truncated value is <= 0 are ignored
+ *   spot_x, spot_y [n_spots] int32 integer grid coordinates of each spot (adata.obs['x'], ['y'])
+ *   gene_order[G]  int32   optional (NULL = 0..G-1): CTA b fits gene gene_order[b]; pass genes sorted by
+ *                          decreasing nnz so long genes start first (LPT)
+ * Initial parameters (ignored with STM_FIT_DEVICE_INIT; required otherwise), float64, original coordinates:
+ *   init_w[G,K], init_mu[G,K,2], init_cov[G,K,2,2]
+ * Outputs, float64, same layouts: out_w, out_mu, out_cov; plus per gene
+ *   out_n_iter int32 (sklearn n_iter_), out_converged int32, out_lower_bound float64 (sklearn lower_bound_),
+ *   out_status int32 (STM_GENE_*).  Outputs of a gene whose status != STM_GENE_OK are zero-filled.
+ * K <= 64.  reg_covar/tol/max_iter as sklearn (reference: 1e-3 / 1e-3 / 100, distribution.py:148-156).
+ * seed is used only by the device init.
+ */
+int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_idx, const float* val,
+                        const int32_t* spot_x, const int32_t* spot_y, int32_t n_spots,
+                        int32_t G, int32_t K, const int32_t* gene_order,
+                        const double* init_w, const double* init_mu, const double* init_cov,
+                        double reg_covar, double tol, int32_t max_iter, uint32_t flags, uint64_t seed,
+                        double* out_w, double* out_mu, double* out_cov,
+                        int32_t* out_n_iter, int32_t* out_converged, double* out_lower_bound,
+                        int32_t* out_status, void* stream);
+
+/*
+ * GMM-to-GMM distance: K x K cost C[i][j] = (w1_i + w2_j) * Hellinger(N1_i, N2_j), solved as an exact
+ * linear assignment (transport LP with unit marginals).  One warp per pair, float64.
+ *
+ * Replaces: distribution_distance     STMiner/Algorithm/distance.py:13-36
+ *           get_hellinger_distance    STMiner/Algorithm/distance.py:50-80
+ *           linear_sum                STMiner/Algorithm/algorithm.py:10-26 (scipy.optimize.linear_sum_assignment)
+ *           build_gmm_distance_array  STMiner/Algorithm/distance.py:83-99  (all i<j pairs)
+ *
+ * w[G,K], mu[G,K,2], cov[G,K,2,2] float64.  Pairs are the linearised strict upper triangle in row-major
+ * order: p = 0 is (0,1), p = 1 is (0,2) ... ; the call computes pairs [pair_begin, pair_end) and writes
+ * out[p - pair_begin] (float64).  A rank of a multi-GPU job passes its own slice.
+ */
+int stm_gmm_dist_pairs(const double* w, const double* mu, const double* cov, int32_t G, int32_t K,
+                       int64_t pair_begin, int64_t pair_end, double* out, void* stream);
+
+/* Mirror a full pair vector (length G(G-1)/2) into a dense symmetric G x G float64 matrix with zero
+ * diagonal (distance.py:93-98). */
+int stm_gmm_dist_fill_square(const double* pairs, int32_t G, double* out_square, void* stream);
+
+/*
+ * One-vs-all variant.  Replaces compare_gmm_distance STMiner/Algorithm/distance.py:102-111.
+ * Query GMM (qw[K], qmu[K,2], qcov[K,2,2]) against G GMMs; out[G] float64.
+ */
+int stm_gmm_dist_one_vs_all(const double* qw, const double* qmu, const double* qcov,
+                            const double* w, const double* mu, const double* cov,
+                            int32_t G, int32_t K, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STMINER_B200_H_ */

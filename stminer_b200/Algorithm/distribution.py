@@ -1,0 +1,174 @@
+"""Per-gene Gaussian-mixture fit on B200 — host mirror of ``STMiner/Algorithm/distribution.py``.
+
+``fit_gmms`` keeps the reference's name, argument meaning and error behaviour
+(distribution.py:148-205) but fits every gene of the list in ONE batched kernel launch through the
+C ABI (``stm_gmm_fit_batched``) instead of a serial sklearn loop.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from .. import _lib
+from ..staging import DeviceSpotMatrix, SpotMatrix
+
+logger = logging.getLogger(__name__)
+
+
+class GMM:
+    """Plain mixture container — same surface as the reference's ``class GMM`` (distribution.py:390-403),
+    which is the duck type every distance function consumes (distance.py:23-28)."""
+
+    def __init__(self, n):
+        self.means_ = np.zeros((n, 2))
+        self.covariances_ = np.zeros((n, 2, 2))
+        self.weights_ = np.zeros((n,))
+        self.n_iter_ = 0
+        self.converged_ = False
+        self.lower_bound_ = -np.inf
+
+    def set_mean(self, means):
+        self.means_ = means
+
+    def set_covariances(self, covariances):
+        self.covariances_ = covariances
+
+    def set_weights(self, weights):
+        self.weights_ = weights
+
+    @property
+    def n_components(self):
+        return self.weights_.shape[0]
+
+    def score_samples(self, X):
+        """log p(x) of the mixture — what ``view_gmm`` (distribution.py:313) needs for plotting."""
+        X = np.asarray(X, dtype=np.float64)
+        out = np.full(X.shape[0], -np.inf)
+        for k in range(self.n_components):
+            d = X - self.means_[k]
+            P = np.linalg.inv(self.covariances_[k])
+            q = np.einsum("ni,ij,nj->n", d, P, d)
+            lp = np.log(self.weights_[k]) - 0.5 * (2 * np.log(2 * np.pi) + np.log(np.linalg.det(self.covariances_[k])) + q)
+            out = np.logaddexp(out, lp)
+        return out
+
+
+class FitResult:
+    """Device-resident result of one batched fit (torch tensors own the buffers)."""
+
+    def __init__(self, genes, weights, means, covariances, n_iter, converged, lower_bound, status):
+        self.genes = genes
+        self.weights = weights          # [G,K] f64
+        self.means = means              # [G,K,2]
+        self.covariances = covariances  # [G,K,2,2]
+        self.n_iter = n_iter
+        self.converged = converged
+        self.lower_bound = lower_bound
+        self.status = status
+
+    def to_host(self):
+        return dict(weights=self.weights.cpu().numpy(), means=self.means.cpu().numpy(),
+                    covariances=self.covariances.cpu().numpy(), n_iter=self.n_iter.cpu().numpy(),
+                    converged=self.converged.cpu().numpy(), lower_bound=self.lower_bound.cpu().numpy(),
+                    status=self.status.cpu().numpy())
+
+
+def fit_spot_matrix(dsm: DeviceSpotMatrix, n_comp: int, init=None, max_iter: int = 100, reg_covar: float = 1e-3,
+                    tol: float = 1e-3, remove_low_exp_spots: bool = False, seed: int = 0,
+                    out: Optional[FitResult] = None) -> FitResult:
+    """Enqueue the batched EM fit of every gene of ``dsm`` on the current CUDA stream.
+
+    ``init`` is ``(weights[G,K], means[G,K,2], covariances[G,K,2,2])`` (numpy or CUDA tensors, float64);
+    ``None`` selects the on-device k-means++/Lloyd initialisation.
+    """
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    G, K = dsm.n_genes, int(n_comp)
+    dev = dsm.device
+    flags = _lib.STM_FIT_REMOVE_LOW_EXP_SPOTS if remove_low_exp_spots else 0
+    if init is None:
+        flags |= _lib.STM_FIT_DEVICE_INIT
+        iw = imu = icov = None
+    else:
+        def dv(a, shape):
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+            t = t.to(device=dev, dtype=torch.float64).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError("init array has shape %s, expected %s" % (tuple(t.shape), shape))
+            return t
+        iw, imu, icov = dv(init[0], (G, K)), dv(init[1], (G, K, 2)), dv(init[2], (G, K, 2, 2))
+    if out is None:
+        out = FitResult(
+            dsm.host.genes,
+            torch.empty((G, K), dtype=torch.float64, device=dev),
+            torch.empty((G, K, 2), dtype=torch.float64, device=dev),
+            torch.empty((G, K, 2, 2), dtype=torch.float64, device=dev),
+            torch.empty((G,), dtype=torch.int32, device=dev),
+            torch.empty((G,), dtype=torch.int32, device=dev),
+            torch.empty((G,), dtype=torch.float64, device=dev),
+            torch.empty((G,), dtype=torch.int32, device=dev))
+    with torch.cuda.device(dev):
+        st = lib.stm_gmm_fit_batched(
+            _lib.ptr(dsm.col_ptr), _lib.ptr(dsm.row_idx), _lib.ptr(dsm.val), _lib.ptr(dsm.spot_x), _lib.ptr(dsm.spot_y),
+            dsm.n_spots, G, K, _lib.ptr(dsm.gene_order), _lib.ptr(iw), _lib.ptr(imu), _lib.ptr(icov),
+            float(reg_covar), float(tol), int(max_iter), int(flags), int(seed),
+            _lib.ptr(out.weights), _lib.ptr(out.means), _lib.ptr(out.covariances), _lib.ptr(out.n_iter),
+            _lib.ptr(out.converged), _lib.ptr(out.lower_bound), _lib.ptr(out.status), _lib.current_stream_ptr())
+    _lib.check(st, "stm_gmm_fit_batched")
+    out._keepalive = (iw, imu, icov)
+    return out
+
+
+def result_to_gmm_dict(genes: Sequence[str], host: dict) -> Dict[str, GMM]:
+    """FitResult (host copy) -> {gene: GMM} with the reference's policies: dropped genes are skipped and
+    counted (distribution.py:196-204); an ill-conditioned gene raises ValueError('Gene id: ...')
+    (distribution.py:200-202)."""
+    gmm_dict: Dict[str, GMM] = {}
+    dropped = 0
+    for g, name in enumerate(genes):
+        s = int(host["status"][g])
+        if s == _lib.STM_GENE_DROPPED:
+            dropped += 1
+            continue
+        if s != _lib.STM_GENE_OK:
+            raise ValueError("Gene id: " + str(name) + "\nError: Fitting the mixture model failed because some "
+                             "components have ill-defined empirical covariance")
+        m = GMM(host["weights"].shape[1])
+        m.set_weights(host["weights"][g].copy())
+        m.set_mean(host["means"][g].copy())
+        m.set_covariances(host["covariances"][g].copy())
+        m.n_iter_ = int(host["n_iter"][g])
+        m.converged_ = bool(host["converged"][g])
+        m.lower_bound_ = float(host["lower_bound"][g])
+        gmm_dict[name] = m
+    if dropped > 0:
+        logger.info("Number of dropped genes: " + str(dropped))
+    return gmm_dict
+
+
+def fit_gmms(adata, gene_name_list, n_comp=15, binary=False, threshold=95, max_iter=100, reg_covar=1e-3,
+             cut=False, remove_low_exp_spots=False, init_params=None, seed=0, device=None):
+    """Drop-in for ``fit_gmms`` (distribution.py:148-156): dict gene -> GMM in ``gene_name_list`` order.
+
+    ``init_params`` (optional, not in the reference) is ``{gene: (weights, means, covariances)}`` or a
+    tuple of stacked arrays; without it the on-device initialisation replaces sklearn's KMeans.
+    ``binary`` / ``cut`` (distribution.py:133-145) are not exposed by ``SPFinder.fit_pattern`` and are
+    not implemented on the device path.
+    """
+    if binary or cut:
+        raise NotImplementedError("binary/cut preprocessing is outside the B200 hot path (SURVEY.md §8 a3)")
+    from ..adata_lite import spot_matrix_from_adata
+    gene_name_list = list(gene_name_list)
+    sm = spot_matrix_from_adata(adata, gene_name_list)
+    dsm = DeviceSpotMatrix(sm, device=device)
+    init = None
+    if init_params is not None:
+        if isinstance(init_params, dict):
+            init = tuple(np.stack([np.asarray(init_params[g][i], dtype=np.float64) for g in sm.genes]) for i in range(3))
+        else:
+            init = init_params
+    res = fit_spot_matrix(dsm, n_comp, init=init, max_iter=max_iter, reg_covar=reg_covar,
+                          remove_low_exp_spots=remove_low_exp_spots, seed=seed)
+    return result_to_gmm_dict(sm.genes, res.to_host())

@@ -1,0 +1,92 @@
+"""ctypes binding of ``libstminer_b200.so`` (the C ABI declared in ``include/stminer_b200.h``).
+
+There is NO CPU fallback: if the library cannot be loaded, or no CUDA device is present when a
+compute entry point is called, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+_lock = threading.Lock()
+_lib = None
+
+c_i32p = C.c_void_p
+_P = C.c_void_p
+
+STM_GENE_OK = 0
+STM_GENE_DROPPED = 1
+STM_GENE_ILL_CONDITIONED = 2
+STM_FIT_REMOVE_LOW_EXP_SPOTS = 1
+STM_FIT_DEVICE_INIT = 2
+
+# every symbol include/stminer_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "stm_version": (C.c_int, []),
+    "stm_last_error_string": (C.c_char_p, []),
+    "stm_gmm_fit_batched": (C.c_int, [
+        _P, _P, _P, _P, _P, C.c_int32,                 # col_ptr,row_idx,val,spot_x,spot_y,n_spots
+        C.c_int32, C.c_int32, _P,                      # G,K,gene_order
+        _P, _P, _P,                                    # init_w,init_mu,init_cov
+        C.c_double, C.c_double, C.c_int32, C.c_uint32, C.c_uint64,  # reg_covar,tol,max_iter,flags,seed
+        _P, _P, _P, _P, _P, _P, _P, _P,                # out_w,out_mu,out_cov,n_iter,converged,lb,status,stream
+    ]),
+    "stm_gmm_dist_pairs": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
+    "stm_gmm_dist_fill_square": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "stm_gmm_dist_one_vs_all": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
+}
+
+
+class StmError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building in-tree first if the sources are newer and nvcc is present) the CUDA library."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.exists(path) or os.environ.get("STM_REBUILD") == "1":
+            _build.build(force=os.environ.get("STM_REBUILD") == "1")
+        if not os.path.exists(path):
+            raise RuntimeError(
+                "stminer_b200: CUDA library %s is missing and could not be built; there is no CPU fallback" % path)
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().stm_last_error_string()
+        raise StmError("%s failed with status %d: %s" % (what, status, (msg or b"").decode()))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("stminer_b200 requires a CUDA device (sm_100a); there is no CPU fallback")
+    return torch
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,138 @@
+"""Host staging of the expression matrix into the hot path's HBM layout.
+
+The reference slices ``adata[:, gene]`` and builds a dense int16 grid per gene
+(STMiner/Algorithm/AlgUtils.py:26-36, O(nnz_total) per gene).  Here ONE pass converts the whole
+matrix into CSC over DISTINCT spots — ``col_ptr / row_idx / val`` plus ``spot_x / spot_y`` — which is
+uploaded once and stays resident for every stage (fit, distances, patterns).
+
+Semantics kept from the reference:
+  * int16 truncation toward zero of every stored value (``coo_matrix(..., dtype=np.int16)``, AlgUtils.py:35),
+  * rows sharing an (x, y) are summed after truncation, with int16 wrap-around (``todense()``, AlgUtils.py:15),
+  * only cells > 0 reach the mixture fit (``array_to_list``, distribution.py:369-373).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+from scipy import sparse
+
+
+def _wrap_i16(a: np.ndarray) -> np.ndarray:
+    return ((a.astype(np.int64) + 32768) % 65536 - 32768).astype(np.int32)
+
+
+@dataclass
+class SpotMatrix:
+    """CSC expression matrix over distinct spots (host copy, numpy)."""
+
+    col_ptr: np.ndarray   # int64 [G+1]
+    row_idx: np.ndarray   # int32 [nnz]
+    val: np.ndarray       # float32 [nnz]
+    spot_x: np.ndarray    # int32 [n_spots]
+    spot_y: np.ndarray    # int32 [n_spots]
+    genes: List[str]
+
+    @property
+    def n_genes(self) -> int:
+        return len(self.col_ptr) - 1
+
+    @property
+    def n_spots(self) -> int:
+        return len(self.spot_x)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col_ptr[-1])
+
+    def nnz_per_gene(self) -> np.ndarray:
+        return np.diff(self.col_ptr)
+
+    def lpt_order(self) -> np.ndarray:
+        """Genes by decreasing nnz (longest processing time first)."""
+        return np.argsort(-self.nnz_per_gene(), kind="stable").astype(np.int32)
+
+    def gene_spots(self, g: int):
+        """(xy[nnz_g, 2] int64 sorted row-major, counts[nnz_g] int64) of gene g, as the oracle wants them."""
+        a, b = int(self.col_ptr[g]), int(self.col_ptr[g + 1])
+        r = self.row_idx[a:b]
+        w = np.trunc(self.val[a:b]).astype(np.int64)
+        keep = w > 0
+        xy = np.column_stack([self.spot_x[r][keep], self.spot_y[r][keep]]).astype(np.int64)
+        w = w[keep]
+        order = np.lexsort((xy[:, 1], xy[:, 0]))
+        return xy[order], w[order]
+
+    def select(self, idx: Sequence[int]) -> "SpotMatrix":
+        idx = np.asarray(idx, dtype=np.int64)
+        lens = np.diff(self.col_ptr)[idx]
+        col_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        take = np.concatenate([np.arange(self.col_ptr[g], self.col_ptr[g + 1]) for g in idx]) if len(idx) else \
+            np.zeros(0, dtype=np.int64)
+        return SpotMatrix(col_ptr, self.row_idx[take], self.val[take], self.spot_x, self.spot_y,
+                          [self.genes[g] for g in idx])
+
+    # ------------------------------------------------------------------ constructors
+    @classmethod
+    def from_matrix(cls, X, x, y, genes: Sequence[str], columns: Optional[Sequence[int]] = None,
+                    truncate_int16: bool = True) -> "SpotMatrix":
+        """Build from an (n_obs, n_var) matrix (scipy sparse or dense) and per-row integer coordinates."""
+        x = np.asarray(x).astype(np.int64).ravel()
+        y = np.asarray(y).astype(np.int64).ravel()
+        if sparse.issparse(X):
+            M = X.tocsc()
+        else:
+            M = sparse.csc_matrix(np.asarray(X))
+        if columns is not None:
+            M = M[:, np.asarray(columns, dtype=np.int64)]
+            genes = [genes[c] for c in columns]
+        M = M.astype(np.float64, copy=True)
+        if truncate_int16:
+            M.data = _wrap_i16(np.trunc(M.data)).astype(np.float64)        # AlgUtils.py:35
+        # distinct spots, row-major (x, y) order
+        ymul = int(y.max()) + 1 if len(y) else 1
+        key = x * ymul + y
+        uniq, inverse = np.unique(key, return_inverse=True)
+        n_obs, n_spots = len(key), len(uniq)
+        if n_spots != n_obs or not np.array_equal(inverse, np.arange(n_obs)):
+            P = sparse.csr_matrix((np.ones(n_obs), (inverse, np.arange(n_obs))), shape=(n_spots, n_obs))
+            M = (P @ M).tocsc()                                              # duplicates summed (todense, AlgUtils.py:15)
+            if truncate_int16:
+                M.data = _wrap_i16(M.data).astype(np.float64)
+        M.eliminate_zeros()
+        M.sort_indices()
+        return cls(M.indptr.astype(np.int64), M.indices.astype(np.int32), M.data.astype(np.float32),
+                   (uniq // ymul).astype(np.int32), (uniq % ymul).astype(np.int32), list(genes))
+
+
+class DeviceSpotMatrix:
+    """SpotMatrix resident in HBM (torch tensors are only the buffer owners)."""
+
+    def __init__(self, sm: SpotMatrix, device=None, order: Optional[np.ndarray] = None, non_blocking: bool = True):
+        import torch
+        from . import _lib
+        _lib.require_cuda()
+        self.host = sm
+        self.device = torch.device(device if device is not None else "cuda")
+        order = sm.lpt_order() if order is None else np.asarray(order, dtype=np.int32)
+
+        def up(a):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            return t.pin_memory().to(self.device, non_blocking=non_blocking) if non_blocking else t.to(self.device)
+
+        self.col_ptr = up(sm.col_ptr)
+        self.row_idx = up(sm.row_idx)
+        self.val = up(sm.val)
+        self.spot_x = up(sm.spot_x)
+        self.spot_y = up(sm.spot_y)
+        self.gene_order = up(order)
+        self.h2d_bytes = sum(a.nbytes for a in (sm.col_ptr, sm.row_idx, sm.val, sm.spot_x, sm.spot_y, order))
+
+    @property
+    def n_genes(self) -> int:
+        return self.host.n_genes
+
+    @property
+    def n_spots(self) -> int:
+        return self.host.n_spots
