@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native STMiner hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload S50|V|T]
+
+A "step" is one pass of the hot path over one batch: the count-weighted GMM fit (on-device
+k-means++/Lloyd initialisation + EM, K=20, reg_covar=tol=1e-3, max_iter=100 — the reference's
+``fit_pattern`` defaults) of every gene of the synthetic Stereo-seq bin50 data set
+(40,000 bins x 10,000 genes, BASELINE.json configs[2], the configuration the genes/s target is quoted on).
+With N ranks every rank fits its own 10,000-gene data set (weak scaling, no data-path collective).
+
+One JSON line is printed by rank 0.  ``value`` is genes/s with inputs resident in HBM; ``e2e`` is the same
+metric through the host-buffer API (pinned H2D of the CSC matrix + fit + D2H of the parameters inside the
+timed region); ``pairs`` reports the second half of the metric (SVG-pair GMM distances/s on 4,000 fitted
+genes, 7,998,000 pairs, pair slices sharded over the ranks and all-gathered with NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_COMP = 20
+FLOP_PER_SPOT_COMP_ITER = 30          # algorithmic FLOPs of one (spot, component, iteration)
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4, SURVEY.md §8d
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="S50", choices=["S50", "V", "T"])
+    ap.add_argument("--genes", type=int, default=0, help="override gene count (debug)")
+    ap.add_argument("--pairs-genes", type=int, default=4000)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="genes in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(name, seed, genes=0):
+    """Synthetic data set of a BASELINE config, cached under /tmp (generation is setup, never timed)."""
+    from stminer_b200.Simulate import CONFIGS, simulate_spot_matrix
+    from stminer_b200.staging import SpotMatrix
+    R, C, hexl, nt, rep = CONFIGS[name]
+    if genes:
+        nt = max(1, min(nt, genes // max(1, min(rep, genes))))
+        rep = max(1, genes // nt)
+    path = "/tmp/stm_bench_%s_%d_%d_%d.npz" % (name, seed, nt, rep)
+    if os.path.exists(path):
+        z = np.load(path)
+        return SpotMatrix(z["col_ptr"], z["row_idx"], z["val"], z["spot_x"], z["spot_y"],
+                          ["gene_%d" % i for i in range(len(z["col_ptr"]) - 1)])
+    sm = simulate_spot_matrix(name, seed=seed, n_templates=nt, replicas=rep)
+    try:
+        np.savez(path, col_ptr=sm.col_ptr, row_idx=sm.row_idx, val=sm.val, spot_x=sm.spot_x, spot_y=sm.spot_y)
+    except OSError:
+        pass
+    return sm
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_fit_one(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    xy, c, K = args
+    from oracle import gmm_oracle as go
+    t = time.perf_counter()
+    gm = go.fit_gmm_reference(xy, c, K)
+    return time.perf_counter() - t, (0 if gm is None else int(gm.n_iter_))
+
+
+class CpuReference:
+    """The reference CPU path (array_to_list + sklearn GaussianMixture.fit, KMeans init included;
+    STMiner/Algorithm/distribution.py:122-130) on a bounded sample: one process per core, 1 BLAS thread each."""
+
+    def __init__(self, cores):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context("spawn").Pool(cores, initializer=_pool_init)
+        self.pool.map(_noop, range(cores * 2))             # spin the workers up (imports) before timing
+
+    def rate(self, sm, n_sample, seed=123):
+        rng = np.random.default_rng(seed)
+        idx = rng.choice(sm.n_genes, size=min(n_sample, sm.n_genes), replace=False)
+        jobs = [(*sm.gene_spots(int(g)), K_COMP) for g in idx]
+        t = time.perf_counter()
+        res = self.pool.map(_cpu_fit_one, jobs, chunksize=1)
+        wall = time.perf_counter() - t
+        return len(jobs) / wall, wall, float(np.mean([r[0] for r in res])), len(jobs)
+
+    def close(self):
+        self.pool.terminate()
+
+
+def _pool_init():
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    sys.path.insert(0, ROOT)
+    import sklearn.mixture  # noqa: F401
+
+
+def _noop(_):
+    return 0
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sm = workload(args.workload, seed=0, genes=args.genes)
+    per_step = args.cpu_sample or max(cores, 8)
+    rates, walls = [], []
+    cpu = CpuReference(cores)
+    for s in range(args.warmup + args.steps):
+        rate, wall, mean_fit, n = cpu.rate(sm, per_step, seed=s)
+        if s >= args.warmup:
+            rates.append(rate); walls.append(wall)
+    cpu.close()
+    value = float(len(rates) * per_step / sum(walls))
+    sample = "%d genes of the %s set per step, process-per-gene pool over %d cores, 1 BLAS thread each" % (
+        per_step, args.workload, cores)
+    line = {"impl": "reference", "metric": "genes_per_sec_gmm_fit", "value": value, "unit": "genes/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, sm, 1),
+            "cpu_baseline": {"value": value, "unit": "genes/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, sm, world):
+    names = {"S50": "synthetic Stereo-seq bin50: 40,000 bins x 10,000 genes, K=20 (BASELINE configs[2])",
+             "V": "synthetic Visium-shaped: 4,992 spots x 2,000 genes, K=20 (BASELINE configs[1])",
+             "T": "synthetic 17x17 test-path stand-in, K=20"}
+    return {"workload": names[args.workload], "genes_per_gpu": sm.n_genes, "spots": sm.n_spots,
+            "nnz_per_gpu": sm.nnz, "n_comp": K_COMP, "reg_covar": 1e-3, "tol": 1e-3, "max_iter": 100,
+            "init": "on-device weighted k-means++ + Lloyd (replaces sklearn KMeans)",
+            "sharding": "genes: one independent data set per rank (weak); pairs: contiguous slices + all-gather",
+            "l2": "L2 flushed (256 MiB write) between timed steps; S50 inputs (%.0f MB) also exceed the 126 MB L2"
+                  % (sm.nnz * 8 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from stminer_b200 import _lib
+    from stminer_b200.Algorithm.distribution import fit_spot_matrix, fit_spot_matrix_host
+    from stminer_b200.Algorithm.distance import gmm_pair_distances
+    from stminer_b200.sharding import allgather_pairs, pair_slice
+    from stminer_b200.staging import DeviceSpotMatrix
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    sm = workload(args.workload, seed=rank, genes=args.genes).pin_memory()
+    G = sm.n_genes
+    dsm = DeviceSpotMatrix(sm, device=dev)
+    order, buckets = dsm.plan(K_COMP)
+    n_launch = int((buckets > 0).sum())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    res = None
+    for _ in range(args.warmup):
+        res = fit_spot_matrix(dsm, K_COMP, init=None, seed=1, out=res)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed: exactly `steps` steps, device-resident inputs -------------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s)                       # evict L2 between timed steps (not timed)
+        ev[s][0].record()
+        res = fit_spot_matrix(dsm, K_COMP, init=None, seed=1, out=res)
+        ev[s][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = max_over_ranks(float(np.sum(step_ms)))
+    ms_per_step = dev_ms / args.steps
+    value = world * G / (ms_per_step / 1e3)
+
+    host = res.to_host()
+    n_iter = host["n_iter"].astype(np.float64)
+    nnz = sm.nnz_per_gene().astype(np.float64)
+    ok = host["status"] == 0
+    flops = FLOP_PER_SPOT_COMP_ITER * float((nnz * n_iter * ok).sum()) * K_COMP
+    em_tflops = flops / (float(np.mean(step_ms)) / 1e3) / 1e12
+
+    # ---- e2e: host buffers in / out through the public API ----------------------------------------
+    for _ in range(2):
+        fit_spot_matrix_host(sm, K_COMP, init=None, device=dev, seed=1)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        out = fit_spot_matrix_host(sm, K_COMP, init=None, device=dev, seed=1)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    h2d = int(dsm.h2d_bytes)
+    d2h = int(sum(v.nbytes for v in out.values()))
+
+    # ---- second half of the metric: SVG-pair distances -------------------------------------------
+    Gp = min(args.pairs_genes, int(ok.sum()))
+    sel = np.flatnonzero(ok)[:Gp]
+    W = torch.from_numpy(host["weights"][sel]).to(dev)
+    MU = torch.from_numpy(host["means"][sel]).to(dev)
+    COV = torch.from_numpy(host["covariances"][sel]).to(dev)
+    total_pairs = Gp * (Gp - 1) // 2
+    pb, pe = pair_slice(total_pairs, rank, world)
+
+    def pairs_step():
+        local = gmm_pair_distances(W, MU, COV, pb, pe, device=dev)
+        return allgather_pairs(local, total_pairs) if world > 1 else local
+    for _ in range(2):
+        pairs_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        full = pairs_step()
+    e1.record()
+    barrier()
+    pairs_ms = max_over_ranks(e0.elapsed_time(e1) / 3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- FP32 FMA peak measured on this GPU (roofline denominator) --------------------------------
+    scratch = torch.zeros(4, dtype=torch.float32, device=dev)
+    blocks, iters = 148 * 8, 20000
+    for _ in range(2):
+        lib.stm_bench_fma(blocks, iters, scratch.data_ptr(), _lib.current_stream_ptr())
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    lib.stm_bench_fma(blocks, iters, scratch.data_ptr(), _lib.current_stream_ptr())
+    f1.record()
+    torch.cuda.synchronize()
+    fma_peak = blocks * 256 * iters * 32 / (f0.elapsed_time(f1) / 1e3) / 1e12
+
+    if rank != 0:
+        return
+    line = {
+        "metric": "genes_per_sec_gmm_fit", "value": value, "unit": "genes/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sm, world),
+        "e2e": {"value": world * G / e2e_s, "unit": "genes/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s},
+        "gpu_launches": args.steps * n_launch,
+        "roofline": {"bound": "fp32_fma", "achieved": em_tflops, "peak": fma_peak, "unit": "TFLOP/s",
+                     "frac": em_tflops / fma_peak, "traffic": None,
+                     "kernel": "gmm_em_kernel (%d nnz-bucket launches per step, run concurrently)" % n_launch,
+                     "peak_source": "measured here with stm_bench_fma (FFMA chains); nominal %.1f TFLOP/s; "
+                                    "MEASURED_PEAKS.json has no FP32 figure" % NOMINAL_FP32_TFLOPS,
+                     "algorithmic_flops_per_step": flops,
+                     "note": "EM sweeps only: 30 FLOP x nnz_g x K x n_iter_g; the k-means++/Lloyd init inside the "
+                             "same launch is not credited",
+                     "hbm_frac": (sm.nnz * 8 + G * K_COMP * 7 * 8) / (float(np.mean(step_ms)) / 1e3) / 1e9 / peak_hbm()},
+        "pairs": {"metric": "svg_pair_gmm_distances_per_sec", "value": total_pairs / (pairs_ms / 1e3),
+                  "unit": "pairs/s", "genes": Gp, "pairs": total_pairs, "ms": pairs_ms,
+                  "sharding": "contiguous pair slices per rank + NCCL all-gather" if world > 1 else "single GPU"},
+        "fit": {"mean_n_iter": float(n_iter[ok].mean()), "genes_ok": int(ok.sum()), "genes_dropped": int((~ok).sum()),
+                "bucket_counts_large_medium_small": buckets.tolist(), "wall_ms_per_step": 1e3 * t_wall / args.steps},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        n_sample = args.cpu_sample or min(512, 6 * max(cores, 8))
+        cpu = CpuReference(cores)
+        rate, wall, mean_fit, n = cpu.rate(sm, n_sample)
+        cpu.close()
+        line["cpu_baseline"] = {"value": rate, "unit": "genes/s", "cores": cores, "kind": "port",
+                                "sample": "%d random genes of the same data set, reference path (array_to_list + "
+                                          "sklearn GaussianMixture.fit, KMeans init included), process-per-gene "
+                                          "pool, 1 BLAS thread each; %.1f s wall, %.2f s mean per fit" % (n, wall, mean_fit)}
+    print(json.dumps(line), flush=True)
+
+
+def peak_hbm():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0   # B200_PROFILING.md fallback
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        import torch
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

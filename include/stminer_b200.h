@@ -61,6 +61,10 @@ const char* stm_last_error_string(void);
  *   spot_x, spot_y [n_spots] int32 integer grid coordinates of each spot (adata.obs['x'], ['y'])
  *   gene_order[G]  int32   optional (NULL = 0..G-1): CTA b fits gene gene_order[b]; pass genes sorted by
  *                          decreasing nnz so long genes start first (LPT)
+ *   bucket_counts_host[3]  HOST int32, optional (NULL = one bucket): how many leading entries of gene_order
+ *                          belong to the large / medium / small nnz bucket, as stm_gmm_fit_plan computes them.
+ *                          Each bucket is launched with a CTA size and shared-memory budget that keeps its
+ *                          genes' spots staged on chip; the buckets of one call run concurrently.
  * Initial parameters (ignored with STM_FIT_DEVICE_INIT; required otherwise), float64, original coordinates:
  *   init_w[G,K], init_mu[G,K,2], init_cov[G,K,2,2]
  * Outputs, float64, same layouts: out_w, out_mu, out_cov; plus per gene
@@ -72,11 +76,21 @@ const char* stm_last_error_string(void);
 int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_idx, const float* val,
                         const int32_t* spot_x, const int32_t* spot_y, int32_t n_spots,
                         int32_t G, int32_t K, const int32_t* gene_order,
+                        const int32_t* bucket_counts_host,
                         const double* init_w, const double* init_mu, const double* init_cov,
                         double reg_covar, double tol, int32_t max_iter, uint32_t flags, uint64_t seed,
                         double* out_w, double* out_mu, double* out_cov,
                         int32_t* out_n_iter, int32_t* out_converged, double* out_lower_bound,
                         int32_t* out_status, void* stream);
+
+/*
+ * Host-side launch plan for stm_gmm_fit_batched (no device work): sorts genes by decreasing nnz (the
+ * reference fits them in list order, distribution.py:184; order only affects scheduling here) and splits
+ * them into the three nnz buckets.  col_ptr_host[G+1], gene_order_host[G] and bucket_counts_host[3] are
+ * HOST arrays; upload gene_order_host and pass both to stm_gmm_fit_batched.
+ */
+int stm_gmm_fit_plan(const int64_t* col_ptr_host, int32_t G, int32_t K,
+                     int32_t* gene_order_host, int32_t* bucket_counts_host);
 
 /*
  * GMM-to-GMM distance: K x K cost C[i][j] = (w1_i + w2_j) * Hellinger(N1_i, N2_j), solved as an exact
@@ -105,6 +119,13 @@ int stm_gmm_dist_fill_square(const double* pairs, int32_t G, double* out_square,
 int stm_gmm_dist_one_vs_all(const double* qw, const double* qmu, const double* qcov,
                             const double* w, const double* mu, const double* cov,
                             int32_t G, int32_t K, double* out, void* stream);
+
+/*
+ * Measurement utility: FP32 FMA-pipe peak micro-benchmark used as the roofline denominator of the EM
+ * kernel (bench.py).  Launches `blocks` CTAs of 256 threads, each thread running `iters` rounds of 16
+ * independent FFMA chains: FLOPs = blocks * 256 * iters * 32.  `out` is a device float (never written).
+ */
+int stm_bench_fma(int32_t blocks, int32_t iters, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -109,16 +109,24 @@ def fit_spot_matrix(dsm: DeviceSpotMatrix, n_comp: int, init=None, max_iter: int
             torch.empty((G,), dtype=torch.int32, device=dev),
             torch.empty((G,), dtype=torch.float64, device=dev),
             torch.empty((G,), dtype=torch.int32, device=dev))
+    order, buckets = dsm.plan(K)
     with torch.cuda.device(dev):
         st = lib.stm_gmm_fit_batched(
             _lib.ptr(dsm.col_ptr), _lib.ptr(dsm.row_idx), _lib.ptr(dsm.val), _lib.ptr(dsm.spot_x), _lib.ptr(dsm.spot_y),
-            dsm.n_spots, G, K, _lib.ptr(dsm.gene_order), _lib.ptr(iw), _lib.ptr(imu), _lib.ptr(icov),
+            dsm.n_spots, G, K, _lib.ptr(order), buckets.ctypes.data, _lib.ptr(iw), _lib.ptr(imu), _lib.ptr(icov),
             float(reg_covar), float(tol), int(max_iter), int(flags), int(seed),
             _lib.ptr(out.weights), _lib.ptr(out.means), _lib.ptr(out.covariances), _lib.ptr(out.n_iter),
             _lib.ptr(out.converged), _lib.ptr(out.lower_bound), _lib.ptr(out.status), _lib.current_stream_ptr())
     _lib.check(st, "stm_gmm_fit_batched")
     out._keepalive = (iw, imu, icov)
     return out
+
+
+def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, **kw) -> dict:
+    """Host buffers in, host buffers out: upload the CSC matrix, fit every gene, read the result back.
+    This is the call ``bench.py`` times end to end."""
+    dsm = DeviceSpotMatrix(sm, device=device)
+    return fit_spot_matrix(dsm, n_comp, init=init, **kw).to_host()
 
 
 def result_to_gmm_dict(genes: Sequence[str], host: dict) -> Dict[str, GMM]:

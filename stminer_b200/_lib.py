@@ -29,14 +29,16 @@ SIGNATURES = {
     "stm_last_error_string": (C.c_char_p, []),
     "stm_gmm_fit_batched": (C.c_int, [
         _P, _P, _P, _P, _P, C.c_int32,                 # col_ptr,row_idx,val,spot_x,spot_y,n_spots
-        C.c_int32, C.c_int32, _P,                      # G,K,gene_order
+        C.c_int32, C.c_int32, _P, _P,                  # G,K,gene_order,bucket_counts_host
         _P, _P, _P,                                    # init_w,init_mu,init_cov
         C.c_double, C.c_double, C.c_int32, C.c_uint32, C.c_uint64,  # reg_covar,tol,max_iter,flags,seed
         _P, _P, _P, _P, _P, _P, _P, _P,                # out_w,out_mu,out_cov,n_iter,converged,lb,status,stream
     ]),
+    "stm_gmm_fit_plan": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     "stm_gmm_dist_pairs": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "stm_gmm_dist_fill_square": (C.c_int, [_P, C.c_int32, _P, _P]),
     "stm_gmm_dist_one_vs_all": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "stm_bench_fma": (C.c_int, [C.c_int32, C.c_int32, _P, _P]),
 }
 
 

@@ -6,7 +6,7 @@
 // distribution.py:369-373 is replaced by integer weights on distinct spots.
 //
 // Kernel shape:
-//   * thread group of GS lanes owns one spot at a time; lane `sub` of the group owns KT components
+//   * a thread group of GS lanes owns one spot at a time; lane `sub` of the group owns KT components
 //     (K <= KT*GS), whose 6 E-step coefficients and 6 M-step accumulators live in registers;
 //   * log2-domain whitened residuals  t = s * U^T (x - mu),  s = sqrt(log2(e)/2):
 //         lp_k = c_k - t0^2 - t1^2          (5 FFMA per spot-component)
@@ -14,18 +14,28 @@
 //     spot that carries responsibility, so FP32 accumulation has no cancellation; the finalize step
 //     maps them back through the (float-rounded, hence exactly consistent) affine map in FP64;
 //   * the lower bound and the cross-warp reduction are accumulated in FP64 so the sklearn stopping
-//     rule fires on the same iteration as the float64 reference.
+//     rule fires on the same iteration as the float64 reference;
+//   * genes are bucketed by nnz on the host (stm_gmm_fit_plan): each bucket gets a CTA size / shared
+//     memory budget that keeps its spots staged on chip; genes beyond the largest budget stream
+//     their spots from L2;
+//   * optional on-device initialisation (weighted greedy k-means++ + Lloyd) replaces the sklearn
+//     KMeans the reference runs inside GaussianMixture (mixture/_base.py:119-128).
 #include <float.h>
+#include <limits.h>
 #include <math.h>
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
 
 #include "stm_common.cuh"
 
 namespace stm {
 namespace {
 
-constexpr int EM_THREADS = 128;
-constexpr int EM_WARPS = EM_THREADS / 32;
 constexpr int EM_CHUNK_PER_GROUP = 2048;  // spots per group between FP64 flushes of the accumulators
+constexpr int KM_MAX_ITER = 300;          // sklearn KMeans default max_iter
+constexpr int KM_LMAX = 6;                // greedy k-means++ candidates: 2 + floor(ln K) <= 6 for K <= 64
 
 struct EmArgs {
   const int64_t* col_ptr;
@@ -45,7 +55,8 @@ struct EmArgs {
   double* out_lb;
   int32_t* out_status;
   int32_t G, K;
-  int32_t smem_spots;  // staging capacity (spots) of this launch
+  int32_t order_begin;  // this launch fits gene_order[order_begin + blockIdx.x]
+  int32_t smem_spots;   // staging capacity (spots) of this launch
   int32_t max_iter;
   uint32_t flags;
   double reg_covar, tol;
@@ -68,6 +79,18 @@ __device__ __forceinline__ int gene_weight(float v, bool remove_low, double mean
   return w;
 }
 
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+// counter-based uniform in [0, 1): hash of (seed, gene, counter)
+__device__ __forceinline__ double u01(uint64_t seed, uint64_t gene, uint64_t ctr) {
+  const uint64_t h = splitmix64(splitmix64(seed ^ (gene * 0xD1342543DE82EF95ULL)) + ctr);
+  return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
 template <int N, int OFF, int NMAX>
 __device__ __forceinline__ void halving_reduce(float (&v)[NMAX], int lane, int& shift) {
   if constexpr (OFF < 32) {
@@ -86,22 +109,24 @@ __device__ __forceinline__ void halving_reduce(float (&v)[NMAX], int lane, int& 
 
 constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-template <int KT, int GS>
+template <int KT, int GS, int T>
 struct EmLayout {
   static constexpr int KP = KT * GS;
   static constexpr int NSTAT = KP * 6;
+  static constexpr int WARPS = T / 32;
   // doubles
-  static constexpr int D_STAT = 0;                // [NSTAT]
-  static constexpr int D_MU = D_STAT + NSTAT;     // [KP*2]
-  static constexpr int D_COV = D_MU + 2 * KP;     // [KP*3]
-  static constexpr int D_W = D_COV + 3 * KP;      // [KP]
-  static constexpr int D_LL = D_W + KP;           // [EM_WARPS]
-  static constexpr int D_MISC = D_LL + EM_WARPS;  // [8]
-  static constexpr int D_END = D_MISC + 8;
+  static constexpr int D_STAT = 0;               // [NSTAT]
+  static constexpr int D_MU = D_STAT + NSTAT;    // [KP*2]
+  static constexpr int D_COV = D_MU + 2 * KP;    // [KP*3]
+  static constexpr int D_W = D_COV + 3 * KP;     // [KP]
+  static constexpr int D_LL = D_W + KP;          // [WARPS]   per-warp partials
+  static constexpr int D_MISC = D_LL + WARPS;    // [8]
+  static constexpr int D_SCR = D_MISC + 8;       // [WARPS * KM_LMAX + 2 * KM_LMAX] k-means++ scratch
+  static constexpr int D_END = round_up(D_SCR + WARPS * KM_LMAX + 2 * KM_LMAX, 2);
   // floats (after doubles)
-  static constexpr int F_PAR = 0;                              // [KP*8]
-  static constexpr int F_RED = F_PAR + KP * 8;                 // [EM_WARPS*NSTAT]
-  static constexpr int F_SPOT = round_up(F_RED + EM_WARPS * NSTAT, 4);  // 3 * cap
+  static constexpr int F_PAR = 0;                                    // [KP*8]
+  static constexpr int F_RED = F_PAR + KP * 8;                       // [WARPS*NSTAT]
+  static constexpr int F_SPOT = round_up(F_RED + WARPS * NSTAT, 4);  // 3 * cap
   static constexpr size_t fixed_bytes() { return (size_t)D_END * 8 + (size_t)F_SPOT * 4 + 64; }
 };
 
@@ -126,7 +151,7 @@ __device__ __forceinline__ bool refresh_component(int k, double* s_d, float* s_p
   // log2( w / (2 pi l00 l11) )
   const float c2 = (float)log2(w / (6.283185307179586476925 * l00 * l11));
   float* q = s_par + 8 * k;
-  q[0] = a00; q[1] = b0; q[2] = a01; q[3] = a11; q[4] = b1; q[5] = c2; q[6] = 0.f; q[7] = 0.f;
+  q[0] = a00; q[1] = b0; q[2] = a01; q[3] = a11; q[4] = b1; q[5] = c2;
   return ok;
 }
 
@@ -150,10 +175,10 @@ struct StreamedSpots {
 };
 
 // One fused E+M sweep over spots [i_begin, i_end) of this CTA.
-template <int KT, int GS, int S, typename Src>
+template <int KT, int GS, int S, int T, typename Src>
 __device__ __forceinline__ void em_sweep(const Src& src, int i_begin, int i_end, int grp, int sub,
                                          const float (&par)[KT][6], float* acc, double& ll) {
-  constexpr int NG = EM_THREADS / GS;
+  constexpr int NG = T / GS;
   // the trip count must be uniform across the warp: the group shuffles below use the full mask
   for (int base = i_begin; base < i_end; base += NG * S) {
     float x[S], y[S], w[S];
@@ -214,13 +239,125 @@ __device__ __forceinline__ void em_sweep(const Src& src, int i_begin, int i_end,
   }
 }
 
-template <int KT, int GS, int S, int MINB>
-__global__ void __launch_bounds__(EM_THREADS, MINB) gmm_em_kernel(const EmArgs p) {
-  using L = EmLayout<KT, GS>;
+// Lloyd assignment sweep: every spot goes to its nearest centre (ties: lowest component index); the
+// owning lane accumulates n, dx, dy (and dxdx, dxdy, dydy when MOMENTS) relative to that centre.
+template <int KT, int GS, int T, bool MOMENTS, typename Src>
+__device__ __forceinline__ void lloyd_sweep(const Src& src, int i_begin, int i_end, int grp, int sub,
+                                            const float (&cx)[KT], const float (&cy)[KT], float* acc) {
+  constexpr int NG = T / GS;
+  for (int base = i_begin; base < i_end; base += NG) {
+    const int i = base + grp;
+    float x = 0.f, y = 0.f, w = 0.f;
+    if (i < i_end) src.get(i, x, y, w);
+    float dx[KT], dy[KT];
+    float best = INFINITY;
+    int jb = 0;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      dx[j] = x - cx[j]; dy[j] = y - cy[j];
+      const float d = fmaf(dx[j], dx[j], dy[j] * dy[j]);
+      if (d < best) { best = d; jb = j; }
+    }
+    int kb = sub * KT + jb;
+#pragma unroll
+    for (int o = 1; o < GS; o <<= 1) {
+      const float ob = __shfl_xor_sync(FULL_MASK, best, o);
+      const int ok = __shfl_xor_sync(FULL_MASK, kb, o);
+      if (ob < best || (ob == best && ok < kb)) { best = ob; kb = ok; }
+    }
+    const bool mine = (kb / KT) == sub;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      const float wj = (mine && jb == j) ? w : 0.f;
+      acc[j * 6 + 0] += wj;
+      acc[j * 6 + 1] = fmaf(wj, dx[j], acc[j * 6 + 1]);
+      acc[j * 6 + 2] = fmaf(wj, dy[j], acc[j * 6 + 2]);
+      if constexpr (MOMENTS) {
+        const float wdx = wj * dx[j];
+        acc[j * 6 + 3] = fmaf(wdx, dx[j], acc[j * 6 + 3]);
+        acc[j * 6 + 4] = fmaf(wdx, dy[j], acc[j * 6 + 4]);
+        acc[j * 6 + 5] = fmaf(wj * dy[j], dy[j], acc[j * 6 + 5]);
+      }
+    }
+  }
+}
+
+// Per-thread accumulators -> warp halving reduction -> cross-warp FP64 sum added into s_d[D_STAT..].
+// Ends with a __syncthreads(); s_d[D_STAT..] is then visible to every thread.
+template <int KT, int GS, int T, int NPAD>
+__device__ __forceinline__ void flush_stats(float (&acc)[NPAD], double* s_d, float* s_red, int tid) {
+  using L = EmLayout<KT, GS, T>;
+  constexpr int NF = NPAD * GS / 32;
+  const int lane = tid & 31, warp = tid >> 5, sub = tid % GS;
+  int shift = 0;
+  halving_reduce<NPAD, GS, NPAD>(acc, lane, shift);
+#pragma unroll
+  for (int i = 0; i < NF; ++i)
+    if (shift + i < KT * 6) s_red[warp * L::NSTAT + sub * KT * 6 + shift + i] = acc[i];
+  __syncthreads();
+  for (int i = tid; i < L::NSTAT; i += T) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < L::WARPS; ++w) t += (double)s_red[w * L::NSTAT + i];
+    s_d[L::D_STAT + i] += t;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int pack_xy(int x, int y) {
+  x = max(-32768, min(32767, x)); y = max(-32768, min(32767, y));
+  return (x & 0xffff) | (y << 16);
+}
+__device__ __forceinline__ float unpack_x(int p) { return (float)(short)(p & 0xffff); }
+__device__ __forceinline__ float unpack_y(int p) { return (float)(p >> 16); }
+
+// Weighted draw of L indices from the seed set: P(i) ~ value(i), thread-major element order.
+// part = this thread's sum of value(i) over its elements i = tid, tid+T, ...
+template <int T, typename ValueFn>
+__device__ __forceinline__ void weighted_pick(double part, int L, const double* u, int ns, ValueFn value,
+                                              double* s_scr, int* s_pick, int tid) {
+  constexpr int WARPS = T / 32;
+  const int lane = tid & 31, warp = tid >> 5;
+  // inclusive scan of the per-thread parts inside each warp
+  double incl = part;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double v = __shfl_up_sync(FULL_MASK, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_scr[warp] = incl;
+  __syncthreads();
+  double warp_off = 0.0, total = 0.0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) { const double v = s_scr[w]; if (w < warp) warp_off += v; total += v; }
+  const double hi = warp_off + incl, lo = hi - part;
+  for (int l = 0; l < L; ++l) {
+    double r = u[l] * total;
+    const bool last_owner = (tid == T - 1) || (tid == ns - 1 && ns < T);
+    if ((r >= lo && r < hi) || (last_owner && r >= hi)) {
+      // walk own elements
+      double res = r - lo;
+      int pick = -1, last_pos = -1;
+      for (int i = tid; i < ns; i += T) {
+        const double v = value(i);
+        if (v > 0.0) { last_pos = i; if (res < v && pick < 0) pick = i; res -= v; }
+      }
+      if (pick < 0) pick = last_pos;  // rounding fell off the end
+      if (pick >= 0) s_pick[l] = pick;
+    }
+  }
+  __syncthreads();
+}
+
+template <int KT, int GS, int S, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
+  using L = EmLayout<KT, GS, T>;
   constexpr int KP = L::KP;
   constexpr int NSTAT = L::NSTAT;
+  constexpr int WARPS = L::WARPS;
   constexpr int NPAD = round_up(KT * 6, 32 / GS);
-  constexpr int NF = NPAD * GS / 32;
+  constexpr int NG = T / GS;
+  constexpr int CHUNK = EM_CHUNK_PER_GROUP * NG;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_d = reinterpret_cast<double*>(smem_raw);
@@ -230,24 +367,28 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) gmm_em_kernel(const EmArgs p
   float* s_x = s_f + L::F_SPOT;
   float* s_y = s_x + p.smem_spots;
   float* s_wt = s_y + p.smem_spots;
-  __shared__ int s_cnt[EM_WARPS];
+  __shared__ int s_cnt[WARPS];
   __shared__ int s_flag[4];
+  __shared__ int s_pick[KM_LMAX];
+  __shared__ int s_ext[4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = tid % GS, grp = tid / GS;
   const int K = p.K;
-  const int g = p.gene_order ? p.gene_order[blockIdx.x] : (int)blockIdx.x;
+  const int slot = p.order_begin + (int)blockIdx.x;
+  const int g = p.gene_order ? p.gene_order[slot] : slot;
   const int64_t p0 = p.col_ptr[g], p1 = p.col_ptr[g + 1];
   const int ncol = (int)(p1 - p0);
   const int32_t* rows = p.row_idx + p0;
   const float* vals = p.val + p0;
   const bool remove_low = (p.flags & STM_FIT_REMOVE_LOW_EXP_SPOTS) != 0;
+  const bool device_init = (p.flags & STM_FIT_DEVICE_INIT) != 0;
 
-  // ---- pre-pass: weights, N, origin -------------------------------------------------------
+  // ---- pre-pass: weights, N, origin, extent -------------------------------------------------
   double mean_nz = 0.0;
   if (remove_low) {
     long long sum = 0, cnt = 0;
-    for (int i = tid; i < ncol; i += EM_THREADS) {
+    for (int i = tid; i < ncol; i += T) {
       const int w = trunc_i16(__ldg(vals + i));
       sum += w; cnt += (w != 0);
     }
@@ -255,31 +396,40 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) gmm_em_kernel(const EmArgs p
     if (lane == 0) { s_d[L::D_LL + warp] = (double)sum; s_d[L::D_STAT + warp] = (double)cnt; }
     __syncthreads();
     double ts = 0, tc = 0;
-    for (int w = 0; w < EM_WARPS; ++w) { ts += s_d[L::D_LL + w]; tc += s_d[L::D_STAT + w]; }
+    for (int w = 0; w < WARPS; ++w) { ts += s_d[L::D_LL + w]; tc += s_d[L::D_STAT + w]; }
     mean_nz = tc > 0 ? ts / tc : 0.0;
     __syncthreads();
   }
+  if (tid < 4) s_ext[tid] = (tid & 1) ? INT_MIN : INT_MAX;  // xmin, xmax, ymin, ymax
+  __syncthreads();
   long long npos = 0, sw = 0, swx = 0, swy = 0;
-  for (int i = tid; i < ncol; i += EM_THREADS) {
+  int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+  for (int i = tid; i < ncol; i += T) {
     const int w = gene_weight(__ldg(vals + i), remove_low, mean_nz);
     if (w > 0) {
       const int r = __ldg(rows + i);
+      const int x = __ldg(p.spot_x + r), y = __ldg(p.spot_y + r);
       npos += 1; sw += w;
-      swx += (long long)w * __ldg(p.spot_x + r);
-      swy += (long long)w * __ldg(p.spot_y + r);
+      swx += (long long)w * x;
+      swy += (long long)w * y;
+      xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
     }
   }
   npos = warp_sum(npos); sw = warp_sum(sw); swx = warp_sum(swx); swy = warp_sum(swy);
+  xmin = __reduce_min_sync(FULL_MASK, xmin); xmax = __reduce_max_sync(FULL_MASK, xmax);
+  ymin = __reduce_min_sync(FULL_MASK, ymin); ymax = __reduce_max_sync(FULL_MASK, ymax);
   if (lane == 0) {
     s_d[L::D_STAT + 4 * warp + 0] = (double)npos; s_d[L::D_STAT + 4 * warp + 1] = (double)sw;
     s_d[L::D_STAT + 4 * warp + 2] = (double)swx;  s_d[L::D_STAT + 4 * warp + 3] = (double)swy;
+    atomicMin(&s_ext[0], xmin); atomicMax(&s_ext[1], xmax); atomicMin(&s_ext[2], ymin); atomicMax(&s_ext[3], ymax);
   }
   __syncthreads();
   double t_npos = 0, t_sw = 0, t_swx = 0, t_swy = 0;
-  for (int w = 0; w < EM_WARPS; ++w) {
+  for (int w = 0; w < WARPS; ++w) {
     t_npos += s_d[L::D_STAT + 4 * w + 0]; t_sw += s_d[L::D_STAT + 4 * w + 1];
     t_swx += s_d[L::D_STAT + 4 * w + 2];  t_swy += s_d[L::D_STAT + 4 * w + 3];
   }
+  xmin = s_ext[0]; xmax = s_ext[1]; ymin = s_ext[2]; ymax = s_ext[3];
   __syncthreads();
   const double N_total = t_sw;
 
@@ -287,22 +437,25 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) gmm_em_kernel(const EmArgs p
   double* o_mu = p.out_mu + (size_t)g * K * 2;
   double* o_cov = p.out_cov + (size_t)g * K * 4;
   if ((int)t_npos < K) {  // distribution.py:125,129-130 -> gene dropped
-    for (int i = tid; i < K; i += EM_THREADS) o_w[i] = 0.0;
-    for (int i = tid; i < 2 * K; i += EM_THREADS) o_mu[i] = 0.0;
-    for (int i = tid; i < 4 * K; i += EM_THREADS) o_cov[i] = 0.0;
+    for (int i = tid; i < K; i += T) o_w[i] = 0.0;
+    for (int i = tid; i < 2 * K; i += T) o_mu[i] = 0.0;
+    for (int i = tid; i < 4 * K; i += T) o_cov[i] = 0.0;
     if (tid == 0) {
       p.out_n_iter[g] = 0; p.out_converged[g] = 0; p.out_lb[g] = 0.0; p.out_status[g] = STM_GENE_DROPPED;
     }
     return;
   }
   const int ox = (int)rint(t_swx / t_sw), oy = (int)rint(t_swy / t_sw);
+  // device-init seeding packs origin-relative coordinates into int16 pairs
+  const bool packable = (xmax - ox) < 32768 && (ox - xmin) < 32768 && (ymax - oy) < 32768 && (oy - ymin) < 32768;
 
   // ---- stage distinct positive spots into shared memory (ordered compaction) ----------------
-  const bool staged = ncol <= p.smem_spots;
+  const bool staged = ncol <= p.smem_spots && (!device_init || packable);
+  const bool stage_packed = staged && device_init;  // seeding layout first: s_x = packed xy, s_y = d2
   int n_spots = ncol;
   if (staged) {
     int n_st = 0;
-    for (int base = 0; base < ncol; base += EM_THREADS) {
+    for (int base = 0; base < ncol; base += T) {
       const int i = base + tid;
       int w = 0, r = 0;
       if (i < ncol) { w = gene_weight(__ldg(vals + i), remove_low, mean_nz); r = __ldg(rows + i); }
@@ -312,11 +465,15 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) gmm_em_kernel(const EmArgs p
       __syncthreads();
       int off = n_st, tot = 0;
 #pragma unroll
-      for (int ww = 0; ww < EM_WARPS; ++ww) { const int c = s_cnt[ww]; if (ww < warp) off += c; tot += c; }
+      for (int ww = 0; ww < WARPS; ++ww) { const int c = s_cnt[ww]; if (ww < warp) off += c; tot += c; }
       if (keep) {
         const int idx = off + __popc(bal & ((1u << lane) - 1u));
-        s_x[idx] = (float)(__ldg(p.spot_x + r) - ox);
-        s_y[idx] = (float)(__ldg(p.spot_y + r) - oy);
+        const int xr = __ldg(p.spot_x + r) - ox, yr = __ldg(p.spot_y + r) - oy;
+        if (stage_packed) {
+          reinterpret_cast<int*>(s_x)[idx] = pack_xy(xr, yr);
+        } else {
+          s_x[idx] = (float)xr; s_y[idx] = (float)yr;
+        }
         s_wt[idx] = (float)w;
       }
       n_st += tot;
@@ -325,39 +482,203 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) gmm_em_kernel(const EmArgs p
     n_spots = n_st;
   }
 
-  // ---- initial parameters -------------------------------------------------------------------
+  const StagedSpots staged_src{s_x, s_y, s_wt};
+  const StreamedSpots stream_src{rows, vals, p.spot_x, p.spot_y, ox, oy, remove_low, mean_nz};
+
   if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; }
-  if (tid < KP) {
-    const int k = tid;
-    if (k < K) {
-      const double* iw = p.init_w + (size_t)g * K;
-      const double* imu = p.init_mu + (size_t)g * K * 2;
-      const double* icov = p.init_cov + (size_t)g * K * 4;
-      s_d[L::D_W + k] = iw[k];
-      s_d[L::D_MU + 2 * k] = imu[2 * k] - ox;
-      s_d[L::D_MU + 2 * k + 1] = imu[2 * k + 1] - oy;
-      s_d[L::D_COV + 3 * k] = icov[4 * k];
-      s_d[L::D_COV + 3 * k + 1] = 0.5 * (icov[4 * k + 1] + icov[4 * k + 2]);
-      s_d[L::D_COV + 3 * k + 2] = icov[4 * k + 3];
-    }
+  // padded components never win a max / an argmin
+  for (int k = K + tid; k < KP; k += T) {
+    float* q = s_par + 8 * k;
+    q[0] = 0.f; q[1] = 0.f; q[2] = 0.f; q[3] = 0.f; q[4] = 0.f; q[5] = -1e30f; q[6] = 1e18f; q[7] = 1e18f;
   }
   __syncthreads();
-  if (tid < KP) {
-    const int k = tid;
-    if (k < K) {
-      if (!refresh_component<L>(k, s_d, s_par)) atomicOr(&s_flag[1], 1);
-    } else {
-      float* q = s_par + 8 * k;
-      q[0] = 0.f; q[1] = 0.f; q[2] = 0.f; q[3] = 0.f; q[4] = 0.f; q[5] = -1e30f; q[6] = 0.f; q[7] = 0.f;
+
+  if (device_init) {
+    // =========================================================================================
+    // Weighted greedy k-means++ seeding on the staged spots (or a strided subsample of a streamed
+    // gene), then Lloyd on all spots, then one-hot responsibilities -> (w, mu, cov) as sklearn's
+    // GaussianMixture._initialize (_gaussian_mixture.py:849-881).
+    // =========================================================================================
+    int* s_pk = reinterpret_cast<int*>(s_x);
+    float* s_d2 = s_y;
+    int ns = n_spots;
+    if (!staged) {
+      const int stride = (ncol + p.smem_spots - 1) / p.smem_spots;
+      ns = (ncol + stride - 1) / stride;
+      for (int j = tid; j < ns; j += T) {
+        const int i = j * stride;
+        const int r = __ldg(rows + i);
+        const int w = gene_weight(__ldg(vals + i), remove_low, mean_nz);
+        s_pk[j] = pack_xy(__ldg(p.spot_x + r) - ox, __ldg(p.spot_y + r) - oy);
+        s_wt[j] = w > 0 ? (float)w : 0.f;
+      }
+      __syncthreads();
     }
+    const int Lc = min(KM_LMAX, 2 + (int)floor(log((double)K)));
+    double* s_scr = s_d + L::D_SCR;
+    double* s_pot = s_scr + WARPS * KM_LMAX;  // [KM_LMAX] reduced candidate potentials
+    // first centre ~ w
+    {
+      double part = 0.0;
+      for (int i = tid; i < ns; i += T) part += (double)s_wt[i];
+      double u[1] = {u01(p.seed, (uint64_t)g, 0)};
+      weighted_pick<T>(part, 1, u, ns, [&](int i) { return (double)s_wt[i]; }, s_scr, s_pick, tid);
+    }
+    float ccx = unpack_x(s_pk[s_pick[0]]), ccy = unpack_y(s_pk[s_pick[0]]);
+    if (tid == 0) { s_par[6] = ccx; s_par[7] = ccy; }
+    double part = 0.0;
+    for (int i = tid; i < ns; i += T) {
+      const float dx = unpack_x(s_pk[i]) - ccx, dy = unpack_y(s_pk[i]) - ccy;
+      const float d = fmaf(dx, dx, dy * dy);
+      s_d2[i] = d;
+      part += (double)(s_wt[i] * d);
+    }
+    for (int c = 1; c < K; ++c) {
+      double u[KM_LMAX];
+      for (int l = 0; l < Lc; ++l) u[l] = u01(p.seed, (uint64_t)g, (uint64_t)c * 8 + l);
+      weighted_pick<T>(part, Lc, u, ns, [&](int i) { return (double)(s_wt[i] * s_d2[i]); }, s_scr, s_pick, tid);
+      float candx[KM_LMAX], candy[KM_LMAX], pot[KM_LMAX];
+#pragma unroll
+      for (int l = 0; l < KM_LMAX; ++l) {
+        const int pi = s_pick[l < Lc ? l : 0];
+        candx[l] = unpack_x(s_pk[pi]); candy[l] = unpack_y(s_pk[pi]); pot[l] = 0.f;
+      }
+      for (int i = tid; i < ns; i += T) {
+        const float x = unpack_x(s_pk[i]), y = unpack_y(s_pk[i]), w = s_wt[i], d0 = s_d2[i];
+#pragma unroll
+        for (int l = 0; l < KM_LMAX; ++l) {
+          const float dx = x - candx[l], dy = y - candy[l];
+          pot[l] = fmaf(w, fminf(d0, fmaf(dx, dx, dy * dy)), pot[l]);
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < KM_LMAX; ++l) {
+        const double v = warp_sum((double)pot[l]);
+        if (lane == 0) s_scr[warp * KM_LMAX + l] = v;
+      }
+      __syncthreads();
+      if (tid < KM_LMAX) {
+        double t = 0.0;
+        for (int w = 0; w < WARPS; ++w) t += s_scr[w * KM_LMAX + tid];
+        s_pot[tid] = t;
+      }
+      __syncthreads();
+      int bl = 0;
+      for (int l = 1; l < Lc; ++l) if (s_pot[l] < s_pot[bl]) bl = l;
+      ccx = unpack_x(s_pk[s_pick[bl]]); ccy = unpack_y(s_pk[s_pick[bl]]);
+      if (tid == 0) { s_par[8 * c + 6] = ccx; s_par[8 * c + 7] = ccy; }
+      part = 0.0;
+      for (int i = tid; i < ns; i += T) {
+        const float dx = unpack_x(s_pk[i]) - ccx, dy = unpack_y(s_pk[i]) - ccy;
+        const float d = fminf(s_d2[i], fmaf(dx, dx, dy * dy));
+        s_d2[i] = d;
+        part += (double)(s_wt[i] * d);
+      }
+      __syncthreads();  // s_pick / s_pot are rewritten by the next round
+    }
+    // seeding layout -> float staging layout
+    if (staged) {
+      for (int i = tid; i < n_spots; i += T) {
+        const int pk = s_pk[i];
+        s_x[i] = unpack_x(pk); s_y[i] = unpack_y(pk);
+      }
+    }
+    if (tid < K) { s_d[L::D_MU + 2 * tid] = (double)s_par[8 * tid + 6]; s_d[L::D_MU + 2 * tid + 1] = (double)s_par[8 * tid + 7]; }
+    __syncthreads();
+
+    // tolerance of sklearn KMeans: tol * mean(var(X, axis=0)) with tol = 1e-4 (cluster/_kmeans.py _tolerance)
+    double vx = 0.0, vy = 0.0;
+    {
+      const double mxo = t_swx / t_sw - ox, myo = t_swy / t_sw - oy;
+      for (int i = tid; i < n_spots; i += T) {
+        float x, y, w;
+        if (staged) staged_src.get(i, x, y, w); else stream_src.get(i, x, y, w);
+        const double dx = x - mxo, dy = y - myo;
+        vx += w * dx * dx; vy += w * dy * dy;
+      }
+      vx = warp_sum(vx); vy = warp_sum(vy);
+      if (lane == 0) { s_scr[2 * warp] = vx; s_scr[2 * warp + 1] = vy; }
+      __syncthreads();
+      vx = 0.0; vy = 0.0;
+      for (int w = 0; w < WARPS; ++w) { vx += s_scr[2 * w]; vy += s_scr[2 * w + 1]; }
+      __syncthreads();
+    }
+    const double km_tol = 1e-4 * 0.5 * (vx + vy) / N_total;
+
+    for (int it = 0; it <= KM_MAX_ITER; ++it) {
+      const bool final_pass = s_flag[0] != 0 || it == KM_MAX_ITER;
+      float cx[KT], cy[KT];
+#pragma unroll
+      for (int j = 0; j < KT; ++j) { cx[j] = s_par[8 * (sub * KT + j) + 6]; cy[j] = s_par[8 * (sub * KT + j) + 7]; }
+      for (int i = tid; i < NSTAT; i += T) s_d[L::D_STAT + i] = 0.0;
+      if (tid == 0) s_d[L::D_MISC + 2] = 0.0;
+      __syncthreads();
+      for (int c0 = 0; c0 < n_spots; c0 += CHUNK) {
+        const int c1 = min(n_spots, c0 + CHUNK);
+        float acc[NPAD];
+#pragma unroll
+        for (int i = 0; i < NPAD; ++i) acc[i] = 0.f;
+        if (final_pass) {
+          if (staged) lloyd_sweep<KT, GS, T, true>(staged_src, c0, c1, grp, sub, cx, cy, acc);
+          else        lloyd_sweep<KT, GS, T, true>(stream_src, c0, c1, grp, sub, cx, cy, acc);
+        } else {
+          if (staged) lloyd_sweep<KT, GS, T, false>(staged_src, c0, c1, grp, sub, cx, cy, acc);
+          else        lloyd_sweep<KT, GS, T, false>(stream_src, c0, c1, grp, sub, cx, cy, acc);
+        }
+        flush_stats<KT, GS, T, NPAD>(acc, s_d, s_red, tid);
+      }
+      if (final_pass) {
+        if (tid < K) {
+          const int k = tid;
+          const double* st = s_d + L::D_STAT + 6 * k;
+          const double n = st[0] + 10.0 * DBL_EPSILON;  // _gaussian_mixture.py:312
+          const double ddx = st[1] / n, ddy = st[2] / n;
+          s_d[L::D_MU + 2 * k] += ddx;
+          s_d[L::D_MU + 2 * k + 1] += ddy;
+          s_d[L::D_COV + 3 * k] = st[3] / n - ddx * ddx + p.reg_covar;
+          s_d[L::D_COV + 3 * k + 1] = st[4] / n - ddx * ddy;
+          s_d[L::D_COV + 3 * k + 2] = st[5] / n - ddy * ddy + p.reg_covar;
+          s_d[L::D_W + k] = n / N_total;                // weights /= n_samples, _gaussian_mixture.py:866
+        }
+        __syncthreads();
+        break;
+      }
+      if (tid < K) {
+        const int k = tid;
+        const double* st = s_d + L::D_STAT + 6 * k;
+        if (st[0] > 0.0) {
+          const double ddx = st[1] / st[0], ddy = st[2] / st[0];
+          s_d[L::D_MU + 2 * k] += ddx;
+          s_d[L::D_MU + 2 * k + 1] += ddy;
+          s_par[8 * k + 6] = (float)s_d[L::D_MU + 2 * k];
+          s_par[8 * k + 7] = (float)s_d[L::D_MU + 2 * k + 1];
+          atomicAdd(&s_d[L::D_MISC + 2], ddx * ddx + ddy * ddy);
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && s_d[L::D_MISC + 2] <= km_tol) s_flag[0] = 1;
+      __syncthreads();
+    }
+    if (tid == 0) s_flag[0] = 0;
+  } else if (tid < K) {
+    const int k = tid;
+    const double* iw = p.init_w + (size_t)g * K;
+    const double* imu = p.init_mu + (size_t)g * K * 2;
+    const double* icov = p.init_cov + (size_t)g * K * 4;
+    s_d[L::D_W + k] = iw[k];
+    s_d[L::D_MU + 2 * k] = imu[2 * k] - ox;
+    s_d[L::D_MU + 2 * k + 1] = imu[2 * k + 1] - oy;
+    s_d[L::D_COV + 3 * k] = icov[4 * k];
+    s_d[L::D_COV + 3 * k + 1] = 0.5 * (icov[4 * k + 1] + icov[4 * k + 2]);
+    s_d[L::D_COV + 3 * k + 2] = icov[4 * k + 3];
+  }
+  __syncthreads();
+  if (tid < K) {
+    if (!refresh_component<L>(tid, s_d, s_par)) atomicOr(&s_flag[1], 1);
   }
   __syncthreads();
 
   // ---- EM loop (sklearn mixture/_base.py:265-278) ---------------------------------------------
-  const StagedSpots staged_src{s_x, s_y, s_wt};
-  const StreamedSpots stream_src{rows, vals, p.spot_x, p.spot_y, ox, oy, remove_low, mean_nz};
-  constexpr int NG = EM_THREADS / GS;
-  constexpr int CHUNK = EM_CHUNK_PER_GROUP * NG;
   double lb_prev = -INFINITY, lb = 0.0;
   int n_iter = 0, converged = 0;
   bool failed = s_flag[1] != 0;
@@ -371,28 +692,17 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) gmm_em_kernel(const EmArgs p
       const float2 q1 = *reinterpret_cast<const float2*>(s_par + 8 * (sub * KT + j) + 4);
       par[j][0] = q0.x; par[j][1] = q0.y; par[j][2] = q0.z; par[j][3] = q0.w; par[j][4] = q1.x; par[j][5] = q1.y;
     }
-    for (int i = tid; i < NSTAT; i += EM_THREADS) s_d[L::D_STAT + i] = 0.0;
+    for (int i = tid; i < NSTAT; i += T) s_d[L::D_STAT + i] = 0.0;
+    __syncthreads();
     double ll = 0.0;
     for (int c0 = 0; c0 < n_spots; c0 += CHUNK) {
       const int c1 = min(n_spots, c0 + CHUNK);
       float acc[NPAD];
 #pragma unroll
       for (int i = 0; i < NPAD; ++i) acc[i] = 0.f;
-      if (staged) em_sweep<KT, GS, S>(staged_src, c0, c1, grp, sub, par, acc, ll);
-      else        em_sweep<KT, GS, S>(stream_src, c0, c1, grp, sub, par, acc, ll);
-      int shift = 0;
-      halving_reduce<NPAD, GS, NPAD>(acc, lane, shift);
-#pragma unroll
-      for (int i = 0; i < NF; ++i)
-        if (shift + i < KT * 6) s_red[warp * NSTAT + sub * KT * 6 + shift + i] = acc[i];
-      __syncthreads();
-      for (int i = tid; i < NSTAT; i += EM_THREADS) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < EM_WARPS; ++w) t += (double)s_red[w * NSTAT + i];
-        s_d[L::D_STAT + i] += t;
-      }
-      __syncthreads();
+      if (staged) em_sweep<KT, GS, S, T>(staged_src, c0, c1, grp, sub, par, acc, ll);
+      else        em_sweep<KT, GS, S, T>(stream_src, c0, c1, grp, sub, par, acc, ll);
+      flush_stats<KT, GS, T, NPAD>(acc, s_d, s_red, tid);
     }
     ll = warp_sum(ll);
     if (lane == 0) s_d[L::D_LL + warp] = ll;
@@ -422,9 +732,9 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) gmm_em_kernel(const EmArgs p
       s_d[L::D_W + k] = n / tot;
       if (!refresh_component<L>(k, s_d, s_par)) atomicOr(&s_flag[1], 1);
     }
-    if (tid == 0) {
+    if (tid == T - 1) {
       double t = 0.0;
-      for (int w = 0; w < EM_WARPS; ++w) t += s_d[L::D_LL + w];
+      for (int w = 0; w < WARPS; ++w) t += s_d[L::D_LL + w];
       // log2 domain -> natural log; mean over the N replicated rows (_base.py:332)
       s_d[L::D_MISC + 1] = t * 0.69314718055994530942 / N_total;
     }
@@ -438,9 +748,9 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) gmm_em_kernel(const EmArgs p
 
   // ---- outputs --------------------------------------------------------------------------------
   if (failed) {
-    for (int i = tid; i < K; i += EM_THREADS) o_w[i] = 0.0;
-    for (int i = tid; i < 2 * K; i += EM_THREADS) o_mu[i] = 0.0;
-    for (int i = tid; i < 4 * K; i += EM_THREADS) o_cov[i] = 0.0;
+    for (int i = tid; i < K; i += T) o_w[i] = 0.0;
+    for (int i = tid; i < 2 * K; i += T) o_mu[i] = 0.0;
+    for (int i = tid; i < 4 * K; i += T) o_cov[i] = 0.0;
   } else if (tid < K) {
     const int k = tid;
     o_w[k] = s_d[L::D_W + k];
@@ -459,36 +769,132 @@ __global__ void __launch_bounds__(EM_THREADS, MINB) gmm_em_kernel(const EmArgs p
   }
 }
 
-template <int KT, int GS, int S, int MINB>
-int launch_em(const EmArgs& a_in, cudaStream_t stream) {
-  using L = EmLayout<KT, GS>;
-  EmArgs a = a_in;
-  auto kern = gmm_em_kernel<KT, GS, S, MINB>;
+// ------------------------------------------------------------------------------------------------
+// Launch configurations.  Bucket b of a component class uses CTA size T_b with MINB_b CTAs per SM;
+// its staging capacity follows from the 228 KB of shared memory an SM has.
+// ------------------------------------------------------------------------------------------------
+constexpr int N_BUCKETS = 3;  // 0: largest genes ... 2: smallest
+
+template <int KT, int GS, int T>
+constexpr size_t em_fixed_bytes() { return EmLayout<KT, GS, T>::fixed_bytes(); }
+
+inline int32_t cap_for(size_t fixed, int minb, int max_optin) {
+  size_t per_cta = ((size_t)228 * 1024) / minb - 1024 - 64;
+  if (per_cta > (size_t)max_optin) per_cta = max_optin;
+  if (per_cta < fixed + 12 * 64) return 0;
+  return (int32_t)(((per_cta - fixed) / 12) & ~(size_t)3);
+}
+
+struct ClassCfg { int T[N_BUCKETS]; int minb[N_BUCKETS]; size_t fixed[N_BUCKETS]; };
+
+inline ClassCfg class_cfg(int K) {
+  ClassCfg c{};
+  if (K <= 40) {
+    c.T[0] = 512; c.T[1] = 256; c.T[2] = 128;
+    c.minb[0] = 1; c.minb[1] = 2; c.minb[2] = 4;
+    if (K <= 5) { c.fixed[0] = em_fixed_bytes<5, 1, 512>(); c.fixed[1] = em_fixed_bytes<5, 1, 256>(); c.fixed[2] = em_fixed_bytes<5, 1, 128>(); }
+    else if (K <= 10) { c.fixed[0] = em_fixed_bytes<5, 2, 512>(); c.fixed[1] = em_fixed_bytes<5, 2, 256>(); c.fixed[2] = em_fixed_bytes<5, 2, 128>(); }
+    else if (K <= 20) { c.fixed[0] = em_fixed_bytes<5, 4, 512>(); c.fixed[1] = em_fixed_bytes<5, 4, 256>(); c.fixed[2] = em_fixed_bytes<5, 4, 128>(); }
+    else { c.fixed[0] = em_fixed_bytes<5, 8, 512>(); c.fixed[1] = em_fixed_bytes<5, 8, 256>(); c.fixed[2] = em_fixed_bytes<5, 8, 128>(); }
+  } else {
+    for (int b = 0; b < N_BUCKETS; ++b) { c.T[b] = 128; c.minb[b] = 3; c.fixed[b] = em_fixed_bytes<8, 8, 128>(); }
+  }
+  return c;
+}
+
+constexpr int DEFAULT_MAX_OPTIN = 232448;  // sm_100: 227 KB per CTA
+
+template <int KT, int GS, int S, int T, int MINB>
+int launch_em(EmArgs a, int n_genes, cudaStream_t stream) {
+  using L = EmLayout<KT, GS, T>;
+  auto kern = gmm_em_kernel<KT, GS, S, T, MINB>;
   int dev = 0, max_optin = 0;
   STM_CHECK_CUDA(cudaGetDevice(&dev));
   STM_CHECK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  // MINB CTAs per SM share 227 KB (+1 KB reserved per CTA)
-  size_t per_cta = ((size_t)228 * 1024) / MINB - 1024 - 64;
-  if (per_cta > (size_t)max_optin) per_cta = max_optin;
   const size_t fixed = L::fixed_bytes();
-  if (per_cta < fixed + 12 * 256) {
+  a.smem_spots = cap_for(fixed, MINB, max_optin);
+  if (a.smem_spots <= 0) {
     set_last_error("stm_gmm_fit_batched: shared-memory budget too small");
     return STM_ERR_UNSUPPORTED;
   }
-  a.smem_spots = (int32_t)((per_cta - fixed) / 12) & ~3;
   const size_t smem = fixed + (size_t)a.smem_spots * 12;
   STM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<a.G, EM_THREADS, smem, stream>>>(a);
+  kern<<<n_genes, T, smem, stream>>>(a);
   STM_CHECK_CUDA(cudaGetLastError());
+  return STM_OK;
+}
+
+template <int KT, int GS>
+int launch_bucket(const EmArgs& a, int bucket, int n_genes, cudaStream_t st) {
+  if (bucket == 0) return launch_em<KT, GS, 2, 512, 1>(a, n_genes, st);
+  if (bucket == 1) return launch_em<KT, GS, 2, 256, 2>(a, n_genes, st);
+  return launch_em<KT, GS, 2, 128, 4>(a, n_genes, st);
+}
+
+int launch_class(const EmArgs& a, int bucket, int n_genes, cudaStream_t st) {
+  const int K = a.K;
+  if (K <= 5) return launch_bucket<5, 1>(a, bucket, n_genes, st);
+  if (K <= 10) return launch_bucket<5, 2>(a, bucket, n_genes, st);
+  if (K <= 20) return launch_bucket<5, 4>(a, bucket, n_genes, st);
+  if (K <= 40) return launch_bucket<5, 8>(a, bucket, n_genes, st);
+  return launch_em<8, 8, 1, 128, 3>(a, n_genes, st);
+}
+
+// auxiliary streams so the buckets of one call overlap (fork/join on the caller's stream)
+struct AuxStreams {
+  cudaStream_t s[N_BUCKETS - 1] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[N_BUCKETS - 1] = {nullptr, nullptr};
+  int dev = -1;
+};
+thread_local AuxStreams g_aux[16];
+
+int get_aux(AuxStreams** out) {
+  int dev = 0;
+  STM_CHECK_CUDA(cudaGetDevice(&dev));
+  AuxStreams& a = g_aux[dev & 15];
+  if (a.dev != dev) {
+    for (int i = 0; i < N_BUCKETS - 1; ++i) {
+      STM_CHECK_CUDA(cudaStreamCreateWithFlags(&a.s[i], cudaStreamNonBlocking));
+      STM_CHECK_CUDA(cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming));
+    }
+    STM_CHECK_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+    a.dev = dev;
+  }
+  *out = &a;
   return STM_OK;
 }
 
 }  // namespace
 }  // namespace stm
 
+extern "C" int stm_gmm_fit_plan(const int64_t* col_ptr_host, int32_t G, int32_t K,
+                                int32_t* gene_order_host, int32_t* bucket_counts_host) {
+  using namespace stm;
+  STM_CHECK_ARG(G >= 0, "G < 0");
+  STM_CHECK_ARG(K >= 1 && K <= 64, "K must be in [1, 64]");
+  STM_CHECK_ARG(gene_order_host && bucket_counts_host && (col_ptr_host || G == 0), "null pointer");
+  std::vector<int32_t> order(G);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+    return (col_ptr_host[a + 1] - col_ptr_host[a]) > (col_ptr_host[b + 1] - col_ptr_host[b]);
+  });
+  const ClassCfg cfg = class_cfg(K);
+  const int32_t cap1 = cap_for(cfg.fixed[1], cfg.minb[1], DEFAULT_MAX_OPTIN);
+  const int32_t cap2 = cap_for(cfg.fixed[2], cfg.minb[2], DEFAULT_MAX_OPTIN);
+  int32_t n0 = 0, n1 = 0, n2 = 0;
+  for (int32_t i = 0; i < G; ++i) {
+    const int64_t n = col_ptr_host[order[i] + 1] - col_ptr_host[order[i]];
+    if (n <= cap2) ++n2; else if (n <= cap1) ++n1; else ++n0;
+    gene_order_host[i] = order[i];
+  }
+  bucket_counts_host[0] = n0; bucket_counts_host[1] = n1; bucket_counts_host[2] = n2;
+  return STM_OK;
+}
+
 extern "C" int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_idx, const float* val,
                                    const int32_t* spot_x, const int32_t* spot_y, int32_t n_spots,
                                    int32_t G, int32_t K, const int32_t* gene_order,
+                                   const int32_t* bucket_counts_host,
                                    const double* init_w, const double* init_mu, const double* init_cov,
                                    double reg_covar, double tol, int32_t max_iter, uint32_t flags, uint64_t seed,
                                    double* out_w, double* out_mu, double* out_cov,
@@ -503,11 +909,15 @@ extern "C" int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_id
   STM_CHECK_ARG(max_iter >= 1, "max_iter < 1");
   STM_CHECK_ARG(out_w && out_mu && out_cov && out_n_iter && out_converged && out_lower_bound && out_status,
                 "null output pointer");
-  if (flags & STM_FIT_DEVICE_INIT) {
-    set_last_error("stm_gmm_fit_batched: STM_FIT_DEVICE_INIT not available in this build");
-    return STM_ERR_UNSUPPORTED;
+  STM_CHECK_ARG((flags & STM_FIT_DEVICE_INIT) || (init_w && init_mu && init_cov),
+                "init_* required without STM_FIT_DEVICE_INIT");
+  int32_t counts[N_BUCKETS] = {0, 0, G};
+  if (bucket_counts_host) {
+    STM_CHECK_ARG(gene_order != nullptr, "bucket_counts_host needs gene_order");
+    int64_t s = 0;
+    for (int b = 0; b < N_BUCKETS; ++b) { counts[b] = bucket_counts_host[b]; STM_CHECK_ARG(counts[b] >= 0, "negative bucket"); s += counts[b]; }
+    STM_CHECK_ARG(s == G, "bucket counts do not sum to G");
   }
-  STM_CHECK_ARG(init_w && init_mu && init_cov, "init_* required without STM_FIT_DEVICE_INIT");
   EmArgs a{};
   a.col_ptr = col_ptr; a.row_idx = row_idx; a.val = val; a.spot_x = spot_x; a.spot_y = spot_y;
   a.gene_order = gene_order; a.init_w = init_w; a.init_mu = init_mu; a.init_cov = init_cov;
@@ -515,10 +925,34 @@ extern "C" int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_id
   a.out_converged = out_converged; a.out_lb = out_lower_bound; a.out_status = out_status;
   a.G = G; a.K = K; a.max_iter = max_iter; a.flags = flags; a.reg_covar = reg_covar; a.tol = tol; a.seed = seed;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (K <= 5) return launch_em<5, 1, 2, 4>(a, st);
-  if (K <= 10) return launch_em<5, 2, 2, 4>(a, st);
-  if (K <= 20) return launch_em<5, 4, 2, 4>(a, st);
-  if (K <= 32) return launch_em<8, 4, 1, 3>(a, st);
-  if (K <= 40) return launch_em<5, 8, 2, 4>(a, st);
-  return launch_em<8, 8, 1, 3>(a, st);
+  int n_active = 0;
+  for (int b = 0; b < N_BUCKETS; ++b) n_active += counts[b] > 0;
+  AuxStreams* aux = nullptr;
+  if (n_active > 1) {
+    int rc = get_aux(&aux);
+    if (rc != STM_OK) return rc;
+    STM_CHECK_CUDA(cudaEventRecord(aux->fork, st));
+  }
+  int begin = 0, used_aux = 0;
+  bool first = true;
+  for (int b = 0; b < N_BUCKETS; ++b) {
+    if (counts[b] == 0) continue;
+    a.order_begin = begin;
+    cudaStream_t s = st;
+    int my_aux = -1;
+    if (!first) {
+      my_aux = used_aux++;
+      s = aux->s[my_aux];
+      STM_CHECK_CUDA(cudaStreamWaitEvent(s, aux->fork, 0));
+    }
+    const int rc = launch_class(a, b, counts[b], s);
+    if (rc != STM_OK) return rc;
+    if (my_aux >= 0) {
+      STM_CHECK_CUDA(cudaEventRecord(aux->join[my_aux], s));
+      STM_CHECK_CUDA(cudaStreamWaitEvent(st, aux->join[my_aux], 0));
+    }
+    first = false;
+    begin += counts[b];
+  }
+  return STM_OK;
 }

@@ -64,6 +64,15 @@ class SpotMatrix:
         order = np.lexsort((xy[:, 1], xy[:, 0]))
         return xy[order], w[order]
 
+    def pin_memory(self) -> "SpotMatrix":
+        """Copy whose arrays live in page-locked host memory, so uploads are true async DMA."""
+        import torch
+        pins = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+                for a in (self.col_ptr, self.row_idx, self.val, self.spot_x, self.spot_y)]
+        out = SpotMatrix(*[t.numpy() for t in pins], list(self.genes))
+        out._pins = pins
+        return out
+
     def select(self, idx: Sequence[int]) -> "SpotMatrix":
         idx = np.asarray(idx, dtype=np.int64)
         lens = np.diff(self.col_ptr)[idx]
@@ -109,25 +118,40 @@ class SpotMatrix:
 class DeviceSpotMatrix:
     """SpotMatrix resident in HBM (torch tensors are only the buffer owners)."""
 
-    def __init__(self, sm: SpotMatrix, device=None, order: Optional[np.ndarray] = None, non_blocking: bool = True):
+    def __init__(self, sm: SpotMatrix, device=None, non_blocking: bool = True):
         import torch
         from . import _lib
         _lib.require_cuda()
         self.host = sm
         self.device = torch.device(device if device is not None else "cuda")
-        order = sm.lpt_order() if order is None else np.asarray(order, dtype=np.int32)
+        self._plans = {}
 
         def up(a):
-            t = torch.from_numpy(np.ascontiguousarray(a))
-            return t.pin_memory().to(self.device, non_blocking=non_blocking) if non_blocking else t.to(self.device)
+            # async DMA when the host array is page-locked (SpotMatrix.pin_memory), staged copy otherwise
+            return torch.from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=non_blocking)
 
         self.col_ptr = up(sm.col_ptr)
         self.row_idx = up(sm.row_idx)
         self.val = up(sm.val)
         self.spot_x = up(sm.spot_x)
         self.spot_y = up(sm.spot_y)
-        self.gene_order = up(order)
-        self.h2d_bytes = sum(a.nbytes for a in (sm.col_ptr, sm.row_idx, sm.val, sm.spot_x, sm.spot_y, order))
+        self._up = up
+        self.h2d_bytes = sum(a.nbytes for a in (sm.col_ptr, sm.row_idx, sm.val, sm.spot_x, sm.spot_y))
+
+    def plan(self, K: int):
+        """(gene_order CUDA tensor, bucket_counts host int32[3]) from ``stm_gmm_fit_plan`` for K components."""
+        from . import _lib
+        if K not in self._plans:
+            lib = _lib.load()
+            G = self.host.n_genes
+            col = np.ascontiguousarray(self.host.col_ptr, dtype=np.int64)
+            order = np.empty(max(G, 1), dtype=np.int32)
+            buckets = np.zeros(3, dtype=np.int32)
+            _lib.check(lib.stm_gmm_fit_plan(col.ctypes.data, G, int(K), order.ctypes.data, buckets.ctypes.data),
+                       "stm_gmm_fit_plan")
+            self._plans[K] = (self._up(order[:G]), buckets)
+            self.h2d_bytes += order[:G].nbytes
+        return self._plans[K]
 
     @property
     def n_genes(self) -> int:

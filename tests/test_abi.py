@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library loads, exports every symbol include/*.h declares, and its host-side entry
+points (version, argument validation, launch plan) behave — no compute calls, no GPU."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+
+from stminer_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(stm_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    decl = declared_symbols()
+    assert {"stm_gmm_fit_batched", "stm_gmm_dist_pairs", "stm_version"} <= decl
+    for name in decl:
+        assert hasattr(lib, name), name
+    assert decl == set(_lib.SIGNATURES), "ctypes signature table and header disagree"
+
+
+def test_version_and_error_string():
+    lib = _lib.load()
+    assert lib.stm_version() >= 100
+    st = lib.stm_gmm_dist_pairs(None, None, None, 4, 0, 0, 1, None, None)   # K = 0
+    assert st == -1
+    assert b"K" in lib.stm_last_error_string()
+    st = lib.stm_gmm_dist_pairs(None, None, None, 4, 3, 0, 100, None, None)  # range outside triangle
+    assert st == -1
+    # G == 0 is a no-op, not an error
+    assert lib.stm_gmm_fit_batched(*([None] * 5), 0, 0, 5, None, None, None, None, None, 1e-3, 1e-3, 100, 0, 0,
+                                   *([None] * 8)) == 0
+    st = lib.stm_gmm_fit_batched(*([None] * 5), 10, 3, 5, None, None, None, None, None, 1e-3, 1e-3, 100, 0, 0,
+                                 *([None] * 8))
+    assert st == -1 and b"null" in lib.stm_last_error_string()
+
+
+def test_fit_plan_orders_by_nnz_and_buckets():
+    lib = _lib.load()
+    nnz = np.array([10, 30000, 500, 6000, 4000, 0, 12000, 100000], dtype=np.int64)
+    col = np.concatenate([[0], np.cumsum(nnz)]).astype(np.int64)
+    order = np.empty(len(nnz), dtype=np.int32)
+    buckets = np.zeros(3, dtype=np.int32)
+    assert lib.stm_gmm_fit_plan(col.ctypes.data, len(nnz), 20, order.ctypes.data, buckets.ctypes.data) == 0
+    assert (np.diff(nnz[order]) <= 0).all()
+    assert sorted(order.tolist()) == list(range(len(nnz)))
+    assert buckets.sum() == len(nnz)
+    # small bucket holds genes that fit 4 CTAs/SM staging (~4.3k spots), medium ~9k
+    small = nnz[order[buckets[0] + buckets[1]:]]
+    medium = nnz[order[buckets[0]:buckets[0] + buckets[1]]]
+    assert small.max() < 4500 and (medium > small.max()).all() and medium.max() < 9500
+    assert set(nnz[order[:buckets[0]]].tolist()) == {30000, 12000, 100000}

@@ -38,3 +38,150 @@ def test_em_parity_fixed_init(cuda_device, config, K, nt, rep):
         n_checked += 1
     assert n_checked >= 0.9 * ok.sum()
     assert n_iter_mismatch <= max(1, 0.05 * ok.sum())
+
+
+def test_em_matches_sklearn_golden(cuda_device):
+    """Committed golden vectors: the real sklearn GaussianMixture on the replicated list (make_golden.py)."""
+    import os
+    from stminer_b200.staging import SpotMatrix
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "gmm_fixed_init.npz"))
+    for i in range(int(z["n"])):
+        p = "g%d_" % i
+        xy, c = z[p + "xy"], z[p + "counts"]
+        K = len(z[p + "w0"])
+        # one gene as a 1-column CSC matrix whose spots are its own distinct coordinates
+        sm = SpotMatrix(np.array([0, len(c)], dtype=np.int64), np.arange(len(c), dtype=np.int32),
+                        c.astype(np.float32), xy[:, 0].astype(np.int32), xy[:, 1].astype(np.int32), ["g"])
+        res = _fit(sm, K, (z[p + "w0"][None], z[p + "mu0"][None], z[p + "cov0"][None]))
+        assert res["status"][0] == 0
+        assert res["n_iter"][0] == int(z[p + "n_iter"])
+        ref = dict(weights=z[p + "weights"], means=z[p + "means"], covariances=z[p + "covariances"])
+        assert_gmm_close(res, 0, ref, what="golden gene %d" % i)
+        assert abs(res["lower_bound"][0] - float(z[p + "lower_bound"])) < 1e-4
+
+
+def test_float_values_truncate_and_dropped_genes(cuda_device):
+    """AlgUtils.py:35 int16 truncation inside the kernel; < K distinct positive spots -> status 1 (dropped)."""
+    from stminer_b200.staging import SpotMatrix
+    rng = np.random.default_rng(0)
+    n_spots = 400
+    sx = (np.arange(n_spots) // 20).astype(np.int32); sy = (np.arange(n_spots) % 20).astype(np.int32)
+    cols, rows, vals = [0], [], []
+    # gene 0: float values (many in (0,1) truncate to 0), gene 1: only 3 positive spots, gene 2: negatives
+    v0 = rng.gamma(1.0, 1.5, n_spots).astype(np.float32)
+    rows += list(range(n_spots)); vals += list(v0); cols.append(len(rows))
+    rows += [5, 9, 77, 100]; vals += [2.5, 1.2, 0.7, 3.0]; cols.append(len(rows))
+    v2 = rng.normal(0, 3, n_spots).astype(np.float32)
+    rows += list(range(n_spots)); vals += list(v2); cols.append(len(rows))
+    sm = SpotMatrix(np.array(cols, dtype=np.int64), np.array(rows, dtype=np.int32), np.array(vals, dtype=np.float32),
+                    sx, sy, ["a", "b", "c"])
+    K = 6
+    W, MU, COV, ok = oracle_inits(sm, K, seed=3)
+    assert ok.tolist() == [True, False, True]
+    res = _fit(sm, K, (W, MU, COV))
+    assert res["status"].tolist() == [0, 1, 0]
+    assert (res["weights"][1] == 0).all()
+    ref = oracle_fit_all(sm, K, W, MU, COV, ok)
+    for g in (0, 2):
+        assert res["n_iter"][g] == ref[g]["n_iter"]
+        assert_gmm_close(res, g, ref[g], what="gene %d" % g)
+
+
+def test_remove_low_exp_spots(cuda_device):
+    """AlgUtils.py:16-17 on device: w <- round(max(w - mean(nonzero w), 0))."""
+    from oracle import gmm_oracle as go
+    from stminer_b200.Simulate import simulate_spot_matrix
+    sm = simulate_spot_matrix("T", seed=5, n_templates=3, replicas=2)
+    K = 4
+    inits, refs, keep = [], [], []
+    for g in range(sm.n_genes):
+        a, b = int(sm.col_ptr[g]), int(sm.col_ptr[g + 1])
+        r = sm.row_idx[a:b]
+        xy, c = go.gene_column_to_counts(sm.spot_x[r], sm.spot_y[r], sm.val[a:b], remove_low_exp_spots=True)
+        keep.append(len(c) >= K)
+        if keep[-1]:
+            i = go.kmeans_init(xy, c, K, seed=g)
+            inits.append(i); refs.append(go.weighted_em(xy, c, *i))
+        else:
+            inits.append((np.full(K, 1 / K), np.zeros((K, 2)), np.tile(np.eye(2), (K, 1, 1)))); refs.append(None)
+    init = tuple(np.stack([i[j] for i in inits]) for j in range(3))
+    res = _fit(sm, K, init, remove_low_exp_spots=True)
+    assert sum(keep) >= 3
+    for g in range(sm.n_genes):
+        if not keep[g]:
+            assert res["status"][g] == 1
+            continue
+        assert res["status"][g] == 0 and res["n_iter"][g] == refs[g]["n_iter"]
+        assert_gmm_close(res, g, refs[g], what="gene %d" % g)
+
+
+def test_long_gene_buckets_and_streaming(cuda_device):
+    """Genes beyond the small-bucket staging budget: medium (256 thr), large (512 thr) and streamed (> 18k spots)."""
+    from stminer_b200.staging import DeviceSpotMatrix, SpotMatrix
+    from oracle import gmm_oracle as go
+    rng = np.random.default_rng(1)
+    R = C = 200
+    sx = (np.arange(R * C) // C).astype(np.int32); sy = (np.arange(R * C) % C).astype(np.int32)
+    cols, rows, vals = [0], [], []
+    for n in (3000, 7000, 15000, 26000):
+        idx = np.sort(rng.choice(R * C, size=n, replace=False))
+        # two blobs + background so the mixture has structure
+        lam = 0.6 + 4 * np.exp(-((sx[idx] - 60) ** 2 + (sy[idx] - 70) ** 2) / 800.0) \
+            + 3 * np.exp(-((sx[idx] - 150) ** 2 + (sy[idx] - 120) ** 2) / 1500.0)
+        rows += idx.tolist(); vals += (1 + rng.poisson(lam)).tolist(); cols.append(len(rows))
+    sm = SpotMatrix(np.array(cols, dtype=np.int64), np.array(rows, dtype=np.int32), np.array(vals, dtype=np.float32),
+                    sx, sy, list("abcd"))
+    K = 20
+    dsm = DeviceSpotMatrix(sm)
+    _, buckets = dsm.plan(K)
+    assert buckets.tolist() == [2, 1, 1]
+    W, MU, COV, ok = oracle_inits(sm, K, seed=2)
+    res = _fit(sm, K, (W, MU, COV))
+    ref = oracle_fit_all(sm, K, W, MU, COV, ok)
+    for g in range(4):
+        assert res["status"][g] == 0
+        assert res["n_iter"][g] == ref[g]["n_iter"], g
+        assert_gmm_close(res, g, ref[g], what="gene %d" % g)
+
+
+@pytest.mark.parametrize("config,K", [("T", 10), ("V", 20)])
+def test_device_init_properties(cuda_device, config, K):
+    """On-device k-means++/Lloyd init (replaces sklearn KMeans, mixture/_base.py:119-128):
+    deterministic per seed; the max_iter=1 / huge-tol run exposes parameters one EM step after the init;
+    the full fit from the device init reaches a lower bound comparable to sklearn's own KMeans-initialised fit."""
+    from oracle import gmm_oracle as go
+    from stminer_b200.Simulate import simulate_spot_matrix
+    sm = simulate_spot_matrix(config, seed=9, n_templates=4, replicas=2)
+    a = _fit(sm, K, None, seed=3)
+    b = _fit(sm, K, None, seed=3)
+    c = _fit(sm, K, None, seed=4)
+    assert (a["status"] == 0).all()
+    for k in ("weights", "means", "covariances", "n_iter", "lower_bound"):
+        assert np.array_equal(a[k], b[k]), k                   # bit-reproducible
+    assert not np.array_equal(a["means"], c["means"])          # the seed matters
+    np.testing.assert_allclose(a["weights"].sum(axis=1), 1.0, rtol=0, atol=1e-9)
+    lbs, refs = [], []
+    for g in range(sm.n_genes):
+        xy, cnt = sm.gene_spots(g)
+        gm = go.fit_gmm_reference(xy, cnt, K, random_state=g)
+        lbs.append(a["lower_bound"][g]); refs.append(gm.lower_bound_)
+    # same optimisation quality as the reference's KMeans-initialised fit (local optima differ per gene)
+    assert np.mean(lbs) > np.mean(refs) - 0.02
+    assert np.abs(np.array(lbs) - np.array(refs)).max() < 0.25
+
+
+def test_device_init_then_oracle_em_parity(cuda_device):
+    """The EM that follows the device init is the same EM: restart the oracle from the parameters the device
+    reports after its first iteration (max_iter=1) and compare the converged fits."""
+    from oracle import gmm_oracle as go
+    from stminer_b200.Simulate import simulate_spot_matrix
+    sm = simulate_spot_matrix("V", seed=13, n_templates=3, replicas=2)
+    K = 20
+    one = _fit(sm, K, None, seed=8, max_iter=1)
+    full = _fit(sm, K, None, seed=8)
+    for g in range(sm.n_genes):
+        xy, c = sm.gene_spots(g)
+        ref = go.weighted_em(xy, c, one["weights"][g], one["means"][g], one["covariances"][g], max_iter=99)
+        if ref["n_iter"] + 1 != full["n_iter"][g]:
+            continue
+        assert_gmm_close(full, g, ref, what="gene %d" % g)

@@ -1,0 +1,54 @@
+"""CPU: one-pass CSC staging keeps the reference's per-gene semantics (AlgUtils.py:26-36)."""
+import numpy as np
+import pandas as pd
+from scipy import sparse
+
+from oracle import gmm_oracle as go
+from stminer_b200.adata_lite import AnnDataLite, column_indices, spot_matrix_from_adata
+from stminer_b200.staging import SpotMatrix
+import pytest
+
+
+def _random_adata(seed=0, n_obs=300, n_var=12, dup=True, dense=False):
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, 9, n_obs); y = rng.integers(0, 11, n_obs)       # many duplicate (x, y) rows
+    if not dup:
+        idx = rng.permutation(9 * 11)[:min(n_obs, 99)]
+        x, y = idx // 11, idx % 11
+        n_obs = len(idx)
+    X = rng.gamma(0.6, 2.0, size=(n_obs, n_var)) * (rng.random((n_obs, n_var)) < 0.4)
+    X[:, 3] *= -1                                                         # a negative column
+    Xs = X if dense else sparse.csr_matrix(X)
+    obs = pd.DataFrame({"x": x, "y": y})
+    var = pd.DataFrame(index=["g%d" % i for i in range(n_var)])
+    return AnnDataLite(Xs, obs=obs, var=var), X, x, y
+
+
+@pytest.mark.parametrize("dup,dense", [(True, False), (False, False), (True, True)])
+def test_spot_matrix_matches_reference_per_gene(dup, dense):
+    adata, X, x, y = _random_adata(dup=dup, dense=dense)
+    genes = ["g5", "g0", "g3", "g7"]
+    sm = spot_matrix_from_adata(adata, genes)
+    assert sm.genes == genes
+    for gi, g in enumerate(genes):
+        col = int(g[1:])
+        xy_ref, c_ref = go.gene_column_to_counts(x, y, X[:, col])
+        xy, c = sm.gene_spots(gi)
+        assert xy.tolist() == xy_ref.tolist()
+        assert c.tolist() == c_ref.tolist()
+
+
+def test_unknown_gene_raises_like_reference():
+    adata, *_ = _random_adata()
+    with pytest.raises(ValueError, match="Gene id: nope"):
+        column_indices(adata, ["g1", "nope"])
+
+
+def test_select_and_lpt_order():
+    adata, *_ = _random_adata()
+    sm = spot_matrix_from_adata(adata)
+    order = sm.lpt_order()
+    assert (np.diff(sm.nnz_per_gene()[order]) <= 0).all()
+    sub = sm.select([4, 1])
+    a = sm.gene_spots(4); b = sub.gene_spots(0)
+    assert a[0].tolist() == b[0].tolist() and a[1].tolist() == b[1].tolist()
