@@ -40,6 +40,12 @@ extern "C" {
 #define STM_FIT_REMOVE_LOW_EXP_SPOTS 1u /* AlgUtils.py:16-17: w <- round(max(w - mean(nonzero w), 0)) */
 #define STM_FIT_DEVICE_INIT 2u          /* ignore init_*; run the on-device weighted k-means++/Lloyd init
                                            (replaces sklearn KMeans inside GaussianMixture, _base.py:119-128) */
+/* optional tuning fields of the device init, 0 = library default */
+#define STM_FIT_LLOYD_ITERS(n) (((uint32_t)(n) & 0xffu) << 8)   /* Lloyd iteration cap (default 8; the EM that follows
+                                                                    refines further), 255 = sklearn's 300 */
+#define STM_FIT_KPP_CANDIDATES(n) (((uint32_t)(n) & 0xfu) << 16) /* greedy k-means++ trials per centre (default 2,
+                                                                    max 6), 15 = sklearn's 2 + floor(ln K) */
+#define STM_FIT_SEED_CAP_256(n) (((uint32_t)(n) & 0xffu) << 20)  /* seed-subset capacity in units of 256 spots */
 
 /* Library / build identification. */
 int stm_version(void);
@@ -87,9 +93,10 @@ int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_idx, const fl
  * Host-side launch plan for stm_gmm_fit_batched (no device work): sorts genes by decreasing nnz (the
  * reference fits them in list order, distribution.py:184; order only affects scheduling here) and splits
  * them into the three nnz buckets.  col_ptr_host[G+1], gene_order_host[G] and bucket_counts_host[3] are
- * HOST arrays; upload gene_order_host and pass both to stm_gmm_fit_batched.
+ * HOST arrays; upload gene_order_host and pass both to stm_gmm_fit_batched.  `flags` must be the flags
+ * of the fit call (the device init reserves shared memory, which moves the bucket boundaries).
  */
-int stm_gmm_fit_plan(const int64_t* col_ptr_host, int32_t G, int32_t K,
+int stm_gmm_fit_plan(const int64_t* col_ptr_host, int32_t G, int32_t K, uint32_t flags,
                      int32_t* gene_order_host, int32_t* bucket_counts_host);
 
 /*

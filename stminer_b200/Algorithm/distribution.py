@@ -77,7 +77,8 @@ class FitResult:
 
 def fit_spot_matrix(dsm: DeviceSpotMatrix, n_comp: int, init=None, max_iter: int = 100, reg_covar: float = 1e-3,
                     tol: float = 1e-3, remove_low_exp_spots: bool = False, seed: int = 0,
-                    out: Optional[FitResult] = None) -> FitResult:
+                    out: Optional[FitResult] = None, lloyd_iters: int = 0, kpp_candidates: int = 0,
+                    seed_cap: int = 0) -> FitResult:
     """Enqueue the batched EM fit of every gene of ``dsm`` on the current CUDA stream.
 
     ``init`` is ``(weights[G,K], means[G,K,2], covariances[G,K,2,2])`` (numpy or CUDA tensors, float64);
@@ -87,9 +88,8 @@ def fit_spot_matrix(dsm: DeviceSpotMatrix, n_comp: int, init=None, max_iter: int
     lib = _lib.load()
     G, K = dsm.n_genes, int(n_comp)
     dev = dsm.device
-    flags = _lib.STM_FIT_REMOVE_LOW_EXP_SPOTS if remove_low_exp_spots else 0
+    flags = _lib.fit_flags(remove_low_exp_spots, init is None, lloyd_iters, kpp_candidates, seed_cap)
     if init is None:
-        flags |= _lib.STM_FIT_DEVICE_INIT
         iw = imu = icov = None
     else:
         def dv(a, shape):
@@ -109,7 +109,7 @@ def fit_spot_matrix(dsm: DeviceSpotMatrix, n_comp: int, init=None, max_iter: int
             torch.empty((G,), dtype=torch.int32, device=dev),
             torch.empty((G,), dtype=torch.float64, device=dev),
             torch.empty((G,), dtype=torch.int32, device=dev))
-    order, buckets = dsm.plan(K)
+    order, buckets = dsm.plan(K, flags)
     with torch.cuda.device(dev):
         st = lib.stm_gmm_fit_batched(
             _lib.ptr(dsm.col_ptr), _lib.ptr(dsm.row_idx), _lib.ptr(dsm.val), _lib.ptr(dsm.spot_x), _lib.ptr(dsm.spot_y),

@@ -23,6 +23,15 @@ STM_GENE_ILL_CONDITIONED = 2
 STM_FIT_REMOVE_LOW_EXP_SPOTS = 1
 STM_FIT_DEVICE_INIT = 2
 
+
+def fit_flags(remove_low_exp_spots=False, device_init=False, lloyd_iters=0, kpp_candidates=0, seed_cap=0):
+    """Compose the ``flags`` word of ``stm_gmm_fit_batched`` / ``stm_gmm_fit_plan`` (0 = library default)."""
+    f = (STM_FIT_REMOVE_LOW_EXP_SPOTS if remove_low_exp_spots else 0) | (STM_FIT_DEVICE_INIT if device_init else 0)
+    f |= (int(lloyd_iters) & 0xff) << 8
+    f |= (int(kpp_candidates) & 0xf) << 16
+    f |= ((int(seed_cap) + 255) // 256 & 0xff) << 20
+    return f
+
 # every symbol include/stminer_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "stm_version": (C.c_int, []),
@@ -34,7 +43,7 @@ SIGNATURES = {
         C.c_double, C.c_double, C.c_int32, C.c_uint32, C.c_uint64,  # reg_covar,tol,max_iter,flags,seed
         _P, _P, _P, _P, _P, _P, _P, _P,                # out_w,out_mu,out_cov,n_iter,converged,lb,status,stream
     ]),
-    "stm_gmm_fit_plan": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
+    "stm_gmm_fit_plan": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint32, _P, _P]),
     "stm_gmm_dist_pairs": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "stm_gmm_dist_fill_square": (C.c_int, [_P, C.c_int32, _P, _P]),
     "stm_gmm_dist_one_vs_all": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
@@ -47,7 +56,8 @@ class StmError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """The in-tree library; STM_LIB_PATH selects a tuning variant built by ``build.build(defines=..., out=...)``."""
+    return os.environ.get("STM_LIB_PATH") or _build.LIB_PATH
 
 
 def load():

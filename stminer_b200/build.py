@@ -42,16 +42,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=None, out: str = None) -> str:
+    """Compile csrc/*.cu into the in-tree library.  ``defines`` / ``out`` build a tuning variant
+    (e.g. ``defines=["STM_EM_MINB_SMALL=5"]``) next to the default library."""
+    lib_path = out or LIB_PATH
+    if not force and not defines and not out and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
-    os.makedirs(BUILD_DIR, exist_ok=True)
+    build_dir = BUILD_DIR if not out else BUILD_DIR + "_" + os.path.basename(out)
+    os.makedirs(build_dir, exist_ok=True)
     objs = []
+    dflags = ["-D" + d for d in (defines or [])]
 
     def compile_one(src):
-        obj = os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *dflags, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -63,11 +68,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -6,6 +6,8 @@
 // distribution.py:369-373 is replaced by integer weights on distinct spots.
 //
 // Kernel shape:
+//   * each gene's positive spots are staged ONCE into shared memory as 8-byte records
+//     (int16 x, int16 y relative to the gene's integer centroid, float weight);
 //   * a thread group of GS lanes owns one spot at a time; lane `sub` of the group owns KT components
 //     (K <= KT*GS), whose 6 E-step coefficients and 6 M-step accumulators live in registers;
 //   * log2-domain whitened residuals  t = s * U^T (x - mu),  s = sqrt(log2(e)/2):
@@ -18,8 +20,9 @@
 //   * genes are bucketed by nnz on the host (stm_gmm_fit_plan): each bucket gets a CTA size / shared
 //     memory budget that keeps its spots staged on chip; genes beyond the largest budget stream
 //     their spots from L2;
-//   * optional on-device initialisation (weighted greedy k-means++ + Lloyd) replaces the sklearn
-//     KMeans the reference runs inside GaussianMixture (mixture/_base.py:119-128).
+//   * optional on-device initialisation (weighted greedy k-means++ and Lloyd on a strided seed subset,
+//     then one assignment pass over all spots) replaces the sklearn KMeans the reference runs inside
+//     GaussianMixture (mixture/_base.py:119-128).
 #include <float.h>
 #include <limits.h>
 #include <math.h>
@@ -36,6 +39,19 @@ namespace {
 constexpr int EM_CHUNK_PER_GROUP = 2048;  // spots per group between FP64 flushes of the accumulators
 constexpr int KM_MAX_ITER = 300;          // sklearn KMeans default max_iter
 constexpr int KM_LMAX = 6;                // greedy k-means++ candidates: 2 + floor(ln K) <= 6 for K <= 64
+
+#ifndef STM_EM_S_SMALL
+#define STM_EM_S_SMALL 2      // spots in flight per thread group, small-gene bucket
+#endif
+#ifndef STM_EM_MINB_SMALL
+#define STM_EM_MINB_SMALL 4   // CTAs (of 128 threads) per SM, small-gene bucket
+#endif
+#ifndef STM_KM_DEFAULT_CAND
+#define STM_KM_DEFAULT_CAND 2     // greedy k-means++ trials per centre when the flags field is 0
+#endif
+#ifndef STM_KM_DEFAULT_LLOYD
+#define STM_KM_DEFAULT_LLOYD 8    // Lloyd iteration cap when the flags field is 0 (EM refines further)
+#endif
 
 struct EmArgs {
   const int64_t* col_ptr;
@@ -57,6 +73,9 @@ struct EmArgs {
   int32_t G, K;
   int32_t order_begin;  // this launch fits gene_order[order_begin + blockIdx.x]
   int32_t smem_spots;   // staging capacity (spots) of this launch
+  int32_t seed_cap;     // k-means seed-set capacity of this launch (0 without device init)
+  int32_t km_max_iter;  // Lloyd iteration cap
+  int32_t km_cand;      // greedy k-means++ candidates per centre
   int32_t max_iter;
   uint32_t flags;
   double reg_covar, tol;
@@ -124,10 +143,10 @@ struct EmLayout {
   static constexpr int D_SCR = D_MISC + 8;       // [WARPS * KM_LMAX + 2 * KM_LMAX] k-means++ scratch
   static constexpr int D_END = round_up(D_SCR + WARPS * KM_LMAX + 2 * KM_LMAX, 2);
   // floats (after doubles)
-  static constexpr int F_PAR = 0;                                    // [KP*8]
-  static constexpr int F_RED = F_PAR + KP * 8;                       // [WARPS*NSTAT]
-  static constexpr int F_SPOT = round_up(F_RED + WARPS * NSTAT, 4);  // 3 * cap
-  static constexpr size_t fixed_bytes() { return (size_t)D_END * 8 + (size_t)F_SPOT * 4 + 64; }
+  static constexpr int F_PAR = 0;                                   // [KP*8]
+  static constexpr int F_RED = F_PAR + KP * 8;                      // [WARPS*NSTAT]
+  static constexpr int F_END = round_up(F_RED + WARPS * NSTAT, 4);  // then float4 seeds[seed_cap], int2 spots[cap]
+  static constexpr size_t fixed_bytes() { return (size_t)D_END * 8 + (size_t)F_END * 4 + 64; }
 };
 
 // Component k: (mu, cov, w) in s_d -> E-step coefficients in s_par.  Returns false if cov is not PD.
@@ -143,25 +162,45 @@ __device__ __forceinline__ bool refresh_component(int k, double* s_d, float* s_p
   ok = ok && (t > 0.0) && isfinite(t) && isfinite(a);
   const double l11 = sqrt(t);
   const double s = 0.84932180028801904272;  // sqrt(log2(e) / 2)
-  const float a00 = (float)(s / l00);
-  const float a11 = (float)(s / l11);
-  const float a01 = (float)(-l10 * s / (l00 * l11));
+  const double i00 = 1.0 / l00, i11 = 1.0 / l11;
+  const float a00 = (float)(s * i00);
+  const float a11 = (float)(s * i11);
+  const float a01 = (float)(-l10 * s * i00 * i11);
   const float b0 = (float)(-(double)a00 * mx);
   const float b1 = (float)(-((double)a01 * mx + (double)a11 * my));
-  // log2( w / (2 pi l00 l11) )
-  const float c2 = (float)log2(w / (6.283185307179586476925 * l00 * l11));
+  // log2( w / (2 pi l00 l11) ) — FP32 like the coefficient that stores it
+  const float c2 = lg2_approx((float)(w * i00 * i11 * 0.15915494309189533577));
   float* q = s_par + 8 * k;
   q[0] = a00; q[1] = b0; q[2] = a01; q[3] = a11; q[4] = b1; q[5] = c2;
   return ok;
 }
 
-struct StagedSpots {
-  const float* x; const float* y; const float* w;
+__device__ __forceinline__ int pack_xy(int x, int y) {
+  x = max(-32768, min(32767, x)); y = max(-32768, min(32767, y));
+  return (x & 0xffff) | (y << 16);
+}
+__device__ __forceinline__ float unpack_x(int p) { return (float)(short)(p & 0xffff); }
+__device__ __forceinline__ float unpack_y(int p) { return (float)(p >> 16); }
+
+// spots staged in shared memory: {int16 x | int16 y, float w}
+struct PackedSpots {
+  const int2* s;
   __device__ __forceinline__ void get(int i, float& xo, float& yo, float& wo) const {
-    xo = x[i]; yo = y[i]; wo = w[i];
+    const int2 v = s[i];
+    xo = unpack_x(v.x); yo = unpack_y(v.x); wo = __int_as_float(v.y);
   }
 };
 
+// k-means seed subset in shared memory: {x, y, w, d2}
+struct SeedSpots {
+  const float4* s;
+  __device__ __forceinline__ void get(int i, float& xo, float& yo, float& wo) const {
+    const float4 v = s[i];
+    xo = v.x; yo = v.y; wo = v.z;
+  }
+};
+
+// spots of a gene too long to stage: re-read from global memory (L2) every sweep
 struct StreamedSpots {
   const int32_t* row_idx; const float* val; const int32_t* spot_x; const int32_t* spot_y;
   int ox, oy; bool remove_low; double mean_nz;
@@ -219,10 +258,11 @@ __device__ __forceinline__ void em_sweep(const Src& src, int i_begin, int i_end,
 #pragma unroll
       for (int o = 1; o < GS; o <<= 1) sum[s] += __shfl_xor_sync(FULL_MASK, sum[s], o);
     }
+    float wl = 0.f;  // sum_s w_s * log2-sum-exp_s of this step (S terms in FP32, then one FP64 add)
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const float scale = w[s] * rcp_approx(sum[s]);
-      if (sub == 0) ll = fma((double)w[s], (double)(m[s] + lg2_approx(sum[s])), ll);
+      wl = fmaf(w[s], m[s] + lg2_approx(sum[s]), wl);
 #pragma unroll
       for (int j = 0; j < KT; ++j) {
         const float r = lp[s][j] * scale;
@@ -236,14 +276,15 @@ __device__ __forceinline__ void em_sweep(const Src& src, int i_begin, int i_end,
         acc[j * 6 + 5] = fmaf(rt1, t1[s][j], acc[j * 6 + 5]);
       }
     }
+    ll += (double)wl;  // every lane of a group holds the same value; lane sub == 0 is the one summed
   }
 }
 
-// Lloyd assignment sweep: every spot goes to its nearest centre (ties: lowest component index); the
-// owning lane accumulates n, dx, dy (and dxdx, dxdy, dydy when MOMENTS) relative to that centre.
-template <int KT, int GS, int T, bool MOMENTS, typename Src>
-__device__ __forceinline__ void lloyd_sweep(const Src& src, int i_begin, int i_end, int grp, int sub,
-                                            const float (&cx)[KT], const float (&cy)[KT], float* acc) {
+// Assignment sweep with moments: every spot goes to its nearest centre (ties: lowest component
+// index); the owning lane accumulates n, dx, dy, dxdx, dxdy, dydy relative to that centre.
+template <int KT, int GS, int T, typename Src>
+__device__ __forceinline__ void assign_moments_sweep(const Src& src, int i_begin, int i_end, int grp, int sub,
+                                                     const float (&cx)[KT], const float (&cy)[KT], float* acc) {
   constexpr int NG = T / GS;
   for (int base = i_begin; base < i_end; base += NG) {
     const int i = base + grp;
@@ -269,15 +310,44 @@ __device__ __forceinline__ void lloyd_sweep(const Src& src, int i_begin, int i_e
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
       const float wj = (mine && jb == j) ? w : 0.f;
+      const float wdx = wj * dx[j];
       acc[j * 6 + 0] += wj;
-      acc[j * 6 + 1] = fmaf(wj, dx[j], acc[j * 6 + 1]);
+      acc[j * 6 + 1] += wdx;
       acc[j * 6 + 2] = fmaf(wj, dy[j], acc[j * 6 + 2]);
-      if constexpr (MOMENTS) {
-        const float wdx = wj * dx[j];
-        acc[j * 6 + 3] = fmaf(wdx, dx[j], acc[j * 6 + 3]);
-        acc[j * 6 + 4] = fmaf(wdx, dy[j], acc[j * 6 + 4]);
-        acc[j * 6 + 5] = fmaf(wj * dy[j], dy[j], acc[j * 6 + 5]);
-      }
+      acc[j * 6 + 3] = fmaf(wdx, dx[j], acc[j * 6 + 3]);
+      acc[j * 6 + 4] = fmaf(wdx, dy[j], acc[j * 6 + 4]);
+      acc[j * 6 + 5] = fmaf(wj * dy[j], dy[j], acc[j * 6 + 5]);
+    }
+  }
+}
+
+// Lloyd iteration sweep (no moments): nearest centre = argmax_k 2 c_k.x - |c_k|^2; the component index
+// rides in the 6 low mantissa bits of the score so the argmax is a plain float max (ties inside 2^-17
+// relative go to the higher index — harmless for an initialiser).  Accumulates n, sum w x, sum w y.
+template <int KT, int GS, int T, typename Src>
+__device__ __forceinline__ void lloyd_sweep(const Src& src, int i_begin, int i_end, int grp, int sub,
+                                            const float (&ax)[KT], const float (&ay)[KT], const float (&bb)[KT],
+                                            float* acc) {
+  constexpr int NG = T / GS;
+  for (int base = i_begin; base < i_end; base += NG) {
+    const int i = base + grp;
+    float x = 0.f, y = 0.f, w = 0.f;
+    if (i < i_end) src.get(i, x, y, w);
+    float best = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      const float sc = fmaf(x, ax[j], fmaf(y, ay[j], bb[j]));
+      best = fmaxf(best, __int_as_float((__float_as_int(sc) & ~63) | (sub * KT + j)));
+    }
+#pragma unroll
+    for (int o = 1; o < GS; o <<= 1) best = fmaxf(best, __shfl_xor_sync(FULL_MASK, best, o));
+    const int jm = (__float_as_int(best) & 63) - sub * KT;  // in [0, KT) only on the owning lane
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      const float wj = (jm == j) ? w : 0.f;
+      acc[j * 6 + 0] += wj;
+      acc[j * 6 + 1] = fmaf(wj, x, acc[j * 6 + 1]);
+      acc[j * 6 + 2] = fmaf(wj, y, acc[j * 6 + 2]);
     }
   }
 }
@@ -304,13 +374,6 @@ __device__ __forceinline__ void flush_stats(float (&acc)[NPAD], double* s_d, flo
   __syncthreads();
 }
 
-__device__ __forceinline__ int pack_xy(int x, int y) {
-  x = max(-32768, min(32767, x)); y = max(-32768, min(32767, y));
-  return (x & 0xffff) | (y << 16);
-}
-__device__ __forceinline__ float unpack_x(int p) { return (float)(short)(p & 0xffff); }
-__device__ __forceinline__ float unpack_y(int p) { return (float)(p >> 16); }
-
 // Weighted draw of L indices from the seed set: P(i) ~ value(i), thread-major element order.
 // part = this thread's sum of value(i) over its elements i = tid, tid+T, ...
 template <int T, typename ValueFn>
@@ -318,7 +381,6 @@ __device__ __forceinline__ void weighted_pick(double part, int L, const double* 
                                               double* s_scr, int* s_pick, int tid) {
   constexpr int WARPS = T / 32;
   const int lane = tid & 31, warp = tid >> 5;
-  // inclusive scan of the per-thread parts inside each warp
   double incl = part;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -331,11 +393,10 @@ __device__ __forceinline__ void weighted_pick(double part, int L, const double* 
 #pragma unroll
   for (int w = 0; w < WARPS; ++w) { const double v = s_scr[w]; if (w < warp) warp_off += v; total += v; }
   const double hi = warp_off + incl, lo = hi - part;
+  const bool last_owner = (tid == T - 1) || (tid == ns - 1 && ns < T);
   for (int l = 0; l < L; ++l) {
-    double r = u[l] * total;
-    const bool last_owner = (tid == T - 1) || (tid == ns - 1 && ns < T);
+    const double r = u[l] * total;
     if ((r >= lo && r < hi) || (last_owner && r >= hi)) {
-      // walk own elements
       double res = r - lo;
       int pick = -1, last_pos = -1;
       for (int i = tid; i < ns; i += T) {
@@ -364,9 +425,8 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   float* s_f = reinterpret_cast<float*>(s_d + L::D_END);
   float* s_par = s_f + L::F_PAR;
   float* s_red = s_f + L::F_RED;
-  float* s_x = s_f + L::F_SPOT;
-  float* s_y = s_x + p.smem_spots;
-  float* s_wt = s_y + p.smem_spots;
+  float4* s_seed = reinterpret_cast<float4*>(s_f + L::F_END);
+  int2* s_spot = reinterpret_cast<int2*>(s_seed + p.seed_cap);
   __shared__ int s_cnt[WARPS];
   __shared__ int s_flag[4];
   __shared__ int s_pick[KM_LMAX];
@@ -446,12 +506,11 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     return;
   }
   const int ox = (int)rint(t_swx / t_sw), oy = (int)rint(t_swy / t_sw);
-  // device-init seeding packs origin-relative coordinates into int16 pairs
+  // the staged record holds origin-relative coordinates as int16
   const bool packable = (xmax - ox) < 32768 && (ox - xmin) < 32768 && (ymax - oy) < 32768 && (oy - ymin) < 32768;
 
   // ---- stage distinct positive spots into shared memory (ordered compaction) ----------------
-  const bool staged = ncol <= p.smem_spots && (!device_init || packable);
-  const bool stage_packed = staged && device_init;  // seeding layout first: s_x = packed xy, s_y = d2
+  const bool staged = ncol <= p.smem_spots && packable;
   int n_spots = ncol;
   if (staged) {
     int n_st = 0;
@@ -468,13 +527,8 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
       for (int ww = 0; ww < WARPS; ++ww) { const int c = s_cnt[ww]; if (ww < warp) off += c; tot += c; }
       if (keep) {
         const int idx = off + __popc(bal & ((1u << lane) - 1u));
-        const int xr = __ldg(p.spot_x + r) - ox, yr = __ldg(p.spot_y + r) - oy;
-        if (stage_packed) {
-          reinterpret_cast<int*>(s_x)[idx] = pack_xy(xr, yr);
-        } else {
-          s_x[idx] = (float)xr; s_y[idx] = (float)yr;
-        }
-        s_wt[idx] = (float)w;
+        s_spot[idx] = make_int2(pack_xy(__ldg(p.spot_x + r) - ox, __ldg(p.spot_y + r) - oy),
+                                __float_as_int((float)w));
       }
       n_st += tot;
       __syncthreads();
@@ -482,7 +536,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     n_spots = n_st;
   }
 
-  const StagedSpots staged_src{s_x, s_y, s_wt};
+  const PackedSpots staged_src{s_spot};
   const StreamedSpots stream_src{rows, vals, p.spot_x, p.spot_y, ox, oy, remove_low, mean_nz};
 
   if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; }
@@ -495,171 +549,178 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
 
   if (device_init) {
     // =========================================================================================
-    // Weighted greedy k-means++ seeding on the staged spots (or a strided subsample of a streamed
-    // gene), then Lloyd on all spots, then one-hot responsibilities -> (w, mu, cov) as sklearn's
-    // GaussianMixture._initialize (_gaussian_mixture.py:849-881).
+    // Seed subset (every stride-th spot, at most seed_cap) -> weighted greedy k-means++ -> Lloyd on the
+    // subset -> one assignment pass over ALL spots -> one-hot responsibilities -> (w, mu, cov) as
+    // sklearn's GaussianMixture._initialize (_gaussian_mixture.py:849-881).
     // =========================================================================================
-    int* s_pk = reinterpret_cast<int*>(s_x);
-    float* s_d2 = s_y;
-    int ns = n_spots;
-    if (!staged) {
-      const int stride = (ncol + p.smem_spots - 1) / p.smem_spots;
-      ns = (ncol + stride - 1) / stride;
-      for (int j = tid; j < ns; j += T) {
-        const int i = j * stride;
-        const int r = __ldg(rows + i);
-        const int w = gene_weight(__ldg(vals + i), remove_low, mean_nz);
-        s_pk[j] = pack_xy(__ldg(p.spot_x + r) - ox, __ldg(p.spot_y + r) - oy);
-        s_wt[j] = w > 0 ? (float)w : 0.f;
-      }
-      __syncthreads();
+    const int stride = (n_spots + p.seed_cap - 1) / p.seed_cap;
+    const int ns = (n_spots + stride - 1) / stride;
+    for (int j = tid; j < ns; j += T) {
+      float x, y, w;
+      if (staged) staged_src.get(j * stride, x, y, w); else stream_src.get(j * stride, x, y, w);
+      s_seed[j] = make_float4(x, y, w, 0.f);
     }
-    const int Lc = min(KM_LMAX, 2 + (int)floor(log((double)K)));
+    __syncthreads();
+    const int Lc = max(1, min(KM_LMAX, p.km_cand));
     double* s_scr = s_d + L::D_SCR;
     double* s_pot = s_scr + WARPS * KM_LMAX;  // [KM_LMAX] reduced candidate potentials
-    // first centre ~ w
-    {
+    {  // first centre ~ w
       double part = 0.0;
-      for (int i = tid; i < ns; i += T) part += (double)s_wt[i];
+      for (int i = tid; i < ns; i += T) part += (double)s_seed[i].z;
       double u[1] = {u01(p.seed, (uint64_t)g, 0)};
-      weighted_pick<T>(part, 1, u, ns, [&](int i) { return (double)s_wt[i]; }, s_scr, s_pick, tid);
+      weighted_pick<T>(part, 1, u, ns, [&](int i) { return (double)s_seed[i].z; }, s_scr, s_pick, tid);
     }
-    float ccx = unpack_x(s_pk[s_pick[0]]), ccy = unpack_y(s_pk[s_pick[0]]);
+    float ccx = s_seed[s_pick[0]].x, ccy = s_seed[s_pick[0]].y;
     if (tid == 0) { s_par[6] = ccx; s_par[7] = ccy; }
+    __syncthreads();
     double part = 0.0;
     for (int i = tid; i < ns; i += T) {
-      const float dx = unpack_x(s_pk[i]) - ccx, dy = unpack_y(s_pk[i]) - ccy;
-      const float d = fmaf(dx, dx, dy * dy);
-      s_d2[i] = d;
-      part += (double)(s_wt[i] * d);
+      float4 v = s_seed[i];
+      const float dx = v.x - ccx, dy = v.y - ccy;
+      v.w = fmaf(dx, dx, dy * dy);
+      s_seed[i] = v;
+      part += (double)(v.z * v.w);
     }
     for (int c = 1; c < K; ++c) {
       double u[KM_LMAX];
       for (int l = 0; l < Lc; ++l) u[l] = u01(p.seed, (uint64_t)g, (uint64_t)c * 8 + l);
-      weighted_pick<T>(part, Lc, u, ns, [&](int i) { return (double)(s_wt[i] * s_d2[i]); }, s_scr, s_pick, tid);
-      float candx[KM_LMAX], candy[KM_LMAX], pot[KM_LMAX];
-#pragma unroll
-      for (int l = 0; l < KM_LMAX; ++l) {
-        const int pi = s_pick[l < Lc ? l : 0];
-        candx[l] = unpack_x(s_pk[pi]); candy[l] = unpack_y(s_pk[pi]); pot[l] = 0.f;
-      }
-      for (int i = tid; i < ns; i += T) {
-        const float x = unpack_x(s_pk[i]), y = unpack_y(s_pk[i]), w = s_wt[i], d0 = s_d2[i];
+      weighted_pick<T>(part, Lc, u, ns, [&](int i) { const float4 v = s_seed[i]; return (double)(v.z * v.w); },
+                       s_scr, s_pick, tid);
+      int bl = 0;
+      if (Lc > 1) {
+        float candx[KM_LMAX], candy[KM_LMAX], pot[KM_LMAX];
 #pragma unroll
         for (int l = 0; l < KM_LMAX; ++l) {
-          const float dx = x - candx[l], dy = y - candy[l];
-          pot[l] = fmaf(w, fminf(d0, fmaf(dx, dx, dy * dy)), pot[l]);
+          const float4 v = s_seed[s_pick[l < Lc ? l : 0]];
+          candx[l] = v.x; candy[l] = v.y; pot[l] = 0.f;
         }
-      }
+        for (int i = tid; i < ns; i += T) {
+          const float4 v = s_seed[i];
 #pragma unroll
-      for (int l = 0; l < KM_LMAX; ++l) {
-        const double v = warp_sum((double)pot[l]);
-        if (lane == 0) s_scr[warp * KM_LMAX + l] = v;
+          for (int l = 0; l < KM_LMAX; ++l) {
+            if (l < Lc) {
+              const float dx = v.x - candx[l], dy = v.y - candy[l];
+              pot[l] = fmaf(v.z, fminf(v.w, fmaf(dx, dx, dy * dy)), pot[l]);
+            }
+          }
+        }
+#pragma unroll
+        for (int l = 0; l < KM_LMAX; ++l) {
+          if (l < Lc) {
+            const double v = warp_sum((double)pot[l]);
+            if (lane == 0) s_scr[warp * KM_LMAX + l] = v;
+          }
+        }
+        __syncthreads();
+        if (tid < Lc) {
+          double t = 0.0;
+          for (int w = 0; w < WARPS; ++w) t += s_scr[w * KM_LMAX + tid];
+          s_pot[tid] = t;
+        }
+        __syncthreads();
+        for (int l = 1; l < Lc; ++l) if (s_pot[l] < s_pot[bl]) bl = l;
       }
-      __syncthreads();
-      if (tid < KM_LMAX) {
-        double t = 0.0;
-        for (int w = 0; w < WARPS; ++w) t += s_scr[w * KM_LMAX + tid];
-        s_pot[tid] = t;
-      }
-      __syncthreads();
-      int bl = 0;
-      for (int l = 1; l < Lc; ++l) if (s_pot[l] < s_pot[bl]) bl = l;
-      ccx = unpack_x(s_pk[s_pick[bl]]); ccy = unpack_y(s_pk[s_pick[bl]]);
+      ccx = s_seed[s_pick[bl]].x; ccy = s_seed[s_pick[bl]].y;
       if (tid == 0) { s_par[8 * c + 6] = ccx; s_par[8 * c + 7] = ccy; }
+      __syncthreads();  // every thread has read the winning seed before any d2 is rewritten
       part = 0.0;
       for (int i = tid; i < ns; i += T) {
-        const float dx = unpack_x(s_pk[i]) - ccx, dy = unpack_y(s_pk[i]) - ccy;
-        const float d = fminf(s_d2[i], fmaf(dx, dx, dy * dy));
-        s_d2[i] = d;
-        part += (double)(s_wt[i] * d);
+        float4 v = s_seed[i];
+        const float dx = v.x - ccx, dy = v.y - ccy;
+        v.w = fminf(v.w, fmaf(dx, dx, dy * dy));
+        s_seed[i] = v;
+        part += (double)(v.z * v.w);
       }
       __syncthreads();  // s_pick / s_pot are rewritten by the next round
-    }
-    // seeding layout -> float staging layout
-    if (staged) {
-      for (int i = tid; i < n_spots; i += T) {
-        const int pk = s_pk[i];
-        s_x[i] = unpack_x(pk); s_y[i] = unpack_y(pk);
-      }
     }
     if (tid < K) { s_d[L::D_MU + 2 * tid] = (double)s_par[8 * tid + 6]; s_d[L::D_MU + 2 * tid + 1] = (double)s_par[8 * tid + 7]; }
     __syncthreads();
 
-    // tolerance of sklearn KMeans: tol * mean(var(X, axis=0)) with tol = 1e-4 (cluster/_kmeans.py _tolerance)
-    double vx = 0.0, vy = 0.0;
+    // tolerance of sklearn KMeans: tol * mean(var(X, axis=0)) with tol = 1e-4 (cluster/_kmeans.py _tolerance),
+    // estimated on the seed subset
+    const SeedSpots seed_src{s_seed};
+    double vx = 0.0, vy = 0.0, vw = 0.0;
     {
       const double mxo = t_swx / t_sw - ox, myo = t_swy / t_sw - oy;
-      for (int i = tid; i < n_spots; i += T) {
-        float x, y, w;
-        if (staged) staged_src.get(i, x, y, w); else stream_src.get(i, x, y, w);
-        const double dx = x - mxo, dy = y - myo;
-        vx += w * dx * dx; vy += w * dy * dy;
+      for (int i = tid; i < ns; i += T) {
+        const float4 v = s_seed[i];
+        const double dx = v.x - mxo, dy = v.y - myo;
+        vx += v.z * dx * dx; vy += v.z * dy * dy; vw += v.z;
       }
-      vx = warp_sum(vx); vy = warp_sum(vy);
-      if (lane == 0) { s_scr[2 * warp] = vx; s_scr[2 * warp + 1] = vy; }
+      vx = warp_sum(vx); vy = warp_sum(vy); vw = warp_sum(vw);
+      if (lane == 0) { s_scr[3 * warp] = vx; s_scr[3 * warp + 1] = vy; s_scr[3 * warp + 2] = vw; }
       __syncthreads();
-      vx = 0.0; vy = 0.0;
-      for (int w = 0; w < WARPS; ++w) { vx += s_scr[2 * w]; vy += s_scr[2 * w + 1]; }
+      vx = 0.0; vy = 0.0; vw = 0.0;
+      for (int w = 0; w < WARPS; ++w) { vx += s_scr[3 * w]; vy += s_scr[3 * w + 1]; vw += s_scr[3 * w + 2]; }
       __syncthreads();
     }
-    const double km_tol = 1e-4 * 0.5 * (vx + vy) / N_total;
+    const double km_tol = 1e-4 * 0.5 * (vx + vy) / fmax(vw, 1.0);
 
-    for (int it = 0; it <= KM_MAX_ITER; ++it) {
-      const bool final_pass = s_flag[0] != 0 || it == KM_MAX_ITER;
+    for (int it = 0; it < p.km_max_iter; ++it) {
+      float ax[KT], ay[KT], bb[KT];
+#pragma unroll
+      for (int j = 0; j < KT; ++j) {
+        const float cx = s_par[8 * (sub * KT + j) + 6], cy = s_par[8 * (sub * KT + j) + 7];
+        ax[j] = 2.f * cx; ay[j] = 2.f * cy; bb[j] = -fmaf(cx, cx, cy * cy);
+      }
+      for (int i = tid; i < NSTAT; i += T) s_d[L::D_STAT + i] = 0.0;
+      if (tid == 0) s_d[L::D_MISC + 2] = 0.0;
+      __syncthreads();
+      {
+        float acc[NPAD];
+#pragma unroll
+        for (int i = 0; i < NPAD; ++i) acc[i] = 0.f;
+        lloyd_sweep<KT, GS, T>(seed_src, 0, ns, grp, sub, ax, ay, bb, acc);
+        flush_stats<KT, GS, T, NPAD>(acc, s_d, s_red, tid);
+      }
+      if (tid < K) {
+        const int k = tid;
+        const double* st = s_d + L::D_STAT + 6 * k;
+        if (st[0] > 0.0) {
+          const double nx = st[1] / st[0], ny = st[2] / st[0];
+          const double ddx = nx - s_d[L::D_MU + 2 * k], ddy = ny - s_d[L::D_MU + 2 * k + 1];
+          s_d[L::D_MU + 2 * k] = nx;
+          s_d[L::D_MU + 2 * k + 1] = ny;
+          s_par[8 * k + 6] = (float)nx;
+          s_par[8 * k + 7] = (float)ny;
+          atomicAdd(&s_d[L::D_MISC + 2], ddx * ddx + ddy * ddy);
+        }
+      }
+      __syncthreads();
+      const bool done = s_d[L::D_MISC + 2] <= km_tol;
+      __syncthreads();
+      if (done) break;
+    }
+    // assignment pass over all spots with second moments -> initial (w, mu, cov)
+    {
       float cx[KT], cy[KT];
 #pragma unroll
       for (int j = 0; j < KT; ++j) { cx[j] = s_par[8 * (sub * KT + j) + 6]; cy[j] = s_par[8 * (sub * KT + j) + 7]; }
       for (int i = tid; i < NSTAT; i += T) s_d[L::D_STAT + i] = 0.0;
-      if (tid == 0) s_d[L::D_MISC + 2] = 0.0;
       __syncthreads();
       for (int c0 = 0; c0 < n_spots; c0 += CHUNK) {
         const int c1 = min(n_spots, c0 + CHUNK);
         float acc[NPAD];
 #pragma unroll
         for (int i = 0; i < NPAD; ++i) acc[i] = 0.f;
-        if (final_pass) {
-          if (staged) lloyd_sweep<KT, GS, T, true>(staged_src, c0, c1, grp, sub, cx, cy, acc);
-          else        lloyd_sweep<KT, GS, T, true>(stream_src, c0, c1, grp, sub, cx, cy, acc);
-        } else {
-          if (staged) lloyd_sweep<KT, GS, T, false>(staged_src, c0, c1, grp, sub, cx, cy, acc);
-          else        lloyd_sweep<KT, GS, T, false>(stream_src, c0, c1, grp, sub, cx, cy, acc);
-        }
+        if (staged) assign_moments_sweep<KT, GS, T>(staged_src, c0, c1, grp, sub, cx, cy, acc);
+        else        assign_moments_sweep<KT, GS, T>(stream_src, c0, c1, grp, sub, cx, cy, acc);
         flush_stats<KT, GS, T, NPAD>(acc, s_d, s_red, tid);
-      }
-      if (final_pass) {
-        if (tid < K) {
-          const int k = tid;
-          const double* st = s_d + L::D_STAT + 6 * k;
-          const double n = st[0] + 10.0 * DBL_EPSILON;  // _gaussian_mixture.py:312
-          const double ddx = st[1] / n, ddy = st[2] / n;
-          s_d[L::D_MU + 2 * k] += ddx;
-          s_d[L::D_MU + 2 * k + 1] += ddy;
-          s_d[L::D_COV + 3 * k] = st[3] / n - ddx * ddx + p.reg_covar;
-          s_d[L::D_COV + 3 * k + 1] = st[4] / n - ddx * ddy;
-          s_d[L::D_COV + 3 * k + 2] = st[5] / n - ddy * ddy + p.reg_covar;
-          s_d[L::D_W + k] = n / N_total;                // weights /= n_samples, _gaussian_mixture.py:866
-        }
-        __syncthreads();
-        break;
       }
       if (tid < K) {
         const int k = tid;
         const double* st = s_d + L::D_STAT + 6 * k;
-        if (st[0] > 0.0) {
-          const double ddx = st[1] / st[0], ddy = st[2] / st[0];
-          s_d[L::D_MU + 2 * k] += ddx;
-          s_d[L::D_MU + 2 * k + 1] += ddy;
-          s_par[8 * k + 6] = (float)s_d[L::D_MU + 2 * k];
-          s_par[8 * k + 7] = (float)s_d[L::D_MU + 2 * k + 1];
-          atomicAdd(&s_d[L::D_MISC + 2], ddx * ddx + ddy * ddy);
-        }
+        const double n = st[0] + 10.0 * DBL_EPSILON;  // _gaussian_mixture.py:312
+        const double ddx = st[1] / n, ddy = st[2] / n;
+        // measured from the float centre the sweep used, not the FP64 master copy
+        s_d[L::D_MU + 2 * k] = (double)s_par[8 * k + 6] + ddx;
+        s_d[L::D_MU + 2 * k + 1] = (double)s_par[8 * k + 7] + ddy;
+        s_d[L::D_COV + 3 * k] = st[3] / n - ddx * ddx + p.reg_covar;
+        s_d[L::D_COV + 3 * k + 1] = st[4] / n - ddx * ddy;
+        s_d[L::D_COV + 3 * k + 2] = st[5] / n - ddy * ddy + p.reg_covar;
+        s_d[L::D_W + k] = n / N_total;                // weights /= n_samples, _gaussian_mixture.py:866
       }
-      __syncthreads();
-      if (tid == 0 && s_d[L::D_MISC + 2] <= km_tol) s_flag[0] = 1;
-      __syncthreads();
     }
-    if (tid == 0) s_flag[0] = 0;
   } else if (tid < K) {
     const int k = tid;
     const double* iw = p.init_w + (size_t)g * K;
@@ -704,7 +765,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
       else        em_sweep<KT, GS, S, T>(stream_src, c0, c1, grp, sub, par, acc, ll);
       flush_stats<KT, GS, T, NPAD>(acc, s_d, s_red, tid);
     }
-    ll = warp_sum(ll);
+    ll = warp_sum(sub == 0 ? ll : 0.0);
     if (lane == 0) s_d[L::D_LL + warp] = ll;
     __syncthreads();
     // M-step finalize: whitened moments -> (w, mu, cov) (sklearn _gaussian_mixture.py:282-320,883-901)
@@ -774,50 +835,54 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
 // its staging capacity follows from the 228 KB of shared memory an SM has.
 // ------------------------------------------------------------------------------------------------
 constexpr int N_BUCKETS = 3;  // 0: largest genes ... 2: smallest
-
-template <int KT, int GS, int T>
-constexpr size_t em_fixed_bytes() { return EmLayout<KT, GS, T>::fixed_bytes(); }
-
-inline int32_t cap_for(size_t fixed, int minb, int max_optin) {
-  size_t per_cta = ((size_t)228 * 1024) / minb - 1024 - 64;
-  if (per_cta > (size_t)max_optin) per_cta = max_optin;
-  if (per_cta < fixed + 12 * 64) return 0;
-  return (int32_t)(((per_cta - fixed) / 12) & ~(size_t)3);
-}
-
-struct ClassCfg { int T[N_BUCKETS]; int minb[N_BUCKETS]; size_t fixed[N_BUCKETS]; };
-
-inline ClassCfg class_cfg(int K) {
-  ClassCfg c{};
-  if (K <= 40) {
-    c.T[0] = 512; c.T[1] = 256; c.T[2] = 128;
-    c.minb[0] = 1; c.minb[1] = 2; c.minb[2] = 4;
-    if (K <= 5) { c.fixed[0] = em_fixed_bytes<5, 1, 512>(); c.fixed[1] = em_fixed_bytes<5, 1, 256>(); c.fixed[2] = em_fixed_bytes<5, 1, 128>(); }
-    else if (K <= 10) { c.fixed[0] = em_fixed_bytes<5, 2, 512>(); c.fixed[1] = em_fixed_bytes<5, 2, 256>(); c.fixed[2] = em_fixed_bytes<5, 2, 128>(); }
-    else if (K <= 20) { c.fixed[0] = em_fixed_bytes<5, 4, 512>(); c.fixed[1] = em_fixed_bytes<5, 4, 256>(); c.fixed[2] = em_fixed_bytes<5, 4, 128>(); }
-    else { c.fixed[0] = em_fixed_bytes<5, 8, 512>(); c.fixed[1] = em_fixed_bytes<5, 8, 256>(); c.fixed[2] = em_fixed_bytes<5, 8, 128>(); }
-  } else {
-    for (int b = 0; b < N_BUCKETS; ++b) { c.T[b] = 128; c.minb[b] = 3; c.fixed[b] = em_fixed_bytes<8, 8, 128>(); }
-  }
-  return c;
-}
-
+constexpr int SPOT_BYTES = 8, SEED_BYTES = 16;
 constexpr int DEFAULT_MAX_OPTIN = 232448;  // sm_100: 227 KB per CTA
 
+inline int32_t cap_for(size_t fixed, int minb, int max_optin, int seed_cap) {
+  size_t per_cta = ((size_t)228 * 1024) / minb - 1024 - 256;  // 1 KB reserved per CTA + static smem
+  if (per_cta > (size_t)max_optin) per_cta = max_optin;
+  const size_t need = fixed + (size_t)seed_cap * SEED_BYTES;
+  if (per_cta < need + SPOT_BYTES * 64) return 0;
+  return (int32_t)(((per_cta - need) / SPOT_BYTES) & ~(size_t)3);
+}
+
+struct BucketCfg { int T, minb; size_t fixed; int seed_cap; };
+
+template <int KT, int GS>
+inline void fill_cfg(BucketCfg (&c)[N_BUCKETS]) {
+  c[0] = {512, 1, EmLayout<KT, GS, 512>::fixed_bytes(), 2048};
+  c[1] = {256, 2, EmLayout<KT, GS, 256>::fixed_bytes(), 1024};
+  c[2] = {128, STM_EM_MINB_SMALL, EmLayout<KT, GS, 128>::fixed_bytes(), 1024};
+}
+
+inline void class_cfg(int K, uint32_t flags, BucketCfg (&c)[N_BUCKETS]) {
+  if (K <= 5) fill_cfg<5, 1>(c);
+  else if (K <= 10) fill_cfg<5, 2>(c);
+  else if (K <= 20) fill_cfg<5, 4>(c);
+  else if (K <= 40) fill_cfg<5, 8>(c);
+  else for (int b = 0; b < N_BUCKETS; ++b) c[b] = {128, 3, EmLayout<8, 8, 128>::fixed_bytes(), 1024};
+  const int user = (int)((flags >> 20) & 0xff) * 256;  // seed-cap field of the flags
+  for (int b = 0; b < N_BUCKETS; ++b) {
+    if (!(flags & STM_FIT_DEVICE_INIT)) c[b].seed_cap = 0;
+    else if (user) c[b].seed_cap = user;
+  }
+}
+
 template <int KT, int GS, int S, int T, int MINB>
-int launch_em(EmArgs a, int n_genes, cudaStream_t stream) {
+int launch_em(EmArgs a, const BucketCfg& cfg, int n_genes, cudaStream_t stream) {
   using L = EmLayout<KT, GS, T>;
   auto kern = gmm_em_kernel<KT, GS, S, T, MINB>;
   int dev = 0, max_optin = 0;
   STM_CHECK_CUDA(cudaGetDevice(&dev));
   STM_CHECK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const size_t fixed = L::fixed_bytes();
-  a.smem_spots = cap_for(fixed, MINB, max_optin);
+  a.seed_cap = cfg.seed_cap;
+  a.smem_spots = cap_for(fixed, MINB, max_optin, a.seed_cap);
   if (a.smem_spots <= 0) {
     set_last_error("stm_gmm_fit_batched: shared-memory budget too small");
     return STM_ERR_UNSUPPORTED;
   }
-  const size_t smem = fixed + (size_t)a.smem_spots * 12;
+  const size_t smem = fixed + (size_t)a.seed_cap * SEED_BYTES + (size_t)a.smem_spots * SPOT_BYTES;
   STM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<n_genes, T, smem, stream>>>(a);
   STM_CHECK_CUDA(cudaGetLastError());
@@ -825,19 +890,21 @@ int launch_em(EmArgs a, int n_genes, cudaStream_t stream) {
 }
 
 template <int KT, int GS>
-int launch_bucket(const EmArgs& a, int bucket, int n_genes, cudaStream_t st) {
-  if (bucket == 0) return launch_em<KT, GS, 2, 512, 1>(a, n_genes, st);
-  if (bucket == 1) return launch_em<KT, GS, 2, 256, 2>(a, n_genes, st);
-  return launch_em<KT, GS, 2, 128, 4>(a, n_genes, st);
+int launch_bucket(const EmArgs& a, const BucketCfg (&c)[N_BUCKETS], int bucket, int n_genes, cudaStream_t st) {
+  if (bucket == 0) return launch_em<KT, GS, 2, 512, 1>(a, c[0], n_genes, st);
+  if (bucket == 1) return launch_em<KT, GS, 2, 256, 2>(a, c[1], n_genes, st);
+  return launch_em<KT, GS, STM_EM_S_SMALL, 128, STM_EM_MINB_SMALL>(a, c[2], n_genes, st);
 }
 
 int launch_class(const EmArgs& a, int bucket, int n_genes, cudaStream_t st) {
   const int K = a.K;
-  if (K <= 5) return launch_bucket<5, 1>(a, bucket, n_genes, st);
-  if (K <= 10) return launch_bucket<5, 2>(a, bucket, n_genes, st);
-  if (K <= 20) return launch_bucket<5, 4>(a, bucket, n_genes, st);
-  if (K <= 40) return launch_bucket<5, 8>(a, bucket, n_genes, st);
-  return launch_em<8, 8, 1, 128, 3>(a, n_genes, st);
+  BucketCfg c[N_BUCKETS];
+  class_cfg(K, a.flags, c);
+  if (K <= 5) return launch_bucket<5, 1>(a, c, bucket, n_genes, st);
+  if (K <= 10) return launch_bucket<5, 2>(a, c, bucket, n_genes, st);
+  if (K <= 20) return launch_bucket<5, 4>(a, c, bucket, n_genes, st);
+  if (K <= 40) return launch_bucket<5, 8>(a, c, bucket, n_genes, st);
+  return launch_em<8, 8, 1, 128, 3>(a, c[bucket], n_genes, st);
 }
 
 // auxiliary streams so the buckets of one call overlap (fork/join on the caller's stream)
@@ -867,7 +934,7 @@ int get_aux(AuxStreams** out) {
 }  // namespace
 }  // namespace stm
 
-extern "C" int stm_gmm_fit_plan(const int64_t* col_ptr_host, int32_t G, int32_t K,
+extern "C" int stm_gmm_fit_plan(const int64_t* col_ptr_host, int32_t G, int32_t K, uint32_t flags,
                                 int32_t* gene_order_host, int32_t* bucket_counts_host) {
   using namespace stm;
   STM_CHECK_ARG(G >= 0, "G < 0");
@@ -878,9 +945,10 @@ extern "C" int stm_gmm_fit_plan(const int64_t* col_ptr_host, int32_t G, int32_t 
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
     return (col_ptr_host[a + 1] - col_ptr_host[a]) > (col_ptr_host[b + 1] - col_ptr_host[b]);
   });
-  const ClassCfg cfg = class_cfg(K);
-  const int32_t cap1 = cap_for(cfg.fixed[1], cfg.minb[1], DEFAULT_MAX_OPTIN);
-  const int32_t cap2 = cap_for(cfg.fixed[2], cfg.minb[2], DEFAULT_MAX_OPTIN);
+  BucketCfg cfg[N_BUCKETS];
+  class_cfg(K, flags, cfg);
+  const int32_t cap1 = cap_for(cfg[1].fixed, cfg[1].minb, DEFAULT_MAX_OPTIN, cfg[1].seed_cap);
+  const int32_t cap2 = cap_for(cfg[2].fixed, cfg[2].minb, DEFAULT_MAX_OPTIN, cfg[2].seed_cap);
   int32_t n0 = 0, n1 = 0, n2 = 0;
   for (int32_t i = 0; i < G; ++i) {
     const int64_t n = col_ptr_host[order[i] + 1] - col_ptr_host[order[i]];
@@ -924,6 +992,9 @@ extern "C" int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_id
   a.out_w = out_w; a.out_mu = out_mu; a.out_cov = out_cov; a.out_n_iter = out_n_iter;
   a.out_converged = out_converged; a.out_lb = out_lower_bound; a.out_status = out_status;
   a.G = G; a.K = K; a.max_iter = max_iter; a.flags = flags; a.reg_covar = reg_covar; a.tol = tol; a.seed = seed;
+  const int user_lloyd = (int)((flags >> 8) & 0xff), user_cand = (int)((flags >> 16) & 0xf);
+  a.km_max_iter = user_lloyd ? (user_lloyd == 255 ? KM_MAX_ITER : user_lloyd) : STM_KM_DEFAULT_LLOYD;
+  a.km_cand = user_cand ? (user_cand == 15 ? 2 + (int)floor(log((double)K)) : user_cand) : STM_KM_DEFAULT_CAND;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int n_active = 0;
   for (int b = 0; b < N_BUCKETS; ++b) n_active += counts[b] > 0;

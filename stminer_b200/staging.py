@@ -138,20 +138,21 @@ class DeviceSpotMatrix:
         self._up = up
         self.h2d_bytes = sum(a.nbytes for a in (sm.col_ptr, sm.row_idx, sm.val, sm.spot_x, sm.spot_y))
 
-    def plan(self, K: int):
+    def plan(self, K: int, flags: int = 0):
         """(gene_order CUDA tensor, bucket_counts host int32[3]) from ``stm_gmm_fit_plan`` for K components."""
         from . import _lib
-        if K not in self._plans:
+        key = (K, flags & ~1)   # the device-init fields move the bucket boundaries
+        if key not in self._plans:
             lib = _lib.load()
             G = self.host.n_genes
             col = np.ascontiguousarray(self.host.col_ptr, dtype=np.int64)
             order = np.empty(max(G, 1), dtype=np.int32)
             buckets = np.zeros(3, dtype=np.int32)
-            _lib.check(lib.stm_gmm_fit_plan(col.ctypes.data, G, int(K), order.ctypes.data, buckets.ctypes.data),
-                       "stm_gmm_fit_plan")
-            self._plans[K] = (self._up(order[:G]), buckets)
+            _lib.check(lib.stm_gmm_fit_plan(col.ctypes.data, G, int(K), int(flags), order.ctypes.data,
+                                            buckets.ctypes.data), "stm_gmm_fit_plan")
+            self._plans[key] = (self._up(order[:G]), buckets)
             self.h2d_bytes += order[:G].nbytes
-        return self._plans[K]
+        return self._plans[key]
 
     @property
     def n_genes(self) -> int:

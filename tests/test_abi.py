@@ -52,12 +52,14 @@ def test_fit_plan_orders_by_nnz_and_buckets():
     col = np.concatenate([[0], np.cumsum(nnz)]).astype(np.int64)
     order = np.empty(len(nnz), dtype=np.int32)
     buckets = np.zeros(3, dtype=np.int32)
-    assert lib.stm_gmm_fit_plan(col.ctypes.data, len(nnz), 20, order.ctypes.data, buckets.ctypes.data) == 0
+    assert lib.stm_gmm_fit_plan(col.ctypes.data, len(nnz), 20, 0, order.ctypes.data, buckets.ctypes.data) == 0
     assert (np.diff(nnz[order]) <= 0).all()
     assert sorted(order.tolist()) == list(range(len(nnz)))
     assert buckets.sum() == len(nnz)
-    # small bucket holds genes that fit 4 CTAs/SM staging (~4.3k spots), medium ~9k
-    small = nnz[order[buckets[0] + buckets[1]:]]
-    medium = nnz[order[buckets[0]:buckets[0] + buckets[1]]]
-    assert small.max() < 4500 and (medium > small.max()).all() and medium.max() < 9500
-    assert set(nnz[order[:buckets[0]]].tolist()) == {30000, 12000, 100000}
+    # 8-byte staged records: the small bucket (4 CTAs/SM) holds ~6.5k spots, the medium one (2 CTAs/SM) ~13k
+    assert buckets.tolist() == [2, 1, 5]
+    assert set(nnz[order[:2]].tolist()) == {30000, 100000} and nnz[order[2]] == 12000
+    # with the device init a seed area is reserved, which lowers the boundaries (6000 no longer fits 4 CTAs/SM)
+    assert lib.stm_gmm_fit_plan(col.ctypes.data, len(nnz), 20, _lib.fit_flags(device_init=True),
+                                order.ctypes.data, buckets.ctypes.data) == 0
+    assert buckets.tolist() == [3, 1, 4]
