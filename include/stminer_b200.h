@@ -115,6 +115,14 @@ int stm_gmm_fit_plan(const int64_t* col_ptr_host, int32_t G, int32_t K, uint32_t
 int stm_gmm_dist_pairs(const double* w, const double* mu, const double* cov, int32_t G, int32_t K,
                        int64_t pair_begin, int64_t pair_end, double* out, void* stream);
 
+/*
+ * Exact linear-sum-assignment cost of B caller-supplied K x K cost matrices (row-major float64, device),
+ * one warp per matrix.  Replaces linear_sum STMiner/Algorithm/algorithm.py:10-26
+ * (scipy.optimize.linear_sum_assignment + cost[row, col].sum()).  out[B] float64; NaN when a matrix holds
+ * non-finite entries (scipy raises ValueError there).
+ */
+int stm_lsap_batched(const double* cost, int32_t K, int64_t B, double* out, void* stream);
+
 /* Mirror a full pair vector (length G(G-1)/2) into a dense symmetric G x G float64 matrix with zero
  * diagonal (distance.py:93-98). */
 int stm_gmm_dist_fill_square(const double* pairs, int32_t G, double* out_square, void* stream);
@@ -126,6 +134,34 @@ int stm_gmm_dist_fill_square(const double* pairs, int32_t G, double* out_square,
 int stm_gmm_dist_one_vs_all(const double* qw, const double* qmu, const double* qcov,
                             const double* w, const double* mu, const double* cov,
                             int32_t G, int32_t K, double* out, void* stream);
+
+/*
+ * Batched exact spot-level EMD (squared-Euclidean cost on integer grid coordinates) between one
+ * source image and G target images.  One CTA per target; integer network simplex, costs computed on the fly.
+ *
+ * Replaces: calculate_ot_distance     STMiner/Algorithm/distance.py:191-202 (ot.dist + ot.emd2, POT 0.9.1)
+ *           the loop of spatial_high_variable_genes  STMiner/SPFinder.py:285-299
+ *
+ *   src_x, src_y [n] int32, src_mass[n] float64 (positive, any scale — normalised inside as a/sum(a))
+ *   tgt_ptr[G+1] int64, tgt_x, tgt_y int32, tgt_mass float64 (positive; normalised per target)
+ *   max_tgt      largest target support in the batch; order[G] optional processing order (largest first)
+ *   max_iter     pivot limit (reference: numItermax=200000); block_size: arcs priced per block search step,
+ *                0 = sqrt(n*m) as LEMON/POT
+ *   workspace    device scratch of at least stm_emd_workspace_bytes(n_src, max_tgt, n_ctas) bytes; n_ctas CTAs
+ *                (one problem at a time each) pull problems from a queue
+ *   out_cost[G] float64 = sum_ij G_ij * M_ij;  out_iters[G] (nullable) pivots;  out_status[G]:
+ *     0 optimal, 1 iteration limit reached (POT returns the current, sub-optimal value with a warning),
+ *     2 empty image, 3 problem does not fit one CTA's shared memory / int16 coordinate span / int32 potentials
+ *     (out_cost = NaN), 4-5 internal limits (cycle longer than 2048 arcs, unbounded ray).
+ */
+int64_t stm_emd_workspace_bytes(int32_t n_src, int64_t max_tgt, int32_t n_ctas);
+int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
+                          const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
+                          const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
+                          int64_t max_iter, int32_t block_size,
+                          void* workspace, int64_t workspace_bytes, int32_t n_ctas,
+                          double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream);
+
 
 /*
  * Measurement utility: FP32 FMA-pipe peak micro-benchmark used as the roofline denominator of the EM

@@ -104,3 +104,92 @@ def distribution_distance(first_gmm, second_gmm, device=None) -> float:
     """Drop-in for ``distribution_distance`` (distance.py:13-36) — a batch of one pair."""
     _, W, MU, COV = stack_gmms({"a": first_gmm, "b": second_gmm})
     return float(gmm_pair_distances(W, MU, COV, device=device).cpu().numpy()[0])
+
+
+# ---------------------------------------------------------------------------------------------------
+# Spot-level exact EMD (distance.py:179-202 of the reference)
+# ---------------------------------------------------------------------------------------------------
+def csr_to_support(img):
+    """The staging of ``calculate_ot_distance`` (distance.py:192-199) for one sparse (x, y) image:
+    supports = coordinates of the stored positive entries (CSR order), masses = ``data[data > 0]`` (the
+    kernel divides by their sum, which equals ``data.sum()`` for the non-negative images the reference builds)."""
+    coo = img.tocsr().tocoo()
+    keep = coo.data > 0
+    return (coo.row[keep].astype(np.int32), coo.col[keep].astype(np.int32), coo.data[keep].astype(np.float64))
+
+
+def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, device=None, return_iters: bool = False):
+    """Exact EMD between one source support ``(x, y, mass)`` and every target support of ``targets``.
+
+    Returns ``(cost[G] float64, status[G] int32)`` as numpy arrays (+ pivots with ``return_iters``).
+    ``max_iter`` mirrors ``numItermax=200000`` of the reference (distance.py:201): a problem that hits it
+    reports status 1 and the cost of its current basis, as POT does.
+    """
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    device = torch.device(device if device is not None else "cuda")
+    G = len(targets)
+    sx, sy, sm = (np.ascontiguousarray(src[0], dtype=np.int32), np.ascontiguousarray(src[1], dtype=np.int32),
+                  np.ascontiguousarray(src[2], dtype=np.float64))
+    sizes = np.array([len(t[0]) for t in targets], dtype=np.int64)
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    cat = lambda k, dt: (np.concatenate([np.asarray(t[k], dtype=dt) for t in targets]) if G else np.zeros(0, dtype=dt))
+    tx, ty, tm = cat(0, np.int32), cat(1, np.int32), cat(2, np.float64)
+    if G == 0:
+        out = (np.zeros(0), np.zeros(0, dtype=np.int32))
+        return out + (np.zeros(0, dtype=np.int64),) if return_iters else out
+    if len(sx) == 0:
+        out = (np.zeros(G), np.full(G, 2, dtype=np.int32))
+        return out + (np.zeros(G, dtype=np.int64),) if return_iters else out
+    max_tgt = int(sizes.max())
+    order = np.argsort(-sizes, kind="stable").astype(np.int32)      # largest problems first
+    up = lambda a: torch.from_numpy(a).to(device)
+    d = [up(a) for a in (sx, sy, sm, ptr, tx, ty, tm, order)]
+    with torch.cuda.device(device):
+        props = torch.cuda.get_device_properties(device)
+        nodes = len(sx) + max_tgt + 1
+        smem = nodes * 18 + 4 * 2048 * 2 + 64 + 1024
+        per_sm = max(1, min(8, (227 * 1024) // smem))
+        n_ctas = int(min(G, props.multi_processor_count * per_sm))
+        ws_bytes = int(lib.stm_emd_workspace_bytes(len(sx), max_tgt, n_ctas))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        cost = torch.empty(G, dtype=torch.float64, device=device)
+        status = torch.empty(G, dtype=torch.int32, device=device)
+        iters = torch.empty(G, dtype=torch.int64, device=device)
+        st = lib.stm_emd_spots_batched(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), len(sx), _lib.ptr(d[3]),
+                                       _lib.ptr(d[4]), _lib.ptr(d[5]), _lib.ptr(d[6]), G, max_tgt, _lib.ptr(d[7]),
+                                       int(max_iter), int(block_size), _lib.ptr(ws), ws_bytes, n_ctas,
+                                       _lib.ptr(cost), _lib.ptr(status), _lib.ptr(iters), _lib.current_stream_ptr())
+    _lib.check(st, "stm_emd_spots_batched")
+    out = (cost.cpu().numpy(), status.cpu().numpy())
+    return out + (iters.cpu().numpy(),) if return_iters else out
+
+
+def ot_distances_to_source(source, targets, max_iter: int = 200000, device=None):
+    """EMD from one sparse image to each image of ``targets`` (the loop of SPFinder.py:285-299)."""
+    return emd_batched(csr_to_support(source), [csr_to_support(t) for t in targets], max_iter=max_iter, device=device)
+
+
+def calculate_ot_distance(source, target, device=None) -> float:
+    """Drop-in for ``calculate_ot_distance`` (distance.py:191-202)."""
+    cost, status = ot_distances_to_source(source, [target], device=device)
+    if status[0] >= 2:
+        raise ValueError("EMD failed with status %d (2 = empty image, 3 = problem too large for the on-chip solver)"
+                         % int(status[0]))
+    return float(cost[0])
+
+
+def build_ot_distance_array(csr_dict, gene_list=None, device=None):
+    """Drop-in for ``build_ot_distance_array`` (distance.py:179-188): symmetric DataFrame of pairwise spot EMDs;
+    row i is one batched launch (source = gene i, targets = genes j > i)."""
+    genes = list(gene_list) if gene_list is not None else list(csr_dict.keys())
+    n = len(genes)
+    sup = [csr_to_support(csr_dict[g]) for g in genes]
+    D = np.zeros((n, n), dtype=np.float64)
+    for i in range(n - 1):
+        cost, status = emd_batched(sup[i], sup[i + 1:], device=device)
+        if (status >= 2).any():
+            raise ValueError("EMD failed for a pair involving gene %s" % genes[i])
+        D[i, i + 1:] = cost
+        D[i + 1:, i] = cost
+    return pd.DataFrame(D, index=genes, columns=genes)

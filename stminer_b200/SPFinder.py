@@ -1,0 +1,346 @@
+"""``SPFinder`` — drop-in façade of the reference's ``STMiner/SPFinder.py`` for the hot path.
+
+Method names, arguments, defaults, attributes and error behaviour follow the reference; the bodies of the
+three hot methods are re-plumbed onto the CUDA library:
+
+* ``fit_pattern``                  -> one batched EM launch        (reference: SPFinder.py:337-398)
+* ``build_distance_array('gmm')``  -> one batched pair launch      (reference: SPFinder.py:424-439)
+* ``spatial_high_variable_genes``  -> one batched spot-EMD launch  (reference: SPFinder.py:251-326)
+
+Everything else here is host glue (preprocessing restatements of the scanpy calls, DataFrame assembly).
+Plotting, GUI, BMK/GEM readers, image patterns are outside the hot path ("out of scope").
+"""
+from __future__ import annotations
+
+import logging
+from collections import Counter
+from typing import Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+from scipy import sparse
+from scipy.sparse import csr_matrix
+from scipy.stats import zscore
+
+from .adata_lite import AnnDataLite, spot_matrix_from_adata
+from .Algorithm.algorithm import cluster
+from .Algorithm.distance import (build_gmm_distance_array, build_ot_distance_array, compare_gmm_distance,
+                                 ot_distances_to_source)
+from .Algorithm.distribution import fit_gmms
+from .IO.IOUtil import merge_bin_coordinate
+
+logger = logging.getLogger(__name__)
+
+
+def scale_array(exp_matrix: np.ndarray, total_count: np.ndarray) -> np.ndarray:
+    """SPFinder.py:32-38."""
+    total_sum = np.sum(exp_matrix)
+    if total_sum == 0:
+        return np.zeros_like(total_count)
+    return exp_matrix * (100 / total_sum)
+
+
+def _n_nonzero(X, axis):
+    if sparse.issparse(X):
+        return np.asarray((X > 0).sum(axis=axis)).ravel()
+    return np.asarray((np.asarray(X) > 0).sum(axis=axis)).ravel()
+
+
+class SPFinder:
+    def __init__(self, adata=None):
+        self.adata = None
+        self.patterns = None
+        self.genes_distance_array = None
+        self.filtered_distance_array = None
+        self.genes_labels = None
+        self.kmeans_fit_result = None
+        self.mds_features = None
+        self.image_gmm = None
+        self.global_distance = None
+        self.all_labels = None
+        self.custom_pattern = None
+        self.csr_dict = {}
+        self.patterns_matrix_dict = {}
+        self.patterns_binary_matrix_dict = {}
+        self._highly_variable_genes = []
+        self._gene_expression_edge = {}
+        self._scope = None
+        self.device = None           # CUDA device of the hot path (None = current device)
+        self.seed = 0                # seed of the on-device mixture initialisation
+        if adata is not None:
+            self.set_adata(adata)
+
+    # ------------------------------------------------------------------ data
+    def set_adata(self, adata) -> None:
+        """SPFinder.py:77-99."""
+        self.adata = adata
+        has_obs_coordinates = "x" in self.adata.obs and "y" in self.adata.obs
+        if has_obs_coordinates:
+            if "spatial" not in self.adata.obsm:
+                self.adata.obsm["spatial"] = self.adata.obs[["x", "y"]].to_numpy()
+        elif "spatial" in self.adata.obsm:
+            position = np.asarray(self.adata.obsm["spatial"])
+            if len(position.shape) != 2 or position.shape[1] < 2:
+                raise ValueError('adata.obsm["spatial"] must be a 2D array with at least two columns.')
+            self.adata.obs["x"] = merge_bin_coordinate(position[:, 0], position[:, 0].min(), bin_size=1)
+            self.adata.obs["y"] = merge_bin_coordinate(position[:, 1], position[:, 1].min(), bin_size=1)
+        else:
+            raise ValueError('AnnData must contain either obs["x"] and obs["y"] or obsm["spatial"].')
+        self._scope = (0, max(self.adata.obs["y"].max(), self.adata.obs["x"].max()))
+
+    def read_h5ad(self, file: str, amplification: int = 1, bin_size: int = 1, merge_bin: bool = False) -> None:
+        """SPFinder.py:101-122 -> IO/read_h5ad.py:16-111."""
+        from .IO.read_h5ad import read_h5ad
+        self.set_adata(read_h5ad(file, amplification=amplification, bin_size=bin_size, merge_bin=merge_bin))
+
+    def merge_bin(self, bin_width: int) -> None:
+        """SPFinder.py:128-151: re-label obs.x / obs.y in place, min-shifted."""
+        self.adata.obs["x"] = merge_bin_coordinate(self.adata.obs["x"], self.adata.obs["x"].min(), bin_size=bin_width)
+        self.adata.obs["y"] = merge_bin_coordinate(self.adata.obs["y"], self.adata.obs["y"].min(), bin_size=bin_width)
+        self._scope = (0, max(self.adata.obs["y"].max(), self.adata.obs["x"].max()))
+
+    # ------------------------------------------------------------------ preprocessing (scanpy restatements)
+    def preprocess(self, normalize: bool, exclude_highly_expressed: bool, log1p: bool, min_cells: int,
+                   min_genes: int, n_top_genes: int = 2000) -> None:
+        """SPFinder.py:400-422.  In-place, like the scanpy calls of the reference:
+        ``filter_genes(min_cells)`` -> ``filter_cells(min_genes)`` -> [``highly_variable_genes``] ->
+        [``normalize_total``] -> [``log1p``].  A real AnnData with scanpy installed goes through scanpy."""
+        a = self.adata
+        if not isinstance(a, AnnDataLite):
+            import scanpy as sc
+            sc.pp.filter_genes(a, min_cells=min_cells)
+            sc.pp.filter_cells(a, min_genes=min_genes)
+            sc.pp.highly_variable_genes(a, flavor="seurat_v3", n_top_genes=n_top_genes)
+            self._highly_variable_genes = list(a.var[a.var["highly_variable"]].index)
+            if normalize:
+                sc.pp.normalize_total(a, exclude_highly_expressed=exclude_highly_expressed)
+            if log1p:
+                sc.pp.log1p(a)
+            return
+        n_cells = _n_nonzero(a.X, 0)
+        a.var["n_cells"] = n_cells
+        a._subset(var_mask=n_cells >= min_cells)                      # sc.pp.filter_genes
+        n_genes = _n_nonzero(a.X, 1)
+        a.obs["n_genes"] = n_genes
+        a._subset(obs_mask=n_genes >= min_genes)                      # sc.pp.filter_cells
+        if n_top_genes is not None and n_top_genes > 0 and n_top_genes < a.n_vars:
+            self._highly_variable_genes = self._seurat_v3_hvg(n_top_genes)
+        else:
+            self._highly_variable_genes = list(a.var.index)
+        if normalize:                                                 # sc.pp.normalize_total(target_sum=None)
+            if exclude_highly_expressed:
+                raise NotImplementedError("exclude_highly_expressed needs scanpy (not in this image)")
+            X = a.X.tocsr().astype(np.float64) if sparse.issparse(a.X) else np.asarray(a.X, dtype=np.float64)
+            counts = np.asarray(X.sum(axis=1)).ravel()
+            target = np.median(counts[counts > 0])
+            scale = np.where(counts > 0, target / np.where(counts > 0, counts, 1.0), 1.0)
+            a.X = sparse.diags(scale) @ X if sparse.issparse(X) else X * scale[:, None]
+        if log1p:                                                     # sc.pp.log1p
+            if sparse.issparse(a.X):
+                a.X = a.X.copy(); a.X.data = np.log1p(a.X.data)
+            else:
+                a.X = np.log1p(a.X)
+
+    def _seurat_v3_hvg(self, n_top_genes: int) -> List[str]:
+        """Variance-ranked stand-in for scanpy's ``seurat_v3`` flavour (its loess fit needs scikit-misc, absent
+        here; the ranking is consumed only when ``n_top_genes > 0``, SPFinder.py:386-387)."""
+        X = self.adata.X
+        if sparse.issparse(X):
+            mean = np.asarray(X.mean(axis=0)).ravel()
+            var = np.asarray(X.multiply(X).mean(axis=0)).ravel() - mean ** 2
+        else:
+            mean, var = np.mean(X, axis=0), np.var(X, axis=0)
+        disp = var / np.maximum(mean, 1e-12)
+        order = np.argsort(-disp, kind="stable")[:n_top_genes]
+        mask = np.zeros(self.adata.n_vars, dtype=bool); mask[order] = True
+        self.adata.var["highly_variable"] = mask
+        return list(self.adata.var.index[mask])
+
+    # ------------------------------------------------------------------ spot-level EMD path
+    def get_genes_csr_array(self, min_cells: int, min_genes: int = 1, normalize: bool = True,
+                            exclude_highly_expressed: bool = False, log1p: bool = False, vmax: float = 100.0,
+                            gene_list: Optional[List[str]] = None) -> None:
+        """SPFinder.py:178-249: preprocess in place, then one sparse (x, y) image per gene with the values
+        clipped at the ``vmax`` percentile (taken over ALL spots, zeros included, and only if it is > 0)."""
+        self.csr_dict = {}
+        self.preprocess(normalize, exclude_highly_expressed, log1p, min_cells, min_genes)
+        arr_list = gene_list if gene_list is not None else list(self.adata.var.index)
+        names = np.asarray(self.adata.var_names)
+        counts = Counter(names.tolist())
+        first = {}
+        for i, n in enumerate(names):
+            first.setdefault(n, i)
+        x = np.asarray(self.adata.obs["x"].values).ravel()
+        y = np.asarray(self.adata.obs["y"].values).ravel()
+        Xc = self.adata.X.tocsc() if sparse.issparse(self.adata.X) else None
+        warned = set()
+        for gene in arr_list:
+            if counts.get(gene, 0) != 1:           # SPFinder.py:225-234 (duplicates) / KeyError on unknown genes
+                if gene not in warned:
+                    warned.add(gene)
+                    logger.warning("Gene [%s] has more than one index, skip.", gene)
+                continue
+            try:
+                j = first[gene]
+                if Xc is not None:
+                    data = np.asarray(Xc[:, j].todense()).ravel().astype(np.float64)
+                else:
+                    data = np.asarray(self.adata.X[:, j], dtype=np.float64).ravel().copy()
+                p = np.percentile(data, vmax)
+                if p > 0:
+                    data[data > p] = p
+                self.csr_dict[gene] = csr_matrix((data, (x, y)))
+            except Exception:
+                logger.error("Error when parsing gene %s.", gene, exc_info=True)
+
+    def spatial_high_variable_genes(self, vmax: float = 100.0, thread: int = 1) -> None:
+        """SPFinder.py:251-326: exact EMD between the per-spot total image and every gene image, then
+        ``DataFrame[Gene, Distance, z-score]`` sorted by Distance descending.  ``thread`` is accepted for
+        compatibility; all genes go into one batched device launch."""
+        if len(self.csr_dict) == 0:
+            self.get_genes_csr_array(min_cells=50, vmax=vmax, normalize=True)
+        data = np.array(self.adata.X.sum(axis=1)).flatten().astype(np.float64)
+        data[data > np.percentile(data, vmax)] = np.percentile(data, vmax)
+        row_indices = np.array(self.adata.obs["x"].values).flatten()
+        column_indices = np.array(self.adata.obs["y"].values).flatten()
+        global_matrix = csr_matrix((data, (row_indices, column_indices)))
+        keys = list(self.csr_dict.keys())
+        dist, status = ot_distances_to_source(global_matrix, [self.csr_dict[k] for k in keys], device=self.device)
+        distance_dict = {}
+        for k, d, s in zip(keys, dist, status):
+            if s == 2:                                # empty image: POT raises, the reference logs and skips
+                logger.error("Failed to compute OT distance for gene %s.", k)
+                continue
+            distance_dict[k] = d
+        self.global_distance = pd.DataFrame(list(distance_dict.items()), columns=["Gene", "Distance"]) \
+            .sort_values(by="Distance", ascending=False)
+        self.global_distance["z-score"] = zscore(np.log1p(self.global_distance["Distance"]))
+
+    # ------------------------------------------------------------------ mixture fit
+    def fit_pattern(self, n_top_genes: int = -1, n_comp: int = 20, normalize: bool = False,
+                    exclude_highly_expressed: bool = False, log1p: bool = False, min_cells: int = 20,
+                    gene_list: Optional[List[str]] = None, remove_low_exp_spots: bool = False) -> None:
+        """SPFinder.py:337-398."""
+        self.preprocess(normalize=normalize, exclude_highly_expressed=exclude_highly_expressed, log1p=log1p,
+                        min_cells=min_cells, min_genes=1, n_top_genes=n_top_genes)
+        if gene_list is not None and isinstance(gene_list, list) and len(gene_list) > 0:
+            gene_to_fit = gene_list
+        elif n_top_genes > 0:
+            gene_to_fit = self._highly_variable_genes
+        else:
+            gene_to_fit = list(self.adata.var.index)
+        try:
+            self.patterns = fit_gmms(self.adata, gene_to_fit, n_comp=n_comp,
+                                     remove_low_exp_spots=remove_low_exp_spots, seed=self.seed, device=self.device)
+        except Exception:
+            logger.error("Failed to fit patterns.", exc_info=True)
+
+    def compare_gene_to_genes(self, gene_name: str) -> pd.DataFrame:
+        """SPFinder.py:165-176."""
+        return compare_gmm_distance(self.patterns[gene_name], self.patterns, device=self.device)
+
+    # ------------------------------------------------------------------ distances / clustering
+    def build_distance_array(self, method: str = "gmm", gene_list: Optional[List[str]] = None) -> None:
+        """SPFinder.py:424-439 -> services/spfinder_analysis.py:18-35."""
+        if gene_list is None:
+            gene_list = list(self.adata.var.index)
+        if method == "gmm":
+            self.genes_distance_array = build_gmm_distance_array(self.patterns, device=self.device)
+        elif method == "ot":
+            self.genes_distance_array = build_ot_distance_array(self.csr_dict, gene_list, device=self.device)
+        elif method in ("mse", "cs"):
+            raise NotImplementedError("method '%s' is a dense-grid O(G^2 XY) path outside the B200 hot path "
+                                      "(SURVEY.md §2 row 2)" % method)
+        else:
+            raise ValueError("Unknown method, method should be one of gmm, mse, cs, ot")
+
+    def cluster_gene(self, n_clusters: int, mds_components: int = 20, use_highly_variable_gene: bool = False,
+                     n_top_genes: int = 500) -> None:
+        """SPFinder.py:526-539 -> services/spfinder_analysis.py:38-62."""
+        if use_highly_variable_gene:
+            df = pd.DataFrame(self.genes_distance_array.mean(axis=1), columns=["mean"])
+            df = df.sort_values(by="mean", ascending=False)
+            hv_gene_list = list(df[:n_top_genes].index)
+            self.filtered_distance_array = self.genes_distance_array.loc[hv_gene_list, hv_gene_list]
+            target = self.filtered_distance_array
+        else:
+            target = self.genes_distance_array
+        self.genes_labels, self.kmeans_fit_result, self.mds_features = cluster(
+            target, n_clusters=n_clusters, mds_components=mds_components)
+
+    # ------------------------------------------------------------------ pattern voting
+    def get_pattern_array(self, vote_rate: float = 0.0, mode: str = "vote") -> None:
+        """SPFinder.py:441-457."""
+        self.patterns_binary_matrix_dict = {}
+        if mode == "vote":
+            for label in set(self.genes_labels["labels"]):
+                gene_list = list(self.genes_labels[self.genes_labels["labels"] == label]["gene_id"])
+                binary_arr, total_count = self._genes_to_pattern(gene_list, vote_rate)
+                self.patterns_matrix_dict[label] = total_count
+                self.patterns_binary_matrix_dict[label] = binary_arr
+        elif mode == "test":
+            pass                                     # unimplemented in the reference as well (SPFinder.py:452-455)
+        else:
+            raise ValueError("mode should be vote or test")
+
+    def _genes_to_pattern(self, gene_list: List[str], vote_rate: float):
+        """SPFinder.py:459-489 on the CSC staging: per gene the int16 grid scaled to sum 100, accumulated;
+        cells where at least ``vote_rate`` of the genes are expressed are kept."""
+        sm = spot_matrix_from_adata(self.adata, gene_list)
+        shape = (int(np.asarray(self.adata.obs["x"]).max()) + 1, int(np.asarray(self.adata.obs["y"]).max()) + 1)
+        total_count = np.zeros(shape)
+        votes = np.zeros(shape)
+        for g in range(sm.n_genes):
+            a, b = int(sm.col_ptr[g]), int(sm.col_ptr[g + 1])
+            r = sm.row_idx[a:b]
+            w = np.trunc(sm.val[a:b])
+            # AlgUtils.py:8-36 keeps negative cells in the grid; nonzero cells vote (np.nonzero, SPFinder.py:471)
+            nz = w != 0
+            xs, ys, w = sm.spot_x[r][nz], sm.spot_y[r][nz], w[nz]
+            s = w.sum()
+            if s != 0:
+                np.add.at(total_count, (xs, ys), w * (100 / s))
+            votes[xs, ys] += 1
+        vote_array = (votes > 0) & (votes / len(gene_list) >= vote_rate)
+        total_count *= vote_array
+        binary_arr = np.where(total_count != 0, 1, total_count)
+        return binary_arr, total_count
+
+    def get_custom_pattern(self, gene_list: List[str], n_components: int = 20, vote_rate: float = 0.0,
+                           mode: str = "vote") -> None:
+        """SPFinder.py:491-524: mixture of the voted pattern image, fitted on the device."""
+        if mode == "vote":
+            _, total_count = self._genes_to_pattern(gene_list, vote_rate)
+            self.custom_pattern = _fit_image(np.round(total_count).astype(np.int32), n_components, self.seed, self.device)
+        elif mode == "test":
+            pass
+        else:
+            raise ValueError("mode should be vote or test")
+
+    def get_all_labels(self) -> None:
+        """SPFinder.py:556-570: nearest voted pattern (by GMM distance) of every fitted gene."""
+        df_list = []
+        for i in self.patterns_binary_matrix_dict:
+            gmm = _fit_image(np.asarray(self.patterns_binary_matrix_dict[i], dtype=np.int32), 20, self.seed, self.device)
+            df = compare_gmm_distance(gmm, self.patterns, device=self.device)
+            df.rename(columns={0: i}, inplace=True)
+            df_list.append(df)
+        total = pd.concat(df_list, axis=1)
+        label = total.idxmin(axis=1)
+        all_labels = pd.DataFrame(label, columns=["label"])
+        all_labels["value"] = [total.loc[g, lab] for g, lab in zip(all_labels.index, all_labels["label"])]
+        self.all_labels = all_labels
+
+
+def _fit_image(image: np.ndarray, n_components: int, seed: int, device):
+    """``get_gmm`` (distribution.py:37-41, max_iter=200 there) for a dense count image, on the device."""
+    from .Algorithm.distribution import fit_spot_matrix, result_to_gmm_dict
+    from .staging import DeviceSpotMatrix, SpotMatrix
+    xs, ys = np.nonzero(image > 0)
+    sm = SpotMatrix(np.array([0, len(xs)], dtype=np.int64), np.arange(len(xs), dtype=np.int32),
+                    image[xs, ys].astype(np.float32), xs.astype(np.int32), ys.astype(np.int32), ["pattern"])
+    res = fit_spot_matrix(DeviceSpotMatrix(sm, device=device), n_components, init=None, max_iter=200, seed=seed)
+    d = result_to_gmm_dict(sm.genes, res.to_host())
+    if "pattern" not in d:
+        raise ValueError("pattern image has fewer distinct spots than components")
+    return d["pattern"]

@@ -45,8 +45,12 @@ SIGNATURES = {
     ]),
     "stm_gmm_fit_plan": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint32, _P, _P]),
     "stm_gmm_dist_pairs": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
+    "stm_lsap_batched": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
     "stm_gmm_dist_fill_square": (C.c_int, [_P, C.c_int32, _P, _P]),
     "stm_gmm_dist_one_vs_all": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
+    "stm_emd_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32]),
+    "stm_emd_spots_batched": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int64, _P,
+                                        C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "stm_bench_fma": (C.c_int, [C.c_int32, C.c_int32, _P, _P]),
 }
 

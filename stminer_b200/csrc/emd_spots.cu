@@ -1,0 +1,412 @@
+// Batched exact spot-level EMD for sm_100a — one CTA per (source image, target image) problem.
+//
+// Restates calculate_ot_distance (STMiner/Algorithm/distance.py:191-202): supports are integer grid
+// coordinates, masses are normalised to 1, the cost is the squared Euclidean distance and the result is
+// the exact transport-LP optimum sum_ij G_ij M_ij that POT's emd2 (network simplex, POT==0.9.1) returns.
+//
+// The solver is a primal network simplex on the bipartite transport graph, arranged for one CTA:
+//   * the n x m cost matrix is never materialised: arc costs come from the coordinates in shared memory;
+//   * masses are scaled to integers (total 2^50), potentials are integers, so every comparison is exact
+//     and the pivot sequence is the one of the CPU oracle (oracle/emd_oracle.c) for the same block size;
+//   * pricing is a block search: the CTA evaluates a block of arcs in parallel and enters the most negative
+//     reduced cost of the first block that has one (LEMON's rule);
+//   * the spanning tree is stored as parent / preorder position / subtree size (uint16) in shared memory, a
+//     subtree being a contiguous segment of the preorder array — the two cycle paths are chased by two
+//     lanes, everything else (leaving-arc search, flow update, potential shift of the re-hung subtree,
+//     preorder re-numbering) is data-parallel over the CTA;
+//   * arc flows (int64) live in a per-CTA slice of a global workspace (touched only along the cycle).
+#include <limits.h>
+#include <math.h>
+
+#include "stm_common.cuh"
+
+namespace stm {
+namespace {
+
+constexpr int EMD_THREADS = 256;
+constexpr int EMD_WARPS = EMD_THREADS / 32;
+constexpr int EMD_MAXPATH = 2048;
+constexpr double EMD_SCALE = 1125899906842624.0;  // 2^50
+constexpr unsigned short NONE16 = 0xffffu;
+
+struct EmdArgs {
+  const int32_t* src_x; const int32_t* src_y; const double* src_mass; int32_t n_src;
+  const int64_t* tgt_ptr; const int32_t* tgt_x; const int32_t* tgt_y; const double* tgt_mass;
+  int32_t G; int32_t cap_nodes;   // shared-memory capacity in nodes
+  int64_t max_iter; int32_t block_size;
+  int64_t* src_int;               // [n_src] integer source masses (prep kernel)
+  int64_t* flow_ws;               // [gridDim.x][cap_nodes]
+  unsigned int* counter;          // dynamic problem queue
+  const int32_t* order;           // optional processing order
+  double* out_cost; int32_t* out_status; int64_t* out_iters;
+};
+
+__device__ __forceinline__ long long shfl_xor_ll(long long v, int o) {
+  return __shfl_xor_sync(FULL_MASK, v, o);
+}
+
+// Deterministic block sum of doubles (fixed strided order + fixed tree).
+__device__ double block_sum(double v, double* s_scr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) s_scr[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < EMD_WARPS; ++w) t += s_scr[w];
+  return t;
+}
+
+// mass[i] / sum * 2^50 rounded to integers; the largest entry absorbs the rounding so the total is exactly 2^50.
+// Single CTA; `out` may be global or shared.
+__device__ void integerize(const double* mass, int n, int64_t* out, double* s_scr, long long* s_ll) {
+  double part = 0.0;
+  for (int i = threadIdx.x; i < n; i += EMD_THREADS) part += mass[i];
+  const double total = block_sum(part, s_scr);
+  long long isum = 0, best = -1;
+  int best_i = 0;
+  for (int i = threadIdx.x; i < n; i += EMD_THREADS) {
+    const long long q = (long long)floor(mass[i] / total * EMD_SCALE + 0.5);
+    out[i] = q;
+    isum += q;
+    if (q > best) { best = q; best_i = i; }
+  }
+  // reduce (sum, argmax with lowest index on ties)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    isum += shfl_xor_ll(isum, o);
+    const long long ob = shfl_xor_ll(best, o);
+    const int oi = __shfl_xor_sync(FULL_MASK, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { s_ll[3 * warp] = isum; s_ll[3 * warp + 1] = best; s_ll[3 * warp + 2] = best_i; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tsum = 0, tb = -1, ti = 0;
+    for (int w = 0; w < EMD_WARPS; ++w) {
+      tsum += s_ll[3 * w];
+      if (s_ll[3 * w + 1] > tb || (s_ll[3 * w + 1] == tb && s_ll[3 * w + 2] < ti)) { tb = s_ll[3 * w + 1]; ti = s_ll[3 * w + 2]; }
+    }
+    out[ti] += (long long)EMD_SCALE - tsum;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(EMD_THREADS) emd_prep_kernel(const double* src_mass, int n, int64_t* src_int) {
+  __shared__ double s_scr[EMD_WARPS];
+  __shared__ long long s_ll[3 * EMD_WARPS];
+  integerize(src_mass, n, src_int, s_scr, s_ll);
+}
+
+__global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int cap = p.cap_nodes;
+  int* s_pi = reinterpret_cast<int*>(smem_raw);                          // [cap]
+  short* s_x = reinterpret_cast<short*>(s_pi + cap);                     // [cap]
+  short* s_y = s_x + cap;                                                // [cap]
+  unsigned short* s_parent = reinterpret_cast<unsigned short*>(s_y + cap);
+  unsigned short* s_pos = s_parent + cap;
+  unsigned short* s_size = s_pos + cap;
+  unsigned short* s_order = s_size + cap;
+  unsigned short* s_tmp = s_order + cap;
+  unsigned short* s_pathA = s_tmp + cap;                                 // [EMD_MAXPATH]
+  unsigned short* s_pathB = s_pathA + EMD_MAXPATH;
+  unsigned short* s_P = s_pathB + EMD_MAXPATH;
+  unsigned short* s_S = s_P + EMD_MAXPATH;
+  __shared__ double s_scr[EMD_WARPS];
+  __shared__ long long s_ll[3 * EMD_WARPS];
+  __shared__ long long s_key[EMD_WARPS];
+  __shared__ int s_i[16];
+  __shared__ long long s_delta;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.n_src;
+  int64_t* flow = p.flow_ws + (size_t)blockIdx.x * cap;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_i[0] = (int)atomicAdd(p.counter, 1u);
+    __syncthreads();
+    const int slot = s_i[0];
+    if (slot >= p.G) break;
+    const int g = p.order ? p.order[slot] : slot;
+    const int64_t t0 = p.tgt_ptr[g];
+    const int m = (int)(p.tgt_ptr[g + 1] - t0);
+    const int N = n + m + 1, root = n + m;
+    if (m <= 0 || n <= 0) {
+      if (tid == 0) { p.out_cost[g] = 0.0; p.out_status[g] = 2; if (p.out_iters) p.out_iters[g] = 0; }
+      continue;
+    }
+    // ---- stage coordinates (relative to the source's first spot), bounding box, capacity checks ----
+    const int ox = p.src_x[0], oy = p.src_y[0];
+    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+    const bool fits = N <= cap && N < 65535 && (int64_t)n * m < 2147483647LL;
+    for (int v = tid; v < n + m; v += EMD_THREADS) {
+      const int x = v < n ? p.src_x[v] : p.tgt_x[t0 + v - n], y = v < n ? p.src_y[v] : p.tgt_y[t0 + v - n];
+      xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
+      if (fits) { s_x[v] = (short)(x - ox); s_y[v] = (short)(y - oy); }
+    }
+    xmin = __reduce_min_sync(FULL_MASK, xmin); xmax = __reduce_max_sync(FULL_MASK, xmax);
+    ymin = __reduce_min_sync(FULL_MASK, ymin); ymax = __reduce_max_sync(FULL_MASK, ymax);
+    if (lane == 0) { s_ll[3 * warp] = ((long long)xmin << 32) | (unsigned)xmax; s_ll[3 * warp + 1] = ((long long)ymin << 32) | (unsigned)ymax; }
+    __syncthreads();
+    for (int w = 0; w < EMD_WARPS; ++w) {
+      xmin = min(xmin, (int)(s_ll[3 * w] >> 32)); xmax = max(xmax, (int)(unsigned)s_ll[3 * w]);
+      ymin = min(ymin, (int)(s_ll[3 * w + 1] >> 32)); ymax = max(ymax, (int)(unsigned)s_ll[3 * w + 1]);
+    }
+    __syncthreads();
+    const long long maxc = (long long)(xmax - xmin) * (xmax - xmin) + (long long)(ymax - ymin) * (ymax - ymin);
+    const long long BIG = (maxc + 1) * (long long)N;
+    const bool coords_ok = (xmax - ox) < 32768 && (ox - xmin) < 32768 && (ymax - oy) < 32768 && (oy - ymin) < 32768;
+    if (!fits || !coords_ok || 2 * BIG + maxc >= 2147483647LL) {   // int32 potentials / int16 coordinates / capacity
+      if (tid == 0) { p.out_cost[g] = nan(""); p.out_status[g] = 3; if (p.out_iters) p.out_iters[g] = 0; }
+      continue;
+    }
+    // ---- integer masses and the initial star basis ----------------------------------------------
+    for (int i = tid; i < n; i += EMD_THREADS) flow[i] = p.src_int[i];
+    integerize(p.tgt_mass + t0, m, flow + n, s_scr, s_ll);
+    for (int v = tid; v < n + m; v += EMD_THREADS) {
+      s_parent[v] = (unsigned short)root; s_order[v + 1] = (unsigned short)v; s_pos[v] = (unsigned short)(v + 1);
+      s_size[v] = 1; s_pi[v] = v < n ? (int)-BIG : (int)BIG;
+    }
+    if (tid == 0) {
+      s_order[0] = (unsigned short)root; s_pos[root] = 0; s_size[root] = (unsigned short)N; s_parent[root] = NONE16;
+      s_pi[root] = 0; flow[root] = 0; s_i[4] = 0;
+    }
+    __syncthreads();
+
+    const int n_arcs = n * m;
+    int B = p.block_size > 0 ? p.block_size : (int)sqrt((double)n_arcs);
+    if (B < 10) B = 10;
+    if (B > n_arcs) B = n_arcs;
+    int next_arc = 0;
+    long long it = 0;
+    int status = 0;
+
+    for (;;) {
+      // ---- entering arc: block search over arcs e = j*n + i ----------------------------------------
+      int scanned = 0, best_e = -1, best_rc = 0;
+      while (scanned < n_arcs) {
+        const int cnt = min(B, n_arcs - scanned);
+        long long key = LLONG_MAX;
+        if (tid < cnt) {
+          int e = next_arc + tid;
+          if (e >= n_arcs) e -= n_arcs;
+          int j = e / n, i = e - j * n;
+          for (int k = tid; k < cnt; k += EMD_THREADS) {
+            const int dx = (int)s_x[i] - (int)s_x[n + j], dy = (int)s_y[i] - (int)s_y[n + j];
+            const int rc = dx * dx + dy * dy + s_pi[i] - s_pi[n + j];
+            const long long kk = ((long long)rc << 32) | (unsigned)k;
+            key = min(key, kk);
+            i += EMD_THREADS;
+            while (i >= n) { i -= n; if (++j >= m) j = 0; }
+          }
+        }
+        for (int o = 16; o > 0; o >>= 1) key = min(key, shfl_xor_ll(key, o));
+        if (lane == 0) s_key[warp] = key;
+        __syncthreads();
+        key = s_key[0];
+#pragma unroll
+        for (int w = 1; w < EMD_WARPS; ++w) key = min(key, s_key[w]);
+        __syncthreads();
+        const int rc = (int)(key >> 32);
+        const int start = next_arc;
+        scanned += cnt;
+        next_arc += cnt;
+        if (next_arc >= n_arcs) next_arc -= n_arcs;
+        if (key != LLONG_MAX && rc < 0) {
+          best_rc = rc;
+          best_e = start + (int)(unsigned)key;
+          if (best_e >= n_arcs) best_e -= n_arcs;
+          break;
+        }
+      }
+      if (best_e < 0) break;                      // optimal
+      if (it >= p.max_iter) { status = 1; break; }
+      ++it;
+      const int ej = best_e / n, ei = best_e - ej * n;
+      const int u_i = ei, u_j = n + ej;
+      // ---- cycle: two lanes walk the endpoints up to the join node --------------------------------
+      if (tid == 0 || tid == 32) {
+        const int from = tid == 0 ? u_i : u_j, other = tid == 0 ? u_j : u_i;
+        unsigned short* path = tid == 0 ? s_pathA : s_pathB;
+        const int po = s_pos[other];
+        int len = 0, v = from;
+        while (true) {
+          const int pv = s_pos[v], sv = s_size[v];
+          if (pv <= po && po < pv + sv) break;
+          if (len < EMD_MAXPATH) path[len] = (unsigned short)v;
+          ++len;
+          v = s_parent[v];
+        }
+        s_i[tid == 0 ? 1 : 2] = len;
+      }
+      __syncthreads();
+      const int lenA = s_i[1], lenB = s_i[2];
+      if (lenA > EMD_MAXPATH || lenB > EMD_MAXPATH) { status = 4; break; }
+      // ---- leaving arc (warp 0): min flow over arcs traversed against their direction; ties resolved by
+      //      the strongly-feasible rule (i side: closest to i; j side wins and takes the one closest to the join)
+      if (warp == 0) {
+        long long dmin = LLONG_MAX;
+        int seq = -1;
+        for (int a = lane; a < lenA; a += 32) {
+          const int v = s_pathA[a];
+          if (v < n) { const long long f = flow[v]; const int sq = lenA - 1 - a; if (f < dmin || (f == dmin && sq > seq)) { dmin = f; seq = sq; } }
+        }
+        for (int b = lane; b < lenB; b += 32) {
+          const int v = s_pathB[b];
+          if (v >= n) { const long long f = flow[v]; const int sq = lenA + b; if (f < dmin || (f == dmin && sq > seq)) { dmin = f; seq = sq; } }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          const long long od = shfl_xor_ll(dmin, o);
+          const int os = __shfl_xor_sync(FULL_MASK, seq, o);
+          if (od < dmin || (od == dmin && os > seq)) { dmin = od; seq = os; }
+        }
+        if (lane == 0) { s_delta = dmin; s_i[3] = seq; }
+      }
+      __syncthreads();
+      const long long delta = s_delta;
+      const int seq = s_i[3];
+      if (seq < 0) { status = 5; break; }        // unbounded: cannot happen for a transport LP
+      const int side = seq >= lenA ? 1 : 0;
+      const int k = side == 0 ? lenA - 1 - seq : seq - lenA;   // leaving arc at path index k of its side
+      const unsigned short* pathX = side == 0 ? s_pathA : s_pathB;
+      const unsigned short* pathY = side == 0 ? s_pathB : s_pathA;
+      const int lenX = side == 0 ? lenA : lenB, lenY = side == 0 ? lenB : lenA;
+      const int q = pathX[k];
+      const int t_in = side == 0 ? u_j : u_i;
+      const int s = s_size[q], a0 = s_pos[q];
+      const int pt = s_pos[t_in];
+      const int ptr = pt < a0 ? pt : pt - s;
+      const int shift = side == 0 ? -best_rc : best_rc;
+      // ---- flow update along the cycle + old flows / positions / sizes of the reversed path --------
+      for (int a = tid; a < lenA; a += EMD_THREADS) { const int v = s_pathA[a]; flow[v] += (v < n) ? -delta : delta; }
+      for (int b = tid; b < lenB; b += EMD_THREADS) { const int v = s_pathB[b]; flow[v] += (v >= n) ? -delta : delta; }
+      for (int t = tid; t <= k; t += EMD_THREADS) { const int v = pathX[t]; s_P[t] = s_pos[v]; s_S[t] = s_size[v]; }
+      // potential shift of the re-hung subtree (a contiguous preorder segment)
+      for (int x = a0 + tid; x < a0 + s; x += EMD_THREADS) s_pi[s_order[x]] += shift;
+      // affected preorder range
+      const int lo = pt < a0 ? pt + 1 : a0, hi = pt < a0 ? a0 + s : pt + 1;
+      for (int x = lo + tid; x < hi; x += EMD_THREADS) s_tmp[x] = s_order[x];
+      __syncthreads();
+      // ---- reversed path: parents, flows, sizes (flows read before anyone overwrites them) ----------
+      {
+        // every thread handles t = tid, tid + T, ...; two passes: read old flows, then write
+        constexpr int MAXT = (EMD_MAXPATH + EMD_THREADS - 1) / EMD_THREADS;
+        long long fo[MAXT];
+#pragma unroll
+        for (int r = 0; r < MAXT; ++r) {
+          const int t = tid + r * EMD_THREADS;
+          fo[r] = (t >= 1 && t <= k) ? flow[pathX[t - 1]] : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < MAXT; ++r) {
+          const int t = tid + r * EMD_THREADS;
+          if (t <= k) {
+            const int v = pathX[t];
+            if (t == 0) { s_parent[v] = (unsigned short)t_in; flow[v] = delta; s_size[v] = (unsigned short)s; }
+            else { s_parent[v] = pathX[t - 1]; flow[v] = fo[r]; s_size[v] = (unsigned short)(s - s_S[t - 1]); }
+          }
+        }
+      }
+      for (int t = k + 1 + tid; t < lenX; t += EMD_THREADS) s_size[pathX[t]] -= (unsigned short)s;
+      for (int t = tid; t < lenY; t += EMD_THREADS) s_size[pathY[t]] += (unsigned short)s;
+      // ---- preorder re-numbering of the affected range ------------------------------------------------
+      for (int x = lo + tid; x < hi; x += EMD_THREADS) {
+        const int v = s_tmp[x];
+        int f;
+        if (x < a0 || x >= a0 + s) {
+          const int xr = x < a0 ? x : x - s;
+          f = xr <= ptr ? xr : xr + s;
+        } else {
+          int l = 0, h = k;   // smallest t with P[t] <= x < P[t] + S[t] (nested intervals)
+          while (l < h) { const int mid = (l + h) >> 1; const int Pm = s_P[mid]; if (Pm <= x && x < Pm + s_S[mid]) h = mid; else l = mid + 1; }
+          const int t = l, Pt = s_P[t];
+          int r;
+          if (t == 0) r = x - Pt;
+          else if (x == Pt) r = s_S[t - 1];
+          else if (x < s_P[t - 1]) r = s_S[t - 1] + 1 + (x - (Pt + 1));
+          else r = x - Pt;
+          f = ptr + 1 + r;
+        }
+        s_order[f] = (unsigned short)v;
+        s_pos[v] = (unsigned short)f;
+      }
+      __syncthreads();
+    }
+    // ---- objective: real tree arcs only ------------------------------------------------------------
+    double part = 0.0;
+    for (int v = tid; v < n + m; v += EMD_THREADS) {
+      const int pr = s_parent[v];
+      const long long f = flow[v];
+      if (pr != root && f != 0) {
+        const int i = v < n ? v : pr, j = v < n ? pr : v;
+        const long long dx = (int)s_x[i] - (int)s_x[j], dy = (int)s_y[i] - (int)s_y[j];
+        part += (double)f * (double)(dx * dx + dy * dy);
+      }
+    }
+    const double total = block_sum(part, s_scr);
+    if (tid == 0) {
+      p.out_cost[g] = total / EMD_SCALE;
+      p.out_status[g] = status;
+      if (p.out_iters) p.out_iters[g] = it;
+    }
+  }
+}
+
+inline size_t emd_smem_bytes(int64_t cap_nodes) {
+  return (size_t)cap_nodes * (4 + 2 + 2 + 5 * 2) + 4 * (size_t)EMD_MAXPATH * 2 + 64;
+}
+inline int64_t emd_ws_cap(int64_t n_src, int64_t max_tgt) { return (n_src + max_tgt + 1 + 7) & ~7LL; }
+
+}  // namespace
+}  // namespace stm
+
+extern "C" int64_t stm_emd_workspace_bytes(int32_t n_src, int64_t max_tgt, int32_t n_ctas) {
+  if (n_src < 0 || max_tgt < 0 || n_ctas <= 0) return -1;
+  return 256 + (int64_t)n_src * 8 + (int64_t)n_ctas * stm::emd_ws_cap(n_src, max_tgt) * 8 + 256;
+}
+
+extern "C" int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
+                                     const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
+                                     const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
+                                     int64_t max_iter, int32_t block_size,
+                                     void* workspace, int64_t workspace_bytes, int32_t n_ctas,
+                                     double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream) {
+  using namespace stm;
+  STM_CHECK_ARG(G >= 0, "G < 0");
+  if (G == 0) return STM_OK;
+  STM_CHECK_ARG(n_src > 0 && src_x && src_y && src_mass, "empty or null source image");
+  STM_CHECK_ARG(tgt_ptr && tgt_x && tgt_y && tgt_mass && out_cost && out_status, "null pointer");
+  STM_CHECK_ARG(max_tgt >= 0 && n_ctas > 0 && max_iter >= 0 && block_size >= 0, "bad size argument");
+  STM_CHECK_ARG(workspace && workspace_bytes >= stm_emd_workspace_bytes(n_src, max_tgt, n_ctas), "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int dev = 0, max_optin = 0;
+  STM_CHECK_CUDA(cudaGetDevice(&dev));
+  STM_CHECK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  // node capacity of one CTA: the whole tree lives in shared memory; larger problems get status 3
+  int64_t cap = emd_ws_cap(n_src, max_tgt);
+  const int64_t max_cap = (((int64_t)max_optin - 1024 - (int64_t)emd_smem_bytes(0)) / 18) & ~7LL;
+  if (cap > max_cap) cap = max_cap;
+  char* ws = static_cast<char*>(workspace);
+  EmdArgs a{};
+  a.src_x = src_x; a.src_y = src_y; a.src_mass = src_mass; a.n_src = n_src;
+  a.tgt_ptr = tgt_ptr; a.tgt_x = tgt_x; a.tgt_y = tgt_y; a.tgt_mass = tgt_mass;
+  a.G = G; a.cap_nodes = (int32_t)cap; a.max_iter = max_iter; a.block_size = block_size;
+  a.counter = reinterpret_cast<unsigned int*>(ws);
+  a.src_int = reinterpret_cast<int64_t*>(ws + 256);
+  a.flow_ws = a.src_int + n_src;
+  a.order = order;
+  a.out_cost = out_cost; a.out_status = out_status; a.out_iters = out_iters;
+  STM_CHECK_CUDA(cudaMemsetAsync(a.counter, 0, 256, st));
+  emd_prep_kernel<<<1, EMD_THREADS, 0, st>>>(src_mass, n_src, a.src_int);
+  STM_CHECK_CUDA(cudaGetLastError());
+  const size_t smem = emd_smem_bytes((int)cap);
+  STM_CHECK_CUDA(cudaFuncSetAttribute(emd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = n_ctas < G ? n_ctas : G;
+  emd_kernel<<<grid, EMD_THREADS, smem, st>>>(a);
+  STM_CHECK_CUDA(cudaGetLastError());
+  return STM_OK;
+}

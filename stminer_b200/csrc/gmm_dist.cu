@@ -203,6 +203,23 @@ __global__ void __launch_bounds__(DIST_THREADS) gmm_dist_kernel(const DistArgs a
   }
 }
 
+// Exact LSAP on a batch of caller-supplied K x K cost matrices (row-major float64), one warp each.
+template <int CPL>
+__global__ void __launch_bounds__(DIST_THREADS) lsap_batched_kernel(const double* __restrict__ cost, int K,
+                                                                    int64_t B, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* C = reinterpret_cast<double*>(smem_raw) + (size_t)warp * K * K;
+  for (int64_t t = (int64_t)blockIdx.x * DIST_WARPS + warp; t < B; t += (int64_t)gridDim.x * DIST_WARPS) {
+    __syncwarp();
+    const double* src = cost + (size_t)t * K * K;
+    for (int e = lane; e < K * K; e += 32) C[e] = src[e];
+    __syncwarp();
+    const double d = lsap_warp<CPL>(C, K, lane);
+    if (lane == 0) out[t] = d;
+  }
+}
+
 __global__ void fill_square_kernel(const double* __restrict__ pairs, int G, double* __restrict__ out) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)G * G) return;
@@ -259,6 +276,29 @@ extern "C" int stm_gmm_dist_one_vs_all(const double* qw, const double* qmu, cons
   STM_CHECK_ARG(qw && qmu && qcov && w && mu && cov && out, "null pointer");
   DistArgs a{w, mu, cov, qw, qmu, qcov, G, K, 0, (int64_t)G, out};
   return launch_dist(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int stm_lsap_batched(const double* cost, int32_t K, int64_t B, double* out, void* stream) {
+  using namespace stm;
+  STM_CHECK_ARG(K >= 1 && K <= 64 && B >= 0, "need 1 <= K <= 64 and B >= 0");
+  if (B == 0) return STM_OK;
+  STM_CHECK_ARG(cost && out, "null pointer");
+  const size_t smem = DIST_WARPS * (size_t)K * K * sizeof(double);
+  int dev = 0, sms = 0;
+  STM_CHECK_CUDA(cudaGetDevice(&dev));
+  STM_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int64_t blocks = (B + DIST_WARPS - 1) / DIST_WARPS;
+  if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (K <= 32) {
+    STM_CHECK_CUDA(cudaFuncSetAttribute(lsap_batched_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lsap_batched_kernel<1><<<(unsigned)blocks, DIST_THREADS, smem, st>>>(cost, K, B, out);
+  } else {
+    STM_CHECK_CUDA(cudaFuncSetAttribute(lsap_batched_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lsap_batched_kernel<2><<<(unsigned)blocks, DIST_THREADS, smem, st>>>(cost, K, B, out);
+  }
+  STM_CHECK_CUDA(cudaGetLastError());
+  return STM_OK;
 }
 
 extern "C" int stm_gmm_dist_fill_square(const double* pairs, int32_t G, double* out_square, void* stream) {
