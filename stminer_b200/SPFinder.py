@@ -320,8 +320,12 @@ class SPFinder:
     def get_all_labels(self) -> None:
         """SPFinder.py:556-570: nearest voted pattern (by GMM distance) of every fitted gene."""
         df_list = []
+        # the reference hard-codes 20 components here, which only works when the genes were fitted with 20
+        # (distance.py:29 takes K from the first mixture); use the fitted genes' K so other K work too
+        n_comp = next(iter(self.patterns.values())).weights_.size
         for i in self.patterns_binary_matrix_dict:
-            gmm = _fit_image(np.asarray(self.patterns_binary_matrix_dict[i], dtype=np.int32), 20, self.seed, self.device)
+            gmm = _fit_image(np.asarray(self.patterns_binary_matrix_dict[i], dtype=np.int32), n_comp, self.seed,
+                             self.device)
             df = compare_gmm_distance(gmm, self.patterns, device=self.device)
             df.rename(columns={0: i}, inplace=True)
             df_list.append(df)

@@ -184,7 +184,16 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     long long it = 0;
     int status = 0;
 
+#ifdef STM_EMD_PROFILE
+    long long c_price = 0, c_walk = 0, c_leave = 0, c_update = 0, n_scanned = 0, c_t0 = 0, sum_len = 0, sum_s = 0, sum_range = 0;
+#define PROF_T(x) { const long long _c = clock64(); x += _c - c_t0; c_t0 = _c; }
+#else
+#define PROF_T(x)
+#endif
     for (;;) {
+#ifdef STM_EMD_PROFILE
+      c_t0 = clock64();
+#endif
       // ---- entering arc: block search over arcs e = j*n + i ----------------------------------------
       int scanned = 0, best_e = -1, best_rc = 0;
       while (scanned < n_arcs) {
@@ -222,6 +231,10 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
           break;
         }
       }
+      PROF_T(c_price)
+#ifdef STM_EMD_PROFILE
+      n_scanned += scanned;
+#endif
       if (best_e < 0) break;                      // optimal
       if (it >= p.max_iter) { status = 1; break; }
       ++it;
@@ -244,6 +257,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
       }
       __syncthreads();
       const int lenA = s_i[1], lenB = s_i[2];
+      PROF_T(c_walk)
       if (lenA > EMD_MAXPATH || lenB > EMD_MAXPATH) { status = 4; break; }
       // ---- leaving arc (warp 0): min flow over arcs traversed against their direction; ties resolved by
       //      the strongly-feasible rule (i side: closest to i; j side wins and takes the one closest to the join)
@@ -268,6 +282,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
       __syncthreads();
       const long long delta = s_delta;
       const int seq = s_i[3];
+      PROF_T(c_leave)
       if (seq < 0) { status = 5; break; }        // unbounded: cannot happen for a transport LP
       const int side = seq >= lenA ? 1 : 0;
       const int k = side == 0 ? lenA - 1 - seq : seq - lenA;   // leaving arc at path index k of its side
@@ -335,7 +350,17 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
         s_pos[v] = (unsigned short)f;
       }
       __syncthreads();
+      PROF_T(c_update)
+#ifdef STM_EMD_PROFILE
+      sum_len += lenA + lenB; sum_s += s; sum_range += hi - lo;
+#endif
     }
+#ifdef STM_EMD_PROFILE
+    if (tid == 0 && g < 2)
+      printf("[emd prof] g=%d n=%d m=%d pivots=%lld cycles/pivot: price %.0f walk %.0f leave %.0f update %.0f | arcs scanned/pivot %.0f cycle len %.1f subtree %.1f range %.1f\n",
+             g, n, m, it, (double)c_price / it, (double)c_walk / it, (double)c_leave / it, (double)c_update / it,
+             (double)n_scanned / it, (double)sum_len / it, (double)sum_s / it, (double)sum_range / it);
+#endif
     // ---- objective: real tree arcs only ------------------------------------------------------------
     double part = 0.0;
     for (int v = tid; v < n + m; v += EMD_THREADS) {

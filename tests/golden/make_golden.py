@@ -68,6 +68,28 @@ def make_dist():
     print("gmm_dist.npz written")
 
 
+def make_emd():
+    """Exact transport-LP optima from scipy's HiGHS (an independent solver; POT is not installable here)."""
+    from oracle import emd_oracle as eo
+    rng = np.random.default_rng(77)
+    out = {}
+    cases = [(6, 5, 5), (40, 25, 9), (100, 140, 14), (282, 150, 17), (200, 200, 17), (64, 1, 8), (1, 30, 8)]
+    for c, (n, m, R) in enumerate(cases):
+        s = rng.permutation(R * R)[:n]; t = rng.permutation(R * R)[:m]
+        sm = rng.gamma(0.8, 2.0, n) + 1e-3; tm = rng.gamma(0.8, 2.0, m) + 1e-3
+        if c == 4:   # integer counts with many ties (degenerate pivots)
+            sm = rng.integers(1, 4, n).astype(float); tm = rng.integers(1, 4, m).astype(float)
+        ref = eo.emd_linprog(s // R, s % R, sm, t // R, t % R, tm)
+        pre = "c%d_" % c
+        out[pre + "sx"] = (s // R).astype(np.int32); out[pre + "sy"] = (s % R).astype(np.int32); out[pre + "sm"] = sm
+        out[pre + "tx"] = (t // R).astype(np.int32); out[pre + "ty"] = (t % R).astype(np.int32); out[pre + "tm"] = tm
+        out[pre + "cost"] = np.float64(ref)
+    out["n"] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(HERE, "emd_small.npz"), **out)
+    print("emd_small.npz:", len(cases), "problems")
+
+
 if __name__ == "__main__":
     make_gmm()
     make_dist()
+    make_emd()

@@ -1,0 +1,87 @@
+"""GPU parity: batched exact spot-level EMD (through the C ABI) vs golden LP optima and the network-simplex oracle."""
+import os
+
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+from oracle import emd_oracle as eo
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "emd_small.npz")
+
+
+def test_emd_matches_lp_golden(cuda_device):
+    from stminer_b200.Algorithm.distance import emd_batched
+    z = np.load(GOLD)
+    for c in range(int(z["n"])):
+        p = "c%d_" % c
+        cost, status = emd_batched((z[p + "sx"], z[p + "sy"], z[p + "sm"]), [(z[p + "tx"], z[p + "ty"], z[p + "tm"])])
+        assert status[0] == 0
+        # north-star tolerance for global_distance is rtol 1e-4; the integer simplex is exact to ~1e-12
+        assert abs(cost[0] - float(z[p + "cost"])) <= 1e-9 * max(1.0, float(z[p + "cost"]))
+
+
+def _random_problem(rng, n, ms, R):
+    s = rng.permutation(R * R)[:n]
+    src = (s // R, s % R, rng.gamma(1.0, 1.0, n) + 0.01)
+    tg = []
+    for m in ms:
+        t = rng.permutation(R * R)[:m]
+        tg.append((t // R, t % R, rng.gamma(1.0, 1.0, m) + 0.01))
+    return src, tg
+
+
+@pytest.mark.parametrize("n,ms,R", [(282, [150, 282, 31, 1, 90], 17), (1200, [700, 400, 1100], 40), (50, list(range(1, 40, 3)), 8)])
+def test_emd_batch_matches_oracle_and_pivot_sequence(cuda_device, n, ms, R):
+    """One source, ragged targets in one launch; same block size -> identical pivot count and cost as the oracle."""
+    from stminer_b200.Algorithm.distance import emd_batched
+    src, tg = _random_problem(np.random.default_rng(n), n, ms, R)
+    cost, status, iters = emd_batched(src, tg, return_iters=True)
+    for g, t in enumerate(tg):
+        c, st, it = eo.emd_network_simplex(*src, *t)
+        assert status[g] == st == 0
+        assert iters[g] == it
+        assert abs(cost[g] - c) <= 1e-12 * max(1.0, c)
+
+
+def test_emd_iteration_limit_and_empty(cuda_device):
+    from stminer_b200.Algorithm.distance import emd_batched
+    src, tg = _random_problem(np.random.default_rng(3), 282, [150], 17)
+    full, st, it = emd_batched(src, tg, return_iters=True)
+    cut, st1, it1 = emd_batched(src, tg, max_iter=int(it[0]) // 2, return_iters=True)
+    ref, rst, rit = eo.emd_network_simplex(*src, *tg[0], max_iter=int(it[0]) // 2)
+    assert st[0] == 0 and st1[0] == 1 and rst == 1 and it1[0] == rit
+    assert abs(cut[0] - ref) <= 1e-12 * ref          # same sub-optimal basis as the oracle (POT semantics)
+    empty = (np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0))
+    c2, s2 = emd_batched(src, [tg[0], empty])
+    assert s2.tolist() == [0, 2]
+
+
+def test_emd_too_large_for_one_cta_reports_status_3(cuda_device):
+    from stminer_b200.Algorithm.distance import emd_batched
+    rng = np.random.default_rng(0)
+    n = 9000
+    src = (rng.integers(0, 300, n), rng.integers(0, 300, n), rng.random(n) + 0.1)
+    tgt = (rng.integers(0, 300, 4000), rng.integers(0, 300, 4000), rng.random(4000) + 0.1)
+    cost, status = emd_batched(src, [tgt])
+    assert status[0] == 3 and np.isnan(cost[0])
+
+
+def test_host_api_csr_images(cuda_device):
+    """calculate_ot_distance / build_ot_distance_array on sparse (x, y) images (distance.py:179-202)."""
+    from stminer_b200.Algorithm.distance import build_ot_distance_array, calculate_ot_distance
+    rng = np.random.default_rng(2)
+    imgs = {}
+    for g in range(5):
+        a = np.zeros((14, 11)); idx = rng.permutation(154)[:30 + 5 * g]
+        a[idx // 11, idx % 11] = rng.gamma(1.0, 2.0, len(idx))
+        imgs["g%d" % g] = csr_matrix(a)
+    d01 = calculate_ot_distance(imgs["g0"], imgs["g1"])
+    assert abs(d01 - eo.calculate_ot_distance(imgs["g0"], imgs["g1"])) < 1e-10 * d01
+    assert calculate_ot_distance(imgs["g2"], imgs["g2"]) < 1e-12
+    df = build_ot_distance_array(imgs)
+    assert list(df.index) == list(imgs) and np.allclose(df.values, df.values.T) and (np.diag(df.values) == 0).all()
+    assert abs(df.loc["g0", "g1"] - d01) < 1e-12
+    ref34 = eo.calculate_ot_distance(imgs["g3"], imgs["g4"])
+    assert abs(df.loc["g3", "g4"] - ref34) < 1e-10 * ref34

@@ -1,0 +1,60 @@
+"""CPU: the network-simplex EMD oracle against exact LP optima (HiGHS) — committed golden values and live."""
+import os
+
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+from oracle import emd_oracle as eo
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "emd_small.npz")
+
+
+def cases():
+    z = np.load(GOLD)
+    for c in range(int(z["n"])):
+        p = "c%d_" % c
+        yield c, {k[len(p):]: z[k] for k in z.files if k.startswith(p)}
+
+
+@pytest.mark.parametrize("c,d", list(cases()))
+def test_network_simplex_matches_lp_golden(c, d):
+    cost, status, pivots = eo.emd_network_simplex(d["sx"], d["sy"], d["sm"], d["tx"], d["ty"], d["tm"])
+    assert status == 0
+    assert abs(cost - float(d["cost"])) <= 1e-9 * max(1.0, float(d["cost"]))
+    # the pivot rule's block size does not change the optimum
+    cost2, status2, _ = eo.emd_network_simplex(d["sx"], d["sy"], d["sm"], d["tx"], d["ty"], d["tm"], block_size=17)
+    assert status2 == 0 and abs(cost2 - cost) <= 1e-11 * max(1.0, cost)
+
+
+def test_network_simplex_matches_lp_live():
+    rng = np.random.default_rng(5)
+    s = rng.permutation(144)[:60]; t = rng.permutation(144)[:45]
+    sm = rng.random(60) + 0.1; tm = rng.random(45) + 0.1
+    a = eo.emd_network_simplex(s // 12, s % 12, sm, t // 12, t % 12, tm)[0]
+    b = eo.emd_linprog(s // 12, s % 12, sm, t // 12, t % 12, tm)
+    assert abs(a - b) < 1e-9 * b
+
+
+def test_iteration_limit_reports_status_1():
+    """POT stops at numItermax and returns the current (sub-optimal) value with a warning (distance.py:201)."""
+    _, d = list(cases())[3]
+    full, st0, pivots = eo.emd_network_simplex(d["sx"], d["sy"], d["sm"], d["tx"], d["ty"], d["tm"])
+    cut, st1, it1 = eo.emd_network_simplex(d["sx"], d["sy"], d["sm"], d["tx"], d["ty"], d["tm"], max_iter=pivots // 2)
+    assert st0 == 0 and st1 == 1 and it1 == pivots // 2
+
+
+def test_calculate_ot_distance_staging_and_properties():
+    """distance.py:191-202 staging from sparse images; EMD of an image with itself is 0; a translation by
+    (dx, dy) costs dx^2 + dy^2; scaling the masses changes nothing (both sides are normalised)."""
+    rng = np.random.default_rng(1)
+    img = np.zeros((12, 15)); idx = rng.permutation(180)[:40]
+    img[idx // 15, idx % 15] = rng.gamma(1.0, 2.0, 40)
+    a = csr_matrix(img)
+    assert eo.calculate_ot_distance(a, a) < 1e-12
+    shifted = np.zeros((16, 18)); shifted[3:15, 2:17] = img
+    assert abs(eo.calculate_ot_distance(a, csr_matrix(shifted)) - (3 ** 2 + 2 ** 2)) < 1e-9
+    b_img = np.zeros((12, 15)); j = rng.permutation(180)[:25]; b_img[j // 15, j % 15] = rng.random(25) + 0.05
+    d1 = eo.calculate_ot_distance(a, csr_matrix(b_img))
+    d2 = eo.calculate_ot_distance(csr_matrix(7.5 * img), csr_matrix(0.2 * b_img))
+    assert abs(d1 - d2) < 1e-9 * d1
