@@ -46,6 +46,15 @@ constexpr int KM_LMAX = 6;                // greedy k-means++ candidates: 2 + fl
 #ifndef STM_EM_MINB_SMALL
 #define STM_EM_MINB_SMALL 4   // CTAs (of 128 threads) per SM, small-gene bucket
 #endif
+#ifndef STM_EM_PACKED
+#define STM_EM_PACKED 1       // FP32x2 packed E/M sweep (FFMA2); 0 = scalar sweep
+#endif
+#ifndef STM_EM_MAGIC_I2F
+#define STM_EM_MAGIC_I2F 0    // int16 -> float by magic-number add instead of I2F (XU pipe)
+#endif
+#ifndef STM_EM_LL_BATCH
+#define STM_EM_LL_BATCH 0     // fold the FP32 log-likelihood partial into FP64 every 8 steps instead of every step
+#endif
 #ifndef STM_KM_DEFAULT_CAND
 #define STM_KM_DEFAULT_CAND 2     // greedy k-means++ trials per centre when the flags field is 0
 #endif
@@ -130,6 +139,7 @@ constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 template <int KT, int GS, int T>
 struct EmLayout {
+  static constexpr int KT_ = KT;
   static constexpr int KP = KT * GS;
   static constexpr int NSTAT = KP * 6;
   static constexpr int WARPS = T / 32;
@@ -144,7 +154,8 @@ struct EmLayout {
   static constexpr int D_END = round_up(D_SCR + WARPS * KM_LMAX + 2 * KM_LMAX, 2);
   // floats (after doubles)
   static constexpr int F_PAR = 0;                                   // [KP*8]
-  static constexpr int F_RED = F_PAR + KP * 8;                      // [WARPS*NSTAT]
+  static constexpr int F_PP = F_PAR + KP * 8;                       // [KP*6] E-step coefficients, pair-interleaved
+  static constexpr int F_RED = F_PP + KP * 6;                       // [WARPS*NSTAT]
   static constexpr int F_END = round_up(F_RED + WARPS * NSTAT, 4);  // then float4 seeds[seed_cap], int2 spots[cap]
   static constexpr size_t fixed_bytes() { return (size_t)D_END * 8 + (size_t)F_END * 4 + 64; }
 };
@@ -172,6 +183,11 @@ __device__ __forceinline__ bool refresh_component(int k, double* s_d, float* s_p
   const float c2 = lg2_approx((float)(w * i00 * i11 * 0.15915494309189533577));
   float* q = s_par + 8 * k;
   q[0] = a00; q[1] = b0; q[2] = a01; q[3] = a11; q[4] = b1; q[5] = c2;
+  // pair-interleaved copy for the packed sweep: lane `sub` reads (component 2q, component 2q+1) as one float2
+  constexpr int KT = L::KT_;
+  const int sub = k / KT, j = k % KT;
+  float* pq = s_par + (L::F_PP - L::F_PAR) + ((sub * (KT / 2) + (j >> 1)) * 6) * 2 + (j & 1);
+  if (j < 2 * (KT / 2)) { pq[0] = a00; pq[2] = b0; pq[4] = a01; pq[6] = a11; pq[8] = b1; pq[10] = c2; }
   return ok;
 }
 
@@ -179,8 +195,18 @@ __device__ __forceinline__ int pack_xy(int x, int y) {
   x = max(-32768, min(32767, x)); y = max(-32768, min(32767, y));
   return (x & 0xffff) | (y << 16);
 }
+// int16 -> float on the ALU/FMA pipes (magic-number add) instead of I2F, which is an XU (MUFU-pipe)
+// instruction — the XU pipe is the sweep's second bottleneck after the FMA pipe.
+__device__ __forceinline__ float small_int_to_float(int v) {   // |v| < 2^22
+  return __int_as_float(0x4B400000 + v) - 12582912.0f;
+}
+#if STM_EM_MAGIC_I2F
+__device__ __forceinline__ float unpack_x(int p) { return small_int_to_float((p << 16) >> 16); }
+__device__ __forceinline__ float unpack_y(int p) { return small_int_to_float(p >> 16); }
+#else
 __device__ __forceinline__ float unpack_x(int p) { return (float)(short)(p & 0xffff); }
 __device__ __forceinline__ float unpack_y(int p) { return (float)(p >> 16); }
+#endif
 
 // spots staged in shared memory: {int16 x | int16 y, float w}
 struct PackedSpots {
@@ -218,6 +244,8 @@ template <int KT, int GS, int S, int T, typename Src>
 __device__ __forceinline__ void em_sweep(const Src& src, int i_begin, int i_end, int grp, int sub,
                                          const float (&par)[KT][6], float* acc, double& ll) {
   constexpr int NG = T / GS;
+  float wl_acc = 0.f;
+  int step = 0;
   // the trip count must be uniform across the warp: the group shuffles below use the full mask
   for (int base = i_begin; base < i_end; base += NG * S) {
     float x[S], y[S], w[S];
@@ -276,8 +304,120 @@ __device__ __forceinline__ void em_sweep(const Src& src, int i_begin, int i_end,
         acc[j * 6 + 5] = fmaf(rt1, t1[s][j], acc[j * 6 + 5]);
       }
     }
-    ll += (double)wl;  // every lane of a group holds the same value; lane sub == 0 is the one summed
+    // every lane of a group holds the same value; lane sub == 0 is the one summed.  The FP32 partial is
+    // folded into FP64 every 8 steps (F2F is an XU instruction).
+#if STM_EM_LL_BATCH
+    wl_acc += wl;
+    if ((++step & 7) == 0) { ll += (double)wl_acc; wl_acc = 0.f; }
+#else
+    ll += (double)wl;
+#endif
   }
+  ll += (double)wl_acc;
+}
+
+// The same sweep with the components of a lane processed in PAIRS by packed FP32x2 instructions (FFMA2 /
+// FADD2 / FMUL2): half the issue slots and half the register-file operand fetches for the FMA-class work,
+// which is what bounds the scalar sweep (3-operand FFMA without operand reuse sustains 0.62 of the FFMA
+// peak on B200, packed 0.81 — scripts/micro/ffma2_bench.cu).  KT = 2*NP + R (R = 0 or 1 scalar leftover).
+template <int KT, int GS, int S, int T, typename Src>
+__device__ __forceinline__ void em_sweep_packed(const Src& src, int i_begin, int i_end, int grp, int sub,
+                                                const f2 (&pp)[(KT / 2) > 0 ? (KT / 2) : 1][6], const float (&ps)[6],
+                                                f2 (&ap)[(KT / 2) > 0 ? (KT / 2) : 1][6], float (&as)[6], double& ll) {
+  constexpr int NG = T / GS;
+  constexpr int NP = KT / 2, R = KT % 2;
+  constexpr int NPA = NP > 0 ? NP : 1;
+  float wl_acc = 0.f;
+  int step = 0;
+  for (int base = i_begin; base < i_end; base += NG * S) {
+    float x[S], y[S], w[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int i = base + grp + s * NG;
+      x[s] = 0.f; y[s] = 0.f; w[s] = 0.f;
+      if (i < i_end) src.get(i, x[s], y[s], w[s]);
+    }
+    f2 t0p[S][NPA], t1p[S][NPA], lpp[S][NPA];
+    float t0s[S], t1s[S], lps[S], m[S], sum[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const f2 xx = f2_make(x[s], x[s]), yy = f2_make(y[s], y[s]);
+      m[s] = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        t0p[s][q] = f2_fma(xx, pp[q][0], pp[q][1]);
+        t1p[s][q] = f2_fma(xx, pp[q][2], f2_fma(yy, pp[q][3], pp[q][4]));
+        lpp[s][q] = f2_sub(pp[q][5], f2_fma(t0p[s][q], t0p[s][q], f2_mul(t1p[s][q], t1p[s][q])));
+        m[s] = fmaxf(m[s], fmaxf(lpp[s][q].x, lpp[s][q].y));
+      }
+      if constexpr (R == 1) {
+        t0s[s] = fmaf(x[s], ps[0], ps[1]);
+        t1s[s] = fmaf(x[s], ps[2], fmaf(y[s], ps[3], ps[4]));
+        lps[s] = fmaf(-t0s[s], t0s[s], fmaf(-t1s[s], t1s[s], ps[5]));
+        m[s] = fmaxf(m[s], lps[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int o = 1; o < GS; o <<= 1) m[s] = fmaxf(m[s], __shfl_xor_sync(FULL_MASK, m[s], o));
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const f2 mm = f2_make(m[s], m[s]);
+      f2 sp = f2_make(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        const f2 d = f2_sub(lpp[s][q], mm);
+        lpp[s][q] = f2_make(ex2_approx(d.x), ex2_approx(d.y));
+        sp = f2_add(sp, lpp[s][q]);
+      }
+      sum[s] = sp.x + sp.y;
+      if constexpr (R == 1) { lps[s] = ex2_approx(lps[s] - m[s]); sum[s] += lps[s]; }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int o = 1; o < GS; o <<= 1) sum[s] += __shfl_xor_sync(FULL_MASK, sum[s], o);
+    }
+    float wl = 0.f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const float scale = w[s] * rcp_approx(sum[s]);
+      wl = fmaf(w[s], m[s] + lg2_approx(sum[s]), wl);
+      const f2 ss = f2_make(scale, scale);
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        const f2 r = f2_mul(lpp[s][q], ss);
+        const f2 rt0 = f2_mul(r, t0p[s][q]);
+        const f2 rt1 = f2_mul(r, t1p[s][q]);
+        ap[q][0] = f2_add(ap[q][0], r);
+        ap[q][1] = f2_add(ap[q][1], rt0);
+        ap[q][2] = f2_add(ap[q][2], rt1);
+        ap[q][3] = f2_fma(rt0, t0p[s][q], ap[q][3]);
+        ap[q][4] = f2_fma(rt0, t1p[s][q], ap[q][4]);
+        ap[q][5] = f2_fma(rt1, t1p[s][q], ap[q][5]);
+      }
+      if constexpr (R == 1) {
+        const float r = lps[s] * scale;
+        const float rt0 = r * t0s[s];
+        const float rt1 = r * t1s[s];
+        as[0] += r;
+        as[1] += rt0;
+        as[2] += rt1;
+        as[3] = fmaf(rt0, t0s[s], as[3]);
+        as[4] = fmaf(rt0, t1s[s], as[4]);
+        as[5] = fmaf(rt1, t1s[s], as[5]);
+      }
+    }
+#if STM_EM_LL_BATCH
+    wl_acc += wl;
+    if ((++step & 7) == 0) { ll += (double)wl_acc; wl_acc = 0.f; }
+#else
+    ll += (double)wl;
+#endif
+  }
+  ll += (double)wl_acc;
 }
 
 // Assignment sweep with moments: every spot goes to its nearest centre (ties: lowest component
@@ -544,6 +684,11 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   for (int k = K + tid; k < KP; k += T) {
     float* q = s_par + 8 * k;
     q[0] = 0.f; q[1] = 0.f; q[2] = 0.f; q[3] = 0.f; q[4] = 0.f; q[5] = -1e30f; q[6] = 1e18f; q[7] = 1e18f;
+    const int psub = k / KT, pj = k % KT;
+    if (pj < 2 * (KT / 2)) {
+      float* pq = s_f + L::F_PP + ((psub * (KT / 2) + (pj >> 1)) * 6) * 2 + (pj & 1);
+      pq[0] = 0.f; pq[2] = 0.f; pq[4] = 0.f; pq[6] = 0.f; pq[8] = 0.f; pq[10] = -1e30f;
+    }
   }
   __syncthreads();
 
@@ -746,6 +891,19 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
 
   while (!failed && n_iter < p.max_iter) {
     ++n_iter;
+#if STM_EM_PACKED
+    constexpr int NP = KT / 2, NPA = NP > 0 ? NP : 1;
+    f2 pp[NPA][6];
+    float ps[6];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      const float2* qa = reinterpret_cast<const float2*>(s_f + L::F_PP) + (sub * NP + q) * 6;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) pp[q][c] = qa[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ps[c] = s_par[8 * (sub * KT + KT - 1) + c];
+#else
     float par[KT][6];
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
@@ -753,6 +911,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
       const float2 q1 = *reinterpret_cast<const float2*>(s_par + 8 * (sub * KT + j) + 4);
       par[j][0] = q0.x; par[j][1] = q0.y; par[j][2] = q0.z; par[j][3] = q0.w; par[j][4] = q1.x; par[j][5] = q1.y;
     }
+#endif
     for (int i = tid; i < NSTAT; i += T) s_d[L::D_STAT + i] = 0.0;
     __syncthreads();
     double ll = 0.0;
@@ -761,8 +920,31 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
       float acc[NPAD];
 #pragma unroll
       for (int i = 0; i < NPAD; ++i) acc[i] = 0.f;
+#if STM_EM_PACKED
+      f2 ap[NPA][6];
+      float as[6];
+#pragma unroll
+      for (int q = 0; q < NPA; ++q) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) ap[q][c] = f2_make(0.f, 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) as[c] = 0.f;
+      if (staged) em_sweep_packed<KT, GS, S, T>(staged_src, c0, c1, grp, sub, pp, ps, ap, as, ll);
+      else        em_sweep_packed<KT, GS, S, T>(stream_src, c0, c1, grp, sub, pp, ps, ap, as, ll);
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { acc[(2 * q) * 6 + c] = ap[q][c].x; acc[(2 * q + 1) * 6 + c] = ap[q][c].y; }
+      }
+      if constexpr (KT % 2 == 1) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc[(KT - 1) * 6 + c] = as[c];
+      }
+#else
       if (staged) em_sweep<KT, GS, S, T>(staged_src, c0, c1, grp, sub, par, acc, ll);
       else        em_sweep<KT, GS, S, T>(stream_src, c0, c1, grp, sub, par, acc, ll);
+#endif
       flush_stats<KT, GS, T, NPAD>(acc, s_d, s_red, tid);
     }
     ll = warp_sum(sub == 0 ? ll : 0.0);

@@ -46,6 +46,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// Packed FP32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2): one issue slot and one set of 64-bit
+// register-file reads for two FP32 lanes.
+typedef float2 f2;
+__device__ __forceinline__ f2 f2_make(float lo, float hi) { return make_float2(lo, hi); }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
