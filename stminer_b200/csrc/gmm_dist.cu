@@ -5,6 +5,7 @@
 // scipy.optimize.linear_sum_assignment, a shortest-augmenting-path LSAP).  All arithmetic is
 // float64 like the reference; the LSAP is exact (dual potentials + Dijkstra over columns with the
 // columns spread over the lanes of the warp).
+#include <limits.h>
 #include <math.h>
 
 #include "stm_common.cuh"
@@ -15,8 +16,9 @@ namespace {
 constexpr int DIST_THREADS = 128;
 constexpr int DIST_WARPS = DIST_THREADS / 32;
 
-// per-component record in shared memory: w, mx, my, cxx, cxy, cyy, det^(1/4), pad
-constexpr int COMP_STRIDE = 8;
+// per-component record in shared memory: w, mx, my, cxx, cxy, cyy, det^(1/4), pad.  A stride of 9 doubles
+// (18 words) keeps the 64-bit loads of 16 consecutive components on 16 distinct bank pairs; 8 made them collide.
+constexpr int COMP_STRIDE = 9;
 
 struct DistArgs {
   const double* w; const double* mu; const double* cov;   // [G,K], [G,K,2], [G,K,2,2]
@@ -45,7 +47,6 @@ __device__ __forceinline__ void load_gmm(double* dst, const double* w, const dou
     d[0] = w[k]; d[1] = mu[2 * k]; d[2] = mu[2 * k + 1];
     d[3] = a; d[4] = b; d[5] = c;
     d[6] = sqrt(sqrt(a * c - b * cov[4 * k + 2]));  // det^(1/4), distance.py:78
-    d[7] = 0.0;
   }
 }
 
@@ -88,13 +89,45 @@ __device__ __forceinline__ T bcast(const T (&a)[CPL], int idx) {
 // Exact LSAP on a K x K row-major cost matrix in shared memory; returns the optimal cost
 // (NaN if the matrix holds non-finite entries — scipy raises ValueError there).
 template <int CPL>
-__device__ double lsap_warp(const double* C, int K, int lane) {
+__device__ double lsap_warp(const double* C, int K, int lane, int* scratch) {
   double u[CPL], v[CPL], sh[CPL];
   int row_of_col[CPL], col_of_row[CPL], pred[CPL];
 #pragma unroll
   for (int c = 0; c < CPL; ++c) { u[c] = 0.0; v[c] = 0.0; row_of_col[c] = -1; col_of_row[c] = -1; }
+  // ---- column reduction (the first phase of Jonker-Volgenant): v_j = min_i C_ij keeps the duals feasible
+  //      with u = 0; a column takes its arg-min row if no lower column asked for it.  Only the rows left
+  //      unassigned need an augmenting path. -----------------------------------------------------------------
+  for (int r = lane; r < K; r += 32) scratch[r] = INT_MAX;
+  __syncwarp();
+  bool invalid = false;   // NaN / -inf entries: scipy raises "matrix contains invalid numeric entries"
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int j = lane + 32 * c;
+    int arg = -1;
+    if (j < K) {
+      double best = INFINITY;
+      for (int i = 0; i < K; ++i) {
+        const double x = C[(size_t)i * K + j];
+        invalid |= !(x > -INFINITY);
+        if (x < best) { best = x; arg = i; }
+      }
+      if (arg >= 0) { v[c] = best; atomicMin(&scratch[arg], j); }   // lowest column wins the row
+    }
+    pred[c] = arg;
+  }
+  if (__any_sync(FULL_MASK, invalid)) return NAN;
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int j = lane + 32 * c;
+    if (j < K && pred[c] >= 0 && scratch[pred[c]] == j) row_of_col[c] = pred[c];
+    const int r = lane + 32 * c;
+    if (r < K && scratch[r] != INT_MAX) col_of_row[c] = scratch[r];
+  }
+  __syncwarp();
 
   for (int cur = 0; cur < K; ++cur) {
+    if (bcast<CPL>(col_of_row, cur) >= 0) continue;   // already matched by the column reduction
     unsigned sc[CPL], sr[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) { sh[c] = INFINITY; pred[c] = -1; sc[c] = 0u; sr[c] = 0u; }
@@ -198,7 +231,7 @@ __global__ void __launch_bounds__(DIST_THREADS) gmm_dist_kernel(const DistArgs a
       C[e] = hellinger_cost(g1 + COMP_STRIDE * ci, g2 + COMP_STRIDE * cj);
     }
     __syncwarp();
-    const double d = lsap_warp<CPL>(C, K, lane);
+    const double d = lsap_warp<CPL>(C, K, lane, reinterpret_cast<int*>(g2));
     if (lane == 0) a.out[t] = d;
   }
 }
@@ -209,13 +242,14 @@ __global__ void __launch_bounds__(DIST_THREADS) lsap_batched_kernel(const double
                                                                     int64_t B, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* C = reinterpret_cast<double*>(smem_raw) + (size_t)warp * K * K;
+  double* C = reinterpret_cast<double*>(smem_raw) + (size_t)warp * ((size_t)K * K + K);
+  int* scratch = reinterpret_cast<int*>(C + (size_t)K * K);
   for (int64_t t = (int64_t)blockIdx.x * DIST_WARPS + warp; t < B; t += (int64_t)gridDim.x * DIST_WARPS) {
     __syncwarp();
     const double* src = cost + (size_t)t * K * K;
     for (int e = lane; e < K * K; e += 32) C[e] = src[e];
     __syncwarp();
-    const double d = lsap_warp<CPL>(C, K, lane);
+    const double d = lsap_warp<CPL>(C, K, lane, scratch);
     if (lane == 0) out[t] = d;
   }
 }
@@ -283,7 +317,7 @@ extern "C" int stm_lsap_batched(const double* cost, int32_t K, int64_t B, double
   STM_CHECK_ARG(K >= 1 && K <= 64 && B >= 0, "need 1 <= K <= 64 and B >= 0");
   if (B == 0) return STM_OK;
   STM_CHECK_ARG(cost && out, "null pointer");
-  const size_t smem = DIST_WARPS * (size_t)K * K * sizeof(double);
+  const size_t smem = DIST_WARPS * ((size_t)K * K + K) * sizeof(double);
   int dev = 0, sms = 0;
   STM_CHECK_CUDA(cudaGetDevice(&dev));
   STM_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

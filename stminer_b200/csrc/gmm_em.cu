@@ -197,7 +197,7 @@ __device__ __forceinline__ int pack_xy(int x, int y) {
 }
 // int16 -> float on the ALU/FMA pipes (magic-number add) instead of I2F, which is an XU (MUFU-pipe)
 // instruction — the XU pipe is the sweep's second bottleneck after the FMA pipe.
-__device__ __forceinline__ float small_int_to_float(int v) {   // |v| < 2^22
+[[maybe_unused]] __device__ __forceinline__ float small_int_to_float(int v) {   // |v| < 2^22
   return __int_as_float(0x4B400000 + v) - 12582912.0f;
 }
 #if STM_EM_MAGIC_I2F
@@ -244,8 +244,8 @@ template <int KT, int GS, int S, int T, typename Src>
 __device__ __forceinline__ void em_sweep(const Src& src, int i_begin, int i_end, int grp, int sub,
                                          const float (&par)[KT][6], float* acc, double& ll) {
   constexpr int NG = T / GS;
-  float wl_acc = 0.f;
-  int step = 0;
+  [[maybe_unused]] float wl_acc = 0.f;
+  [[maybe_unused]] int step = 0;
   // the trip count must be uniform across the warp: the group shuffles below use the full mask
   for (int base = i_begin; base < i_end; base += NG * S) {
     float x[S], y[S], w[S];
@@ -327,8 +327,8 @@ __device__ __forceinline__ void em_sweep_packed(const Src& src, int i_begin, int
   constexpr int NG = T / GS;
   constexpr int NP = KT / 2, R = KT % 2;
   constexpr int NPA = NP > 0 ? NP : 1;
-  float wl_acc = 0.f;
-  int step = 0;
+  [[maybe_unused]] float wl_acc = 0.f;
+  [[maybe_unused]] int step = 0;
   for (int base = i_begin; base < i_end; base += NG * S) {
     float x[S], y[S], w[S];
 #pragma unroll
