@@ -604,15 +604,49 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   __syncthreads();
   long long npos = 0, sw = 0, swx = 0, swy = 0;
   int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
-  for (int i = tid; i < ncol; i += T) {
-    const int w = gene_weight(__ldg(vals + i), remove_low, mean_nz);
-    if (w > 0) {
-      const int r = __ldg(rows + i);
-      const int x = __ldg(p.spot_x + r), y = __ldg(p.spot_y + r);
-      npos += 1; sw += w;
-      swx += (long long)w * x;
-      swy += (long long)w * y;
-      xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
+  // A gene that fits the staging budget is read from global memory ONCE: the same pass gathers the statistics
+  // and stages the positive spots (ordered ballot compaction) relative to a provisional origin — the first
+  // entry's spot — which is shifted to the integer centroid afterwards, in shared memory.
+  const bool try_stage = ncol <= p.smem_spots;
+  const int x0 = ncol > 0 ? __ldg(p.spot_x + __ldg(rows)) : 0, y0 = ncol > 0 ? __ldg(p.spot_y + __ldg(rows)) : 0;
+  int n_st = 0;
+  if (try_stage) {
+    for (int base = 0; base < ncol; base += T) {
+      const int i = base + tid;
+      int w = 0, x = 0, y = 0;
+      if (i < ncol) {
+        w = gene_weight(__ldg(vals + i), remove_low, mean_nz);
+        if (w > 0) { const int r = __ldg(rows + i); x = __ldg(p.spot_x + r); y = __ldg(p.spot_y + r); }
+      }
+      const bool keep = w > 0;
+      const unsigned bal = __ballot_sync(FULL_MASK, keep);
+      if (lane == 0) s_cnt[warp] = __popc(bal);
+      __syncthreads();
+      int off = n_st, tot = 0;
+#pragma unroll
+      for (int ww = 0; ww < WARPS; ++ww) { const int c = s_cnt[ww]; if (ww < warp) off += c; tot += c; }
+      if (keep) {
+        npos += 1; sw += w;
+        swx += (long long)w * x;
+        swy += (long long)w * y;
+        xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
+        const int idx = off + __popc(bal & ((1u << lane) - 1u));
+        s_spot[idx] = make_int2(pack_xy(x - x0, y - y0), __float_as_int((float)w));
+      }
+      n_st += tot;
+      __syncthreads();
+    }
+  } else {
+    for (int i = tid; i < ncol; i += T) {
+      const int w = gene_weight(__ldg(vals + i), remove_low, mean_nz);
+      if (w > 0) {
+        const int r = __ldg(rows + i);
+        const int x = __ldg(p.spot_x + r), y = __ldg(p.spot_y + r);
+        npos += 1; sw += w;
+        swx += (long long)w * x;
+        swy += (long long)w * y;
+        xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
+      }
     }
   }
   npos = warp_sum(npos); sw = warp_sum(sw); swx = warp_sum(swx); swy = warp_sum(swy);
@@ -647,33 +681,17 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   }
   const int ox = (int)rint(t_swx / t_sw), oy = (int)rint(t_swy / t_sw);
   // the staged record holds origin-relative coordinates as int16
-  const bool packable = (xmax - ox) < 32768 && (ox - xmin) < 32768 && (ymax - oy) < 32768 && (oy - ymin) < 32768;
-
-  // ---- stage distinct positive spots into shared memory (ordered compaction) ----------------
-  const bool staged = ncol <= p.smem_spots && packable;
+  const bool packable = (xmax - xmin) < 32768 && (ymax - ymin) < 32768;
+  const bool staged = try_stage && packable;
   int n_spots = ncol;
   if (staged) {
-    int n_st = 0;
-    for (int base = 0; base < ncol; base += T) {
-      const int i = base + tid;
-      int w = 0, r = 0;
-      if (i < ncol) { w = gene_weight(__ldg(vals + i), remove_low, mean_nz); r = __ldg(rows + i); }
-      const bool keep = w > 0;
-      const unsigned bal = __ballot_sync(FULL_MASK, keep);
-      if (lane == 0) s_cnt[warp] = __popc(bal);
-      __syncthreads();
-      int off = n_st, tot = 0;
-#pragma unroll
-      for (int ww = 0; ww < WARPS; ++ww) { const int c = s_cnt[ww]; if (ww < warp) off += c; tot += c; }
-      if (keep) {
-        const int idx = off + __popc(bal & ((1u << lane) - 1u));
-        s_spot[idx] = make_int2(pack_xy(__ldg(p.spot_x + r) - ox, __ldg(p.spot_y + r) - oy),
-                                __float_as_int((float)w));
-      }
-      n_st += tot;
-      __syncthreads();
-    }
     n_spots = n_st;
+    const int dx = ox - x0, dy = oy - y0;   // provisional origin -> integer centroid
+    for (int i = tid; i < n_spots; i += T) {
+      const int pk = s_spot[i].x;
+      s_spot[i].x = pack_xy(((pk << 16) >> 16) - dx, (pk >> 16) - dy);
+    }
+    __syncthreads();
   }
 
   const PackedSpots staged_src{s_spot};
