@@ -68,10 +68,15 @@ static void integerize(const double* mass, int n, int64_t* out) {
 /*
  * Exact EMD.  Returns 0 (optimal), 1 (iteration limit reached: cost of the current basis, like POT), 2 (empty
  * input).  *iters receives the number of pivots.  block_size <= 0 selects max(10, sqrt(n*m)) like LEMON.
+ *
+ * cand_threads = 0: plain block search (one pivot per pricing pass).
+ * cand_threads = T > 0: candidate list, the way the CUDA kernel with T threads prices — arc offset k of a block
+ * belongs to class (k mod T) / 32 (the warp that evaluates it); the pass keeps the best arc of every class, and
+ * "minor" pivots then re-price only those T/32 candidates until none is negative (LEMON's candidate-list idea).
  */
 int stm_oracle_emd(const int32_t* sx, const int32_t* sy, const double* smass, int n,
                    const int32_t* tx, const int32_t* ty, const double* tmass, int m,
-                   int64_t max_iter, int64_t block_size, double* cost_out, int64_t* iters) {
+                   int64_t max_iter, int64_t block_size, int cand_threads, double* cost_out, int64_t* iters) {
   *cost_out = 0.0;
   if (iters) *iters = 0;
   if (n <= 0 || m <= 0) return 2;
@@ -111,23 +116,44 @@ int stm_oracle_emd(const int32_t* sx, const int32_t* sy, const double* smass, in
   if (B > n_arcs) B = n_arcs;
   int64_t next_arc = 0, it = 0;
   int status = 0;
+  const int n_cls = cand_threads > 0 ? cand_threads / 32 : 0;
+  int64_t cand_e[64];
+  int n_cand = 0;
   for (;;) {
-    /* ---- entering arc: block search over arcs e = j*n + i ------------------------------------ */
+    /* ---- entering arc ----------------------------------------------------------------------- */
     int64_t scanned = 0, best_e = -1, best_rc = 0;
-    while (scanned < n_arcs) {
+    if (n_cand > 0) {   /* minor iteration: re-price the candidates kept by the last pass */
+      for (int c = 0; c < n_cls; ++c) {
+        const int64_t e = cand_e[c];
+        if (e < 0) continue;
+        const int j = (int)(e / n), i = (int)(e - (int64_t)j * n);
+        const int64_t rc = arc_cost(&g, i, j) + g.pi[i] - g.pi[n + j];
+        if (rc < best_rc) { best_rc = rc; best_e = e; }   /* lowest class wins ties */
+      }
+      if (best_e < 0) n_cand = 0;
+    }
+    while (best_e < 0 && scanned < n_arcs) {   /* major pass: block search over arcs e = j*n + i */
       int64_t cnt = B < n_arcs - scanned ? B : n_arcs - scanned;
+      int64_t cls_rc[64];
+      for (int c = 0; c < n_cls; ++c) { cand_e[c] = -1; cls_rc[c] = 0; }
       best_e = -1; best_rc = 0;
+      int64_t best_k = -1;
       for (int64_t k = 0; k < cnt; ++k) {
         int64_t e = next_arc + k;
         if (e >= n_arcs) e -= n_arcs;
         const int j = (int)(e / n), i = (int)(e - (int64_t)j * n);
         const int64_t rc = arc_cost(&g, i, j) + g.pi[i] - g.pi[n + j];
-        if (rc < best_rc) { best_rc = rc; best_e = e; }   /* first minimum in block order */
+        if (rc < best_rc) { best_rc = rc; best_e = e; best_k = k; }   /* first minimum in block order */
+        if (n_cls > 0) {
+          const int c = (int)((k % cand_threads) / 32);
+          if (rc < cls_rc[c]) { cls_rc[c] = rc; cand_e[c] = e; }
+        }
       }
+      (void)best_k;
       scanned += cnt;
       next_arc += cnt;
       if (next_arc >= n_arcs) next_arc -= n_arcs;
-      if (best_e >= 0) break;
+      if (best_e >= 0) { n_cand = n_cls; break; }
     }
     if (best_e < 0) break; /* optimal */
     if (it >= max_iter) { status = 1; break; }
@@ -223,7 +249,7 @@ int stm_oracle_emd_batched(const int32_t* sx, const int32_t* sy, const double* s
                            int64_t max_iter, int64_t block_size, double* cost, int32_t* status, int64_t* iters) {
   for (int g = 0; g < G; ++g) {
     const int64_t a = tgt_ptr[g], b = tgt_ptr[g + 1];
-    status[g] = stm_oracle_emd(sx, sy, smass, n, tx + a, ty + a, tmass + a, (int)(b - a), max_iter, block_size,
+    status[g] = stm_oracle_emd(sx, sy, smass, n, tx + a, ty + a, tmass + a, (int)(b - a), max_iter, block_size, 0,
                                &cost[g], iters ? &iters[g] : 0);
   }
   return 0;

@@ -29,7 +29,7 @@ def _lib():
         lib = C.CDLL(path)
         lib.stm_oracle_emd.restype = C.c_int
         lib.stm_oracle_emd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                       C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+                                       C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -45,15 +45,16 @@ def csr_to_problem(img):
     return x, y, mass
 
 
-def emd_network_simplex(sx, sy, smass, tx, ty, tmass, max_iter=200000, block_size=0):
-    """(cost, status, pivots).  max_iter mirrors ``numItermax=200000`` (distance.py:201)."""
+def emd_network_simplex(sx, sy, smass, tx, ty, tmass, max_iter=200000, block_size=0, cand_threads=0):
+    """(cost, status, pivots).  max_iter mirrors ``numItermax=200000`` (distance.py:201).  ``cand_threads`` = T
+    prices like the CUDA kernel with T threads (candidate list, see emd_oracle.c); 0 = plain block search."""
     sx = np.ascontiguousarray(sx, dtype=np.int32); sy = np.ascontiguousarray(sy, dtype=np.int32)
     tx = np.ascontiguousarray(tx, dtype=np.int32); ty = np.ascontiguousarray(ty, dtype=np.int32)
     smass = np.ascontiguousarray(smass, dtype=np.float64); tmass = np.ascontiguousarray(tmass, dtype=np.float64)
     cost = C.c_double(0.0); iters = C.c_int64(0)
     st = _lib().stm_oracle_emd(sx.ctypes.data, sy.ctypes.data, smass.ctypes.data, len(sx),
                                tx.ctypes.data, ty.ctypes.data, tmass.ctypes.data, len(tx),
-                               int(max_iter), int(block_size), C.byref(cost), C.byref(iters))
+                               int(max_iter), int(block_size), int(cand_threads), C.byref(cost), C.byref(iters))
     return cost.value, st, iters.value
 
 

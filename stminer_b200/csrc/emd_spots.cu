@@ -23,8 +23,7 @@
 namespace stm {
 namespace {
 
-constexpr int EMD_THREADS = 256;
-constexpr int EMD_WARPS = EMD_THREADS / 32;
+constexpr int EMD_PREP_THREADS = 256;
 constexpr int EMD_MAXPATH = 2048;
 constexpr double EMD_SCALE = 1125899906842624.0;  // 2^50
 constexpr unsigned short NONE16 = 0xffffu;
@@ -46,7 +45,9 @@ __device__ __forceinline__ long long shfl_xor_ll(long long v, int o) {
 }
 
 // Deterministic block sum of doubles (fixed strided order + fixed tree).
+template <int EMD_THREADS>
 __device__ double block_sum(double v, double* s_scr) {
+  constexpr int EMD_WARPS = EMD_THREADS / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   v = warp_sum(v);
   __syncthreads();
@@ -59,10 +60,12 @@ __device__ double block_sum(double v, double* s_scr) {
 
 // mass[i] / sum * 2^50 rounded to integers; the largest entry absorbs the rounding so the total is exactly 2^50.
 // Single CTA; `out` may be global or shared.
+template <int EMD_THREADS>
 __device__ void integerize(const double* mass, int n, int64_t* out, double* s_scr, long long* s_ll) {
+  constexpr int EMD_WARPS = EMD_THREADS / 32;
   double part = 0.0;
   for (int i = threadIdx.x; i < n; i += EMD_THREADS) part += mass[i];
-  const double total = block_sum(part, s_scr);
+  const double total = block_sum<EMD_THREADS>(part, s_scr);
   long long isum = 0, best = -1;
   int best_i = 0;
   for (int i = threadIdx.x; i < n; i += EMD_THREADS) {
@@ -93,19 +96,23 @@ __device__ void integerize(const double* mass, int n, int64_t* out, double* s_sc
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(EMD_THREADS) emd_prep_kernel(const double* src_mass, int n, int64_t* src_int) {
-  __shared__ double s_scr[EMD_WARPS];
-  __shared__ long long s_ll[3 * EMD_WARPS];
-  integerize(src_mass, n, src_int, s_scr, s_ll);
+__global__ void __launch_bounds__(EMD_PREP_THREADS) emd_prep_kernel(const double* src_mass, int n, int64_t* src_int) {
+  __shared__ double s_scr[EMD_PREP_THREADS / 32];
+  __shared__ long long s_ll[3 * EMD_PREP_THREADS / 32];
+  integerize<EMD_PREP_THREADS>(src_mass, n, src_int, s_scr, s_ll);
 }
 
+template <int EMD_THREADS>
 __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
+  constexpr int EMD_WARPS = EMD_THREADS / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap = p.cap_nodes;
+  // s_pi holds ADJUSTED potentials: pi_i + |x_i|^2 for sources, pi_j - |x_j|^2 for sinks, so that the reduced
+  // cost of arc (i, j) is  s_pi[i] - s_pi[j] - 2 x_i.x_j  (one subtraction + two IMAD per arc); a subtree shift
+  // adds the same constant to either form.
   int* s_pi = reinterpret_cast<int*>(smem_raw);                          // [cap]
-  short* s_x = reinterpret_cast<short*>(s_pi + cap);                     // [cap]
-  short* s_y = s_x + cap;                                                // [cap]
-  unsigned short* s_parent = reinterpret_cast<unsigned short*>(s_y + cap);
+  int* s_xy = s_pi + cap;                                                // [cap] {int16 x | int16 y}
+  unsigned short* s_parent = reinterpret_cast<unsigned short*>(s_xy + cap);
   unsigned short* s_pos = s_parent + cap;
   unsigned short* s_size = s_pos + cap;
   unsigned short* s_order = s_size + cap;
@@ -145,7 +152,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     for (int v = tid; v < n + m; v += EMD_THREADS) {
       const int x = v < n ? p.src_x[v] : p.tgt_x[t0 + v - n], y = v < n ? p.src_y[v] : p.tgt_y[t0 + v - n];
       xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
-      if (fits) { s_x[v] = (short)(x - ox); s_y[v] = (short)(y - oy); }
+      if (fits) s_xy[v] = ((x - ox) & 0xffff) | ((y - oy) << 16);
     }
     xmin = __reduce_min_sync(FULL_MASK, xmin); xmax = __reduce_max_sync(FULL_MASK, xmax);
     ymin = __reduce_min_sync(FULL_MASK, ymin); ymax = __reduce_max_sync(FULL_MASK, ymax);
@@ -165,10 +172,11 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     }
     // ---- integer masses and the initial star basis ----------------------------------------------
     for (int i = tid; i < n; i += EMD_THREADS) flow[i] = p.src_int[i];
-    integerize(p.tgt_mass + t0, m, flow + n, s_scr, s_ll);
+    integerize<EMD_THREADS>(p.tgt_mass + t0, m, flow + n, s_scr, s_ll);
     for (int v = tid; v < n + m; v += EMD_THREADS) {
       s_parent[v] = (unsigned short)root; s_order[v + 1] = (unsigned short)v; s_pos[v] = (unsigned short)(v + 1);
-      s_size[v] = 1; s_pi[v] = v < n ? (int)-BIG : (int)BIG;
+      const int xy = s_xy[v], xr = (xy << 16) >> 16, yr = xy >> 16, r2 = xr * xr + yr * yr;
+      s_size[v] = 1; s_pi[v] = v < n ? (int)-BIG + r2 : (int)BIG - r2;
     }
     if (tid == 0) {
       s_order[0] = (unsigned short)root; s_pos[root] = 0; s_size[root] = (unsigned short)N; s_parent[root] = NONE16;
@@ -177,7 +185,9 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     __syncthreads();
 
     const int n_arcs = n * m;
-    int B = p.block_size > 0 ? p.block_size : (int)sqrt((double)n_arcs);
+    // pricing block: LEMON uses sqrt(#arcs); a CTA prices in parallel, so larger blocks (fewer, better pivots and
+    // fewer barriers per arc) win — 32 arcs per thread measured best on Visium-size problems
+    int B = p.block_size > 0 ? p.block_size : max((int)sqrt((double)n_arcs), 32 * EMD_THREADS);
     if (B < 10) B = 10;
     if (B > n_arcs) B = n_arcs;
     int next_arc = 0;
@@ -203,14 +213,19 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
           int e = next_arc + tid;
           if (e >= n_arcs) e -= n_arcs;
           int j = e / n, i = e - j * n;
+          int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
+          int brc = 0, bk = -1;
           for (int k = tid; k < cnt; k += EMD_THREADS) {
-            const int dx = (int)s_x[i] - (int)s_x[n + j], dy = (int)s_y[i] - (int)s_y[n + j];
-            const int rc = dx * dx + dy * dy + s_pi[i] - s_pi[n + j];
-            const long long kk = ((long long)rc << 32) | (unsigned)k;
-            key = min(key, kk);
+            const int xy = s_xy[i];
+            const int rc = ((xy << 16) >> 16) * nx2 + ((xy >> 16) * ny2 + (s_pi[i] - bj));
+            if (rc < brc) { brc = rc; bk = k; }
             i += EMD_THREADS;
-            while (i >= n) { i -= n; if (++j >= m) j = 0; }
+            if (i >= n) {   // next target row(s): reload the target's terms
+              do { i -= n; if (++j >= m) j = 0; } while (i >= n);
+              txy = s_xy[n + j]; nx2 = -2 * ((txy << 16) >> 16); ny2 = -2 * (txy >> 16); bj = s_pi[n + j];
+            }
           }
+          if (bk >= 0) key = ((long long)brc << 32) | (unsigned)bk;
         }
         for (int o = 16; o > 0; o >>= 1) key = min(key, shfl_xor_ll(key, o));
         if (lane == 0) s_key[warp] = key;
@@ -241,17 +256,17 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
       const int ej = best_e / n, ei = best_e - ej * n;
       const int u_i = ei, u_j = n + ej;
       // ---- cycle: two lanes walk the endpoints up to the join node --------------------------------
-      if (tid == 0 || tid == 32) {
+      if (tid == 0 || tid == 32) {   // lanes of two different warps, so the two walks overlap
         const int from = tid == 0 ? u_i : u_j, other = tid == 0 ? u_j : u_i;
         unsigned short* path = tid == 0 ? s_pathA : s_pathB;
         const int po = s_pos[other];
         int len = 0, v = from;
         while (true) {
-          const int pv = s_pos[v], sv = s_size[v];
+          const int pv = s_pos[v], sv = s_size[v], nv = s_parent[v];   // three independent loads per step
           if (pv <= po && po < pv + sv) break;
           if (len < EMD_MAXPATH) path[len] = (unsigned short)v;
           ++len;
-          v = s_parent[v];
+          v = nv;
         }
         s_i[tid == 0 ? 1 : 2] = len;
       }
@@ -368,11 +383,12 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
       const long long f = flow[v];
       if (pr != root && f != 0) {
         const int i = v < n ? v : pr, j = v < n ? pr : v;
-        const long long dx = (int)s_x[i] - (int)s_x[j], dy = (int)s_y[i] - (int)s_y[j];
+        const int a = s_xy[i], b = s_xy[j];
+        const long long dx = ((a << 16) >> 16) - ((b << 16) >> 16), dy = (a >> 16) - (b >> 16);
         part += (double)f * (double)(dx * dx + dy * dy);
       }
     }
-    const double total = block_sum(part, s_scr);
+    const double total = block_sum<EMD_THREADS>(part, s_scr);
     if (tid == 0) {
       p.out_cost[g] = total / EMD_SCALE;
       p.out_status[g] = status;
@@ -413,7 +429,7 @@ extern "C" int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y,
   STM_CHECK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   // node capacity of one CTA: the whole tree lives in shared memory; larger problems get status 3
   int64_t cap = emd_ws_cap(n_src, max_tgt);
-  const int64_t max_cap = (((int64_t)max_optin - 1024 - (int64_t)emd_smem_bytes(0)) / 18) & ~7LL;
+  const int64_t max_cap = (((int64_t)max_optin - 4096 - (int64_t)emd_smem_bytes(0)) / 18) & ~7LL;   // static smem + 1 KB reserve
   if (cap > max_cap) cap = max_cap;
   char* ws = static_cast<char*>(workspace);
   EmdArgs a{};
@@ -426,12 +442,19 @@ extern "C" int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y,
   a.order = order;
   a.out_cost = out_cost; a.out_status = out_status; a.out_iters = out_iters;
   STM_CHECK_CUDA(cudaMemsetAsync(a.counter, 0, 256, st));
-  emd_prep_kernel<<<1, EMD_THREADS, 0, st>>>(src_mass, n_src, a.src_int);
+  emd_prep_kernel<<<1, EMD_PREP_THREADS, 0, st>>>(src_mass, n_src, a.src_int);
   STM_CHECK_CUDA(cudaGetLastError());
   const size_t smem = emd_smem_bytes((int)cap);
-  STM_CHECK_CUDA(cudaFuncSetAttribute(emd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = n_ctas < G ? n_ctas : G;
-  emd_kernel<<<grid, EMD_THREADS, smem, st>>>(a);
+  // Problems that leave room for only one CTA per SM get 1,024 threads (pricing is the dominant phase and
+  // scales with the thread count); small problems run several 256-thread CTAs per SM.
+  if (smem * 2 + 2048 > (size_t)max_optin) {
+    STM_CHECK_CUDA(cudaFuncSetAttribute(emd_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    emd_kernel<1024><<<grid, 1024, smem, st>>>(a);
+  } else {
+    STM_CHECK_CUDA(cudaFuncSetAttribute(emd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    emd_kernel<256><<<grid, 256, smem, st>>>(a);
+  }
   STM_CHECK_CUDA(cudaGetLastError());
   return STM_OK;
 }

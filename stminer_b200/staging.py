@@ -126,15 +126,18 @@ class DeviceSpotMatrix:
         self.device = torch.device(device if device is not None else "cuda")
         self._plans = {}
 
-        def up(a):
-            # async DMA when the host array is page-locked (SpotMatrix.pin_memory), staged copy otherwise
-            return torch.from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=non_blocking)
+        pins = getattr(sm, "_pins", None)   # page-locked torch tensors behind the arrays (SpotMatrix.pin_memory)
 
-        self.col_ptr = up(sm.col_ptr)
-        self.row_idx = up(sm.row_idx)
-        self.val = up(sm.val)
-        self.spot_x = up(sm.spot_x)
-        self.spot_y = up(sm.spot_y)
+        def up(a, k=None):
+            # async DMA straight from the page-locked tensor when there is one, staged copy otherwise
+            t = pins[k] if (pins is not None and k is not None) else torch.from_numpy(np.ascontiguousarray(a))
+            return t.to(self.device, non_blocking=non_blocking)
+
+        self.col_ptr = up(sm.col_ptr, 0)
+        self.row_idx = up(sm.row_idx, 1)
+        self.val = up(sm.val, 2)
+        self.spot_x = up(sm.spot_x, 3)
+        self.spot_y = up(sm.spot_y, 4)
         self._up = up
         self.h2d_bytes = sum(a.nbytes for a in (sm.col_ptr, sm.row_idx, sm.val, sm.spot_x, sm.spot_y))
 

@@ -37,9 +37,12 @@ def test_emd_batch_matches_oracle_and_pivot_sequence(cuda_device, n, ms, R):
     """One source, ragged targets in one launch; same block size -> identical pivot count and cost as the oracle."""
     from stminer_b200.Algorithm.distance import emd_batched
     src, tg = _random_problem(np.random.default_rng(n), n, ms, R)
-    cost, status, iters = emd_batched(src, tg, return_iters=True)
+    # default block size: optimum must agree
+    cost0, status0 = emd_batched(src, tg)
+    cost, status, iters = emd_batched(src, tg, block_size=777, return_iters=True)
     for g, t in enumerate(tg):
-        c, st, it = eo.emd_network_simplex(*src, *t)
+        c, st, it = eo.emd_network_simplex(*src, *t, block_size=777)
+        assert status0[g] == 0 and abs(cost0[g] - c) <= 1e-12 * max(1.0, c)
         assert status[g] == st == 0
         assert iters[g] == it
         assert abs(cost[g] - c) <= 1e-12 * max(1.0, c)
@@ -48,9 +51,9 @@ def test_emd_batch_matches_oracle_and_pivot_sequence(cuda_device, n, ms, R):
 def test_emd_iteration_limit_and_empty(cuda_device):
     from stminer_b200.Algorithm.distance import emd_batched
     src, tg = _random_problem(np.random.default_rng(3), 282, [150], 17)
-    full, st, it = emd_batched(src, tg, return_iters=True)
-    cut, st1, it1 = emd_batched(src, tg, max_iter=int(it[0]) // 2, return_iters=True)
-    ref, rst, rit = eo.emd_network_simplex(*src, *tg[0], max_iter=int(it[0]) // 2)
+    full, st, it = emd_batched(src, tg, block_size=500, return_iters=True)
+    cut, st1, it1 = emd_batched(src, tg, max_iter=int(it[0]) // 2, block_size=500, return_iters=True)
+    ref, rst, rit = eo.emd_network_simplex(*src, *tg[0], max_iter=int(it[0]) // 2, block_size=500)
     assert st[0] == 0 and st1[0] == 1 and rst == 1 and it1[0] == rit
     assert abs(cut[0] - ref) <= 1e-12 * ref          # same sub-optimal basis as the oracle (POT semantics)
     empty = (np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0))

@@ -189,3 +189,27 @@ def test_device_init_then_oracle_em_parity(cuda_device):
         if ref["n_iter"] + 1 != full["n_iter"][g]:
             continue
         assert_gmm_close(full, g, ref, what="gene %d" % g)
+
+
+def test_very_long_gene_chunked_accumulation(cuda_device):
+    """A Stereo-seq bin10-like gene (1000 x 1000 grid, 150k spots): streamed from L2, FP32 accumulators flushed
+    to FP64 every 2048 spots per thread group (BASELINE configs[3], long-nnz genes)."""
+    from stminer_b200.staging import SpotMatrix
+    from oracle import gmm_oracle as go
+    rng = np.random.default_rng(4)
+    R = 1000
+    idx = np.sort(rng.choice(R * R, size=150000, replace=False))
+    x, y = (idx // R).astype(np.int32), (idx % R).astype(np.int32)
+    lam = 0.3 + 3 * np.exp(-((x - 300.0) ** 2 + (y - 650.0) ** 2) / 2e4) + 2 * np.exp(-((x - 720.0) ** 2 + (y - 240.0) ** 2) / 5e4)
+    w = (1 + rng.poisson(lam)).astype(np.float32)
+    sm = SpotMatrix(np.array([0, len(idx)], dtype=np.int64), np.arange(len(idx), dtype=np.int32), w, x, y, ["long"])
+    K = 20
+    # cheap deterministic init (k-means on 150k x ~2.4 replicated rows would dominate the test): blobs on a lattice
+    gx, gy = np.meshgrid(np.linspace(100, 900, 5), np.linspace(125, 875, 4), indexing="ij")
+    mu0 = np.column_stack([gx.ravel(), gy.ravel()]); w0 = np.full(K, 1 / K); cov0 = np.tile(np.eye(2) * 150.0 ** 2, (K, 1, 1))
+    res = _fit(sm, K, (w0[None], mu0[None], cov0[None]), max_iter=12)
+    xy, c = sm.gene_spots(0)
+    ref = go.weighted_em(xy, c, w0, mu0, cov0, max_iter=12)
+    assert res["status"][0] == 0 and res["n_iter"][0] == ref["n_iter"]
+    assert abs(res["lower_bound"][0] - ref["lower_bound"]) < 1e-4
+    assert_gmm_close(res, 0, ref, what="long gene")

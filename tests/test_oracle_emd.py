@@ -25,6 +25,9 @@ def test_network_simplex_matches_lp_golden(c, d):
     # the pivot rule's block size does not change the optimum
     cost2, status2, _ = eo.emd_network_simplex(d["sx"], d["sy"], d["sm"], d["tx"], d["ty"], d["tm"], block_size=17)
     assert status2 == 0 and abs(cost2 - cost) <= 1e-11 * max(1.0, cost)
+    # neither does the candidate-list variant of the pivot rule
+    cost3, status3, _ = eo.emd_network_simplex(d["sx"], d["sy"], d["sm"], d["tx"], d["ty"], d["tm"], cand_threads=256)
+    assert status3 == 0 and abs(cost3 - cost) <= 1e-11 * max(1.0, cost)
 
 
 def test_network_simplex_matches_lp_live():
