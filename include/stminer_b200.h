@@ -40,6 +40,9 @@ extern "C" {
 #define STM_FIT_REMOVE_LOW_EXP_SPOTS 1u /* AlgUtils.py:16-17: w <- round(max(w - mean(nonzero w), 0)) */
 #define STM_FIT_DEVICE_INIT 2u          /* ignore init_*; run the on-device weighted k-means++/Lloyd init
                                            (replaces sklearn KMeans inside GaussianMixture, _base.py:119-128) */
+#define STM_FIT_COMPACT_INPUT 4u        /* row_idx points to uint16 and val to int16 (values already truncated by the
+                                           host, AlgUtils.py:35); needs n_spots <= 65536.  4 B per stored value
+                                           instead of 8: halves the host->device transfer the e2e path is bound by */
 /* optional tuning fields of the device init, 0 = library default */
 #define STM_FIT_LLOYD_ITERS(n) (((uint32_t)(n) & 0xffu) << 8)   /* Lloyd iteration cap (default 8; the EM that follows
                                                                     refines further), 255 = sklearn's 300 */
@@ -61,9 +64,9 @@ const char* stm_last_error_string(void);
  *
  * Input is the expression matrix in CSC form over DISTINCT spots:
  *   col_ptr[G+1]   int64   column (gene) pointers
- *   row_idx[nnz]   int32   spot index of each stored value
+ *   row_idx[nnz]   int32   spot index of each stored value          (uint16 with STM_FIT_COMPACT_INPUT)
  *   val[nnz]       float   expression value; truncated toward zero to int16 inside (AlgUtils.py:35);
- *                          entries whose truncated value is <= 0 are ignored
+ *                          entries whose truncated value is <= 0 are ignored   (int16 with STM_FIT_COMPACT_INPUT)
  *   spot_x, spot_y [n_spots] int32 integer grid coordinates of each spot (adata.obs['x'], ['y'])
  *   gene_order[G]  int32   optional (NULL = 0..G-1): CTA b fits gene gene_order[b]; pass genes sorted by
  *                          decreasing nnz so long genes start first (LPT)

@@ -22,11 +22,14 @@ STM_GENE_DROPPED = 1
 STM_GENE_ILL_CONDITIONED = 2
 STM_FIT_REMOVE_LOW_EXP_SPOTS = 1
 STM_FIT_DEVICE_INIT = 2
+STM_FIT_COMPACT_INPUT = 4
 
 
-def fit_flags(remove_low_exp_spots=False, device_init=False, lloyd_iters=0, kpp_candidates=0, seed_cap=0):
+def fit_flags(remove_low_exp_spots=False, device_init=False, lloyd_iters=0, kpp_candidates=0, seed_cap=0,
+              compact=False):
     """Compose the ``flags`` word of ``stm_gmm_fit_batched`` / ``stm_gmm_fit_plan`` (0 = library default)."""
     f = (STM_FIT_REMOVE_LOW_EXP_SPOTS if remove_low_exp_spots else 0) | (STM_FIT_DEVICE_INIT if device_init else 0)
+    f |= STM_FIT_COMPACT_INPUT if compact else 0
     f |= (int(lloyd_iters) & 0xff) << 8
     f |= (int(kpp_candidates) & 0xf) << 16
     f |= ((int(seed_cap) + 255) // 256 & 0xff) << 20

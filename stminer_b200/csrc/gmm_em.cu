@@ -91,21 +91,30 @@ struct EmArgs {
   uint64_t seed;
 };
 
-// int16 truncation semantics of AlgUtils.py:35 (coo_matrix(..., dtype=np.int16)).
-__device__ __forceinline__ int trunc_i16(float v) {
-  int iv = (int)v;  // toward zero
-  return (int)(short)iv;
-}
-
-// AlgUtils.py:16-17,22-23: round(max(w - mean_nonzero, 0)) when remove_low_exp_spots.
-__device__ __forceinline__ int gene_weight(float v, bool remove_low, double mean_nz) {
-  int w = trunc_i16(v);
-  if (remove_low) {
-    double d = (double)w - mean_nz;
-    w = d > 0.0 ? (int)rint(d) : 0;
+// One gene's column in either input encoding: {int32 row, float value} or, with STM_FIT_COMPACT_INPUT,
+// {uint16 row, int16 value} — half the bytes over PCIe / HBM for matrices with < 65,536 spots whose values
+// the host staging already truncated to int16 (AlgUtils.py:35).
+struct Column {
+  const void* rows; const void* vals; bool compact;
+  __device__ __forceinline__ int row(int i) const {
+    return compact ? (int)__ldg(static_cast<const unsigned short*>(rows) + i)
+                   : __ldg(static_cast<const int32_t*>(rows) + i);
   }
-  return w;
-}
+  __device__ __forceinline__ int trunc_value(int i) const {   // int16 truncation of AlgUtils.py:35
+    if (compact) return (int)__ldg(static_cast<const short*>(vals) + i);
+    const int iv = (int)__ldg(static_cast<const float*>(vals) + i);   // toward zero
+    return (int)(short)iv;
+  }
+  // AlgUtils.py:16-17,22-23: round(max(w - mean_nonzero, 0)) when remove_low_exp_spots
+  __device__ __forceinline__ int weight(int i, bool remove_low, double mean_nz) const {
+    int w = trunc_value(i);
+    if (remove_low) {
+      const double d = (double)w - mean_nz;
+      w = d > 0.0 ? (int)rint(d) : 0;
+    }
+    return w;
+  }
+};
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ULL;
@@ -228,11 +237,11 @@ struct SeedSpots {
 
 // spots of a gene too long to stage: re-read from global memory (L2) every sweep
 struct StreamedSpots {
-  const int32_t* row_idx; const float* val; const int32_t* spot_x; const int32_t* spot_y;
+  Column col; const int32_t* spot_x; const int32_t* spot_y;
   int ox, oy; bool remove_low; double mean_nz;
   __device__ __forceinline__ void get(int i, float& xo, float& yo, float& wo) const {
-    const int r = __ldg(row_idx + i);
-    const int w = gene_weight(__ldg(val + i), remove_low, mean_nz);
+    const int r = col.row(i);
+    const int w = col.weight(i, remove_low, mean_nz);
     xo = (float)(__ldg(spot_x + r) - ox);
     yo = (float)(__ldg(spot_y + r) - oy);
     wo = w > 0 ? (float)w : 0.f;
@@ -579,8 +588,12 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   const int g = p.gene_order ? p.gene_order[slot] : slot;
   const int64_t p0 = p.col_ptr[g], p1 = p.col_ptr[g + 1];
   const int ncol = (int)(p1 - p0);
-  const int32_t* rows = p.row_idx + p0;
-  const float* vals = p.val + p0;
+  const bool compact = (p.flags & STM_FIT_COMPACT_INPUT) != 0;
+  const Column col{compact ? static_cast<const void*>(reinterpret_cast<const unsigned short*>(p.row_idx) + p0)
+                           : static_cast<const void*>(p.row_idx + p0),
+                   compact ? static_cast<const void*>(reinterpret_cast<const short*>(p.val) + p0)
+                           : static_cast<const void*>(p.val + p0),
+                   compact};
   const bool remove_low = (p.flags & STM_FIT_REMOVE_LOW_EXP_SPOTS) != 0;
   const bool device_init = (p.flags & STM_FIT_DEVICE_INIT) != 0;
 
@@ -589,7 +602,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   if (remove_low) {
     long long sum = 0, cnt = 0;
     for (int i = tid; i < ncol; i += T) {
-      const int w = trunc_i16(__ldg(vals + i));
+      const int w = col.trunc_value(i);
       sum += w; cnt += (w != 0);
     }
     sum = warp_sum(sum); cnt = warp_sum(cnt);
@@ -608,15 +621,15 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   // and stages the positive spots (ordered ballot compaction) relative to a provisional origin — the first
   // entry's spot — which is shifted to the integer centroid afterwards, in shared memory.
   const bool try_stage = ncol <= p.smem_spots;
-  const int x0 = ncol > 0 ? __ldg(p.spot_x + __ldg(rows)) : 0, y0 = ncol > 0 ? __ldg(p.spot_y + __ldg(rows)) : 0;
+  const int x0 = ncol > 0 ? __ldg(p.spot_x + col.row(0)) : 0, y0 = ncol > 0 ? __ldg(p.spot_y + col.row(0)) : 0;
   int n_st = 0;
   if (try_stage) {
     for (int base = 0; base < ncol; base += T) {
       const int i = base + tid;
       int w = 0, x = 0, y = 0;
       if (i < ncol) {
-        w = gene_weight(__ldg(vals + i), remove_low, mean_nz);
-        if (w > 0) { const int r = __ldg(rows + i); x = __ldg(p.spot_x + r); y = __ldg(p.spot_y + r); }
+        w = col.weight(i, remove_low, mean_nz);
+        if (w > 0) { const int r = col.row(i); x = __ldg(p.spot_x + r); y = __ldg(p.spot_y + r); }
       }
       const bool keep = w > 0;
       const unsigned bal = __ballot_sync(FULL_MASK, keep);
@@ -638,9 +651,9 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     }
   } else {
     for (int i = tid; i < ncol; i += T) {
-      const int w = gene_weight(__ldg(vals + i), remove_low, mean_nz);
+      const int w = col.weight(i, remove_low, mean_nz);
       if (w > 0) {
-        const int r = __ldg(rows + i);
+        const int r = col.row(i);
         const int x = __ldg(p.spot_x + r), y = __ldg(p.spot_y + r);
         npos += 1; sw += w;
         swx += (long long)w * x;
@@ -695,7 +708,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   }
 
   const PackedSpots staged_src{s_spot};
-  const StreamedSpots stream_src{rows, vals, p.spot_x, p.spot_y, ox, oy, remove_low, mean_nz};
+  const StreamedSpots stream_src{col, p.spot_x, p.spot_y, ox, oy, remove_low, mean_nz};
 
   if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; }
   // padded components never win a max / an argmin
@@ -1173,6 +1186,7 @@ extern "C" int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_id
   if (G == 0) return STM_OK;
   STM_CHECK_ARG(col_ptr && row_idx && val && spot_x && spot_y, "null input pointer");
   STM_CHECK_ARG(n_spots > 0, "n_spots <= 0");
+  STM_CHECK_ARG(!(flags & STM_FIT_COMPACT_INPUT) || n_spots <= 65536, "compact input needs n_spots <= 65536");
   STM_CHECK_ARG(K >= 1 && K <= 64, "K must be in [1, 64]");
   STM_CHECK_ARG(max_iter >= 1, "max_iter < 1");
   STM_CHECK_ARG(out_w && out_mu && out_cov && out_n_iter && out_converged && out_lower_bound && out_status,

@@ -56,7 +56,7 @@ class SpotMatrix:
     def gene_spots(self, g: int):
         """(xy[nnz_g, 2] int64 sorted row-major, counts[nnz_g] int64) of gene g, as the oracle wants them."""
         a, b = int(self.col_ptr[g]), int(self.col_ptr[g + 1])
-        r = self.row_idx[a:b]
+        r = self.row_idx[a:b].astype(np.int64)
         w = np.trunc(self.val[a:b]).astype(np.int64)
         keep = w > 0
         xy = np.column_stack([self.spot_x[r][keep], self.spot_y[r][keep]]).astype(np.int64)
@@ -64,14 +64,60 @@ class SpotMatrix:
         order = np.lexsort((xy[:, 1], xy[:, 0]))
         return xy[order], w[order]
 
+    @property
+    def is_compact(self) -> bool:
+        """True when ``row_idx`` is uint16 and ``val`` int16 (the 4 B / value wire format)."""
+        return self.row_idx.dtype == np.uint16 and self.val.dtype == np.int16
+
+    def compact(self) -> "SpotMatrix":
+        """4 B / value encoding — uint16 spot index + int16 value — for matrices with <= 65,536 spots whose values
+        are already int16 integers (what ``from_matrix`` produces).  Halves the host->device transfer; the
+        kernel reads it with ``STM_FIT_COMPACT_INPUT``.  Returns ``self`` when not applicable."""
+        if self.is_compact:
+            return self
+        if self.n_spots > 65536 or self.nnz == 0:
+            return self
+        v = self.val
+        if not (np.all(v == np.trunc(v)) and v.min() >= -32768 and v.max() <= 32767):
+            return self
+        return SpotMatrix(self.col_ptr, self.row_idx.astype(np.uint16), v.astype(np.int16), self.spot_x, self.spot_y,
+                          list(self.genes))
+
     def pin_memory(self) -> "SpotMatrix":
         """Copy whose arrays live in page-locked host memory, so uploads are true async DMA."""
         import torch
-        pins = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-                for a in (self.col_ptr, self.row_idx, self.val, self.spot_x, self.spot_y)]
-        out = SpotMatrix(*[t.numpy() for t in pins], list(self.genes))
+        def pin(a):
+            a = np.ascontiguousarray(a)
+            if a.dtype == np.uint16:      # torch has no uint16 arithmetic; the bytes are what travels
+                return torch.from_numpy(a.view(np.int16)).pin_memory()
+            return torch.from_numpy(a).pin_memory()
+        pins = [pin(a) for a in (self.col_ptr, self.row_idx, self.val, self.spot_x, self.spot_y)]
+        arrs = [t.numpy() for t in pins]
+        if self.row_idx.dtype == np.uint16:
+            arrs[1] = arrs[1].view(np.uint16)
+        out = SpotMatrix(*arrs, list(self.genes))
         out._pins = pins
         return out
+
+    def slice_genes(self, g0: int, g1: int) -> "SpotMatrix":
+        """Contiguous gene range [g0, g1) as views (no copy of the values; page-locked storage stays page-locked)."""
+        a, b = int(self.col_ptr[g0]), int(self.col_ptr[g1])
+        out = SpotMatrix((self.col_ptr[g0:g1 + 1] - self.col_ptr[g0]).astype(np.int64), self.row_idx[a:b],
+                         self.val[a:b], self.spot_x, self.spot_y, self.genes[g0:g1])
+        pins = getattr(self, "_pins", None)
+        if pins is not None:
+            import torch
+            out._pins = [torch.from_numpy(out.col_ptr), pins[1][a:b], pins[2][a:b], pins[3], pins[4]]
+        return out
+
+    def nnz_balanced_chunks(self, n_chunks: int):
+        """Gene boundaries of ``n_chunks`` contiguous ranges with roughly equal numbers of stored values."""
+        G = self.n_genes
+        n_chunks = max(1, min(int(n_chunks), G))
+        targets = np.linspace(0, self.nnz, n_chunks + 1)
+        cuts = np.searchsorted(self.col_ptr, targets, side="left")
+        cuts[0], cuts[-1] = 0, G
+        return sorted(set(int(c) for c in cuts))
 
     def select(self, idx: Sequence[int]) -> "SpotMatrix":
         idx = np.asarray(idx, dtype=np.int64)
@@ -118,7 +164,7 @@ class SpotMatrix:
 class DeviceSpotMatrix:
     """SpotMatrix resident in HBM (torch tensors are only the buffer owners)."""
 
-    def __init__(self, sm: SpotMatrix, device=None, non_blocking: bool = True):
+    def __init__(self, sm: SpotMatrix, device=None, non_blocking: bool = True, spots=None):
         import torch
         from . import _lib
         _lib.require_cuda()
@@ -130,21 +176,28 @@ class DeviceSpotMatrix:
 
         def up(a, k=None):
             # async DMA straight from the page-locked tensor when there is one, staged copy otherwise
-            t = pins[k] if (pins is not None and k is not None) else torch.from_numpy(np.ascontiguousarray(a))
+            if pins is not None and k is not None:
+                t = pins[k]
+            else:
+                a = np.ascontiguousarray(a)
+                t = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
             return t.to(self.device, non_blocking=non_blocking)
+
+        self.compact = sm.is_compact
 
         self.col_ptr = up(sm.col_ptr, 0)
         self.row_idx = up(sm.row_idx, 1)
         self.val = up(sm.val, 2)
-        self.spot_x = up(sm.spot_x, 3)
-        self.spot_y = up(sm.spot_y, 4)
+        # the spot table is shared by the chunks of a pipelined upload
+        self.spot_x, self.spot_y = spots if spots is not None else (up(sm.spot_x, 3), up(sm.spot_y, 4))
         self._up = up
-        self.h2d_bytes = sum(a.nbytes for a in (sm.col_ptr, sm.row_idx, sm.val, sm.spot_x, sm.spot_y))
+        self.h2d_bytes = sum(a.nbytes for a in (sm.col_ptr, sm.row_idx, sm.val))
+        self.h2d_bytes += 0 if spots is not None else sm.spot_x.nbytes + sm.spot_y.nbytes
 
     def plan(self, K: int, flags: int = 0):
         """(gene_order CUDA tensor, bucket_counts host int32[3]) from ``stm_gmm_fit_plan`` for K components."""
         from . import _lib
-        key = (K, flags & ~1)   # the device-init fields move the bucket boundaries
+        key = (K, flags & ~5)   # the device-init fields move the bucket boundaries
         if key not in self._plans:
             lib = _lib.load()
             G = self.host.n_genes

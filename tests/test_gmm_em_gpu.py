@@ -213,3 +213,26 @@ def test_very_long_gene_chunked_accumulation(cuda_device):
     assert res["status"][0] == 0 and res["n_iter"][0] == ref["n_iter"]
     assert abs(res["lower_bound"][0] - ref["lower_bound"]) < 1e-4
     assert_gmm_close(res, 0, ref, what="long gene")
+
+
+def test_pipelined_host_fit_matches_resident_fit(cuda_device):
+    """fit_spot_matrix_host uploads nnz-balanced gene chunks on a copy stream while earlier chunks are fitted;
+    from fixed initial parameters the result is bit-identical to the one-shot resident fit."""
+    from stminer_b200.Algorithm.distribution import fit_spot_matrix_host
+    from stminer_b200.Simulate import simulate_spot_matrix
+    sm = simulate_spot_matrix("V", seed=3, n_templates=5, replicas=4)
+    K = 8
+    rng = np.random.default_rng(0)
+    G = sm.n_genes
+    W = np.full((G, K), 1.0 / K)
+    MU = np.stack([np.column_stack([rng.uniform(5, 70, K), rng.uniform(5, 120, K)]) for _ in range(G)])
+    COV = np.tile(np.eye(2) * 100.0, (G, K, 1, 1))
+    a = _fit(sm, K, (W, MU, COV))
+    for pinned, compact in ((False, False), (True, False), (True, True), (False, True)):
+        src = sm.pin_memory() if pinned else sm
+        b = fit_spot_matrix_host(src, K, init=(W, MU, COV), n_chunks=5, compact=compact)
+        for k in ("weights", "means", "covariances", "n_iter", "status", "lower_bound"):
+            assert np.array_equal(a[k], b[k]), (k, pinned, compact)
+    c = fit_spot_matrix_host(sm, K, init=None, n_chunks=3, seed=2)
+    d = fit_spot_matrix_host(sm, K, init=None, n_chunks=3, seed=2)
+    assert (c["status"] == 0).all() and np.array_equal(c["means"], d["means"])

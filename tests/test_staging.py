@@ -52,3 +52,21 @@ def test_select_and_lpt_order():
     sub = sm.select([4, 1])
     a = sm.gene_spots(4); b = sub.gene_spots(0)
     assert a[0].tolist() == b[0].tolist() and a[1].tolist() == b[1].tolist()
+
+
+def test_compact_wire_format_round_trip():
+    """uint16 spot index + int16 value (4 B / value) carries the same per-gene spots; matrices that do not
+    qualify (float values, > 65,536 spots) are left alone."""
+    adata, *_ = _random_adata()
+    sm = spot_matrix_from_adata(adata)
+    c = sm.compact()
+    assert c.is_compact and c.row_idx.dtype == np.uint16 and c.val.dtype == np.int16
+    for g in range(sm.n_genes):
+        a, b = sm.gene_spots(g), c.gene_spots(g)
+        assert a[0].tolist() == b[0].tolist() and a[1].tolist() == b[1].tolist()
+    part = c.slice_genes(2, 7)
+    assert part.is_compact and part.n_genes == 5 and part.gene_spots(0)[1].tolist() == sm.gene_spots(2)[1].tolist()
+    floats = spot_matrix_from_adata(adata, truncate_int16=False)
+    assert floats.compact() is floats
+    cuts = sm.nnz_balanced_chunks(4)
+    assert cuts[0] == 0 and cuts[-1] == sm.n_genes and cuts == sorted(cuts)
