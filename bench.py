@@ -213,7 +213,7 @@ def run_ours(args, rank, world, local_rank):
     sm = workload(args.workload, seed=rank, genes=args.genes).compact().pin_memory()
     G = sm.n_genes
     dsm = DeviceSpotMatrix(sm, device=dev)
-    order, buckets = dsm.plan(K_COMP)
+    order, buckets = dsm.plan(K_COMP, _lib.fit_flags(device_init=True, compact=dsm.compact))
     n_launch = int((buckets > 0).sum())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
