@@ -44,10 +44,8 @@ extern "C" {
                                            host, AlgUtils.py:35); needs n_spots <= 65536.  4 B per stored value
                                            instead of 8: halves the host->device transfer the e2e path is bound by */
 /* optional tuning fields of the device init, 0 = library default */
-#define STM_FIT_LLOYD_ITERS(n) (((uint32_t)(n) & 0xffu) << 8)   /* Lloyd iteration cap (default 8; the EM that follows
+#define STM_FIT_LLOYD_ITERS(n) (((uint32_t)(n) & 0xffu) << 8)   /* Lloyd iteration cap (default 4; the EM that follows
                                                                     refines further), 255 = sklearn's 300 */
-#define STM_FIT_KPP_CANDIDATES(n) (((uint32_t)(n) & 0xfu) << 16) /* greedy k-means++ trials per centre (default 2,
-                                                                    max 6), 15 = sklearn's 2 + floor(ln K) */
 #define STM_FIT_SEED_CAP_256(n) (((uint32_t)(n) & 0xffu) << 20)  /* seed-subset capacity in units of 256 spots */
 
 /* Library / build identification. */

@@ -31,7 +31,7 @@ def fit_flags(remove_low_exp_spots=False, device_init=False, lloyd_iters=0, kpp_
     f = (STM_FIT_REMOVE_LOW_EXP_SPOTS if remove_low_exp_spots else 0) | (STM_FIT_DEVICE_INIT if device_init else 0)
     f |= STM_FIT_COMPACT_INPUT if compact else 0
     f |= (int(lloyd_iters) & 0xff) << 8
-    f |= (int(kpp_candidates) & 0xf) << 16
+    del kpp_candidates   # retired: the seeding is plain D^2 sampling by exponential race
     f |= ((int(seed_cap) + 255) // 256 & 0xff) << 20
     return f
 

@@ -20,8 +20,8 @@
 //   * genes are bucketed by nnz on the host (stm_gmm_fit_plan): each bucket gets a CTA size / shared
 //     memory budget that keeps its spots staged on chip; genes beyond the largest budget stream
 //     their spots from L2;
-//   * optional on-device initialisation (weighted greedy k-means++ and Lloyd on a strided seed subset,
-//     then one assignment pass over all spots) replaces the sklearn KMeans the reference runs inside
+//   * optional on-device initialisation (weighted k-means++ by an exponential race and Lloyd on a strided seed
+//     subset, then one assignment pass over all spots) replaces the sklearn KMeans the reference runs inside
 //     GaussianMixture (mixture/_base.py:119-128).
 #include <float.h>
 #include <limits.h>
@@ -59,7 +59,7 @@ constexpr int KM_LMAX = 6;                // greedy k-means++ candidates: 2 + fl
 #define STM_KM_DEFAULT_CAND 2     // greedy k-means++ trials per centre when the flags field is 0
 #endif
 #ifndef STM_KM_DEFAULT_LLOYD
-#define STM_KM_DEFAULT_LLOYD 8    // Lloyd iteration cap when the flags field is 0 (EM refines further)
+#define STM_KM_DEFAULT_LLOYD 4    // Lloyd iteration cap when the flags field is 0 (EM refines further)
 #endif
 
 struct EmArgs {
@@ -122,12 +122,6 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
   return z ^ (z >> 31);
 }
-// counter-based uniform in [0, 1): hash of (seed, gene, counter)
-__device__ __forceinline__ double u01(uint64_t seed, uint64_t gene, uint64_t ctr) {
-  const uint64_t h = splitmix64(splitmix64(seed ^ (gene * 0xD1342543DE82EF95ULL)) + ctr);
-  return (double)(h >> 11) * (1.0 / 9007199254740992.0);
-}
-
 template <int N, int OFF, int NMAX>
 __device__ __forceinline__ void halving_reduce(float (&v)[NMAX], int lane, int& shift) {
   if constexpr (OFF < 32) {
@@ -523,42 +517,6 @@ __device__ __forceinline__ void flush_stats(float (&acc)[NPAD], double* s_d, flo
   __syncthreads();
 }
 
-// Weighted draw of L indices from the seed set: P(i) ~ value(i), thread-major element order.
-// part = this thread's sum of value(i) over its elements i = tid, tid+T, ...
-template <int T, typename ValueFn>
-__device__ __forceinline__ void weighted_pick(double part, int L, const double* u, int ns, ValueFn value,
-                                              double* s_scr, int* s_pick, int tid) {
-  constexpr int WARPS = T / 32;
-  const int lane = tid & 31, warp = tid >> 5;
-  double incl = part;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double v = __shfl_up_sync(FULL_MASK, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) s_scr[warp] = incl;
-  __syncthreads();
-  double warp_off = 0.0, total = 0.0;
-#pragma unroll
-  for (int w = 0; w < WARPS; ++w) { const double v = s_scr[w]; if (w < warp) warp_off += v; total += v; }
-  const double hi = warp_off + incl, lo = hi - part;
-  const bool last_owner = (tid == T - 1) || (tid == ns - 1 && ns < T);
-  for (int l = 0; l < L; ++l) {
-    const double r = u[l] * total;
-    if ((r >= lo && r < hi) || (last_owner && r >= hi)) {
-      double res = r - lo;
-      int pick = -1, last_pos = -1;
-      for (int i = tid; i < ns; i += T) {
-        const double v = value(i);
-        if (v > 0.0) { last_pos = i; if (res < v && pick < 0) pick = i; res -= v; }
-      }
-      if (pick < 0) pick = last_pos;  // rounding fell off the end
-      if (pick >= 0) s_pick[l] = pick;
-    }
-  }
-  __syncthreads();
-}
-
 template <int KT, int GS, int S, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   using L = EmLayout<KT, GS, T>;
@@ -578,7 +536,6 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   int2* s_spot = reinterpret_cast<int2*>(s_seed + p.seed_cap);
   __shared__ int s_cnt[WARPS];
   __shared__ int s_flag[4];
-  __shared__ int s_pick[KM_LMAX];
   __shared__ int s_ext[4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -597,6 +554,12 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   const bool remove_low = (p.flags & STM_FIT_REMOVE_LOW_EXP_SPOTS) != 0;
   const bool device_init = (p.flags & STM_FIT_DEVICE_INIT) != 0;
 
+#ifdef STM_EM_PROFILE
+  long long pf_t = clock64(), pf_pro = 0, pf_seed = 0, pf_lloyd = 0, pf_assign = 0, pf_em = 0;
+#define EM_PROF(x) { const long long _c = clock64(); x += _c - pf_t; pf_t = _c; }
+#else
+#define EM_PROF(x)
+#endif
   // ---- pre-pass: weights, N, origin, extent -------------------------------------------------
   double mean_nz = 0.0;
   if (remove_low) {
@@ -624,27 +587,41 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   const int x0 = ncol > 0 ? __ldg(p.spot_x + col.row(0)) : 0, y0 = ncol > 0 ? __ldg(p.spot_y + col.row(0)) : 0;
   int n_st = 0;
   if (try_stage) {
-    for (int base = 0; base < ncol; base += T) {
-      const int i = base + tid;
-      int w = 0, x = 0, y = 0;
-      if (i < ncol) {
-        w = col.weight(i, remove_low, mean_nz);
-        if (w > 0) { const int r = col.row(i); x = __ldg(p.spot_x + r); y = __ldg(p.spot_y + r); }
+    // 4 consecutive entries per thread and step: 8 independent loads + 8 gathers in flight per thread, and a
+    // quarter of the barriers of a one-entry-per-thread compaction (the loop is global-latency bound)
+    constexpr int E = 4;
+    for (int base = 0; base < ncol; base += E * T) {
+      int w[E], x[E], y[E];
+      int cnt = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = base + E * tid + e;
+        w[e] = i < ncol ? col.weight(i, remove_low, mean_nz) : 0;
       }
-      const bool keep = w > 0;
-      const unsigned bal = __ballot_sync(FULL_MASK, keep);
-      if (lane == 0) s_cnt[warp] = __popc(bal);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = base + E * tid + e;
+        x[e] = 0; y[e] = 0;
+        if (w[e] > 0) { const int r = col.row(i); x[e] = __ldg(p.spot_x + r); y[e] = __ldg(p.spot_y + r); ++cnt; }
+      }
+      int incl = cnt;   // inclusive warp scan of the per-thread keep counts
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += v; }
+      if (lane == 31) s_cnt[warp] = incl;
       __syncthreads();
       int off = n_st, tot = 0;
 #pragma unroll
       for (int ww = 0; ww < WARPS; ++ww) { const int c = s_cnt[ww]; if (ww < warp) off += c; tot += c; }
-      if (keep) {
-        npos += 1; sw += w;
-        swx += (long long)w * x;
-        swy += (long long)w * y;
-        xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
-        const int idx = off + __popc(bal & ((1u << lane) - 1u));
-        s_spot[idx] = make_int2(pack_xy(x - x0, y - y0), __float_as_int((float)w));
+      int idx = off + incl - cnt;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if (w[e] > 0) {
+          npos += 1; sw += w[e];
+          swx += (long long)w[e] * x[e];
+          swy += (long long)w[e] * y[e];
+          xmin = min(xmin, x[e]); xmax = max(xmax, x[e]); ymin = min(ymin, y[e]); ymax = max(ymax, y[e]);
+          s_spot[idx++] = make_int2(pack_xy(x[e] - x0, y[e] - y0), __float_as_int((float)w[e]));
+        }
       }
       n_st += tot;
       __syncthreads();
@@ -723,6 +700,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   }
   __syncthreads();
 
+  EM_PROF(pf_pro)
   if (device_init) {
     // =========================================================================================
     // Seed subset (every stride-th spot, at most seed_cap) -> weighted greedy k-means++ -> Lloyd on the
@@ -737,81 +715,52 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
       s_seed[j] = make_float4(x, y, w, 0.f);
     }
     __syncthreads();
-    const int Lc = max(1, min(KM_LMAX, p.km_cand));
+    // k-means++ (D^2 sampling, Arthur & Vassilvitskii) by an exponential race: drawing index i with probability
+    // v_i / sum(v) is arg-min_i E_i / v_i with E_i ~ Exp(1), so one pass updates the squared distances to the
+    // centre just chosen AND races for the next centre, and the draw is a single block arg-min — no prefix
+    // sums, no inverse-CDF walk.  E_i comes from a counter-based hash of (seed, gene, round, i).
     double* s_scr = s_d + L::D_SCR;
-    double* s_pot = s_scr + WARPS * KM_LMAX;  // [KM_LMAX] reduced candidate potentials
-    {  // first centre ~ w
-      double part = 0.0;
-      for (int i = tid; i < ns; i += T) part += (double)s_seed[i].z;
-      double u[1] = {u01(p.seed, (uint64_t)g, 0)};
-      weighted_pick<T>(part, 1, u, ns, [&](int i) { return (double)s_seed[i].z; }, s_scr, s_pick, tid);
-    }
-    float ccx = s_seed[s_pick[0]].x, ccy = s_seed[s_pick[0]].y;
-    if (tid == 0) { s_par[6] = ccx; s_par[7] = ccy; }
-    __syncthreads();
-    double part = 0.0;
-    for (int i = tid; i < ns; i += T) {
-      float4 v = s_seed[i];
-      const float dx = v.x - ccx, dy = v.y - ccy;
-      v.w = fmaf(dx, dx, dy * dy);
-      s_seed[i] = v;
-      part += (double)(v.z * v.w);
-    }
-    for (int c = 1; c < K; ++c) {
-      double u[KM_LMAX];
-      for (int l = 0; l < Lc; ++l) u[l] = u01(p.seed, (uint64_t)g, (uint64_t)c * 8 + l);
-      weighted_pick<T>(part, Lc, u, ns, [&](int i) { const float4 v = s_seed[i]; return (double)(v.z * v.w); },
-                       s_scr, s_pick, tid);
-      int bl = 0;
-      if (Lc > 1) {
-        float candx[KM_LMAX], candy[KM_LMAX], pot[KM_LMAX];
-#pragma unroll
-        for (int l = 0; l < KM_LMAX; ++l) {
-          const float4 v = s_seed[s_pick[l < Lc ? l : 0]];
-          candx[l] = v.x; candy[l] = v.y; pot[l] = 0.f;
-        }
-        for (int i = tid; i < ns; i += T) {
-          const float4 v = s_seed[i];
-#pragma unroll
-          for (int l = 0; l < KM_LMAX; ++l) {
-            if (l < Lc) {
-              const float dx = v.x - candx[l], dy = v.y - candy[l];
-              pot[l] = fmaf(v.z, fminf(v.w, fmaf(dx, dx, dy * dy)), pot[l]);
-            }
-          }
-        }
-#pragma unroll
-        for (int l = 0; l < KM_LMAX; ++l) {
-          if (l < Lc) {
-            const double v = warp_sum((double)pot[l]);
-            if (lane == 0) s_scr[warp * KM_LMAX + l] = v;
-          }
-        }
-        __syncthreads();
-        if (tid < Lc) {
-          double t = 0.0;
-          for (int w = 0; w < WARPS; ++w) t += s_scr[w * KM_LMAX + tid];
-          s_pot[tid] = t;
-        }
-        __syncthreads();
-        for (int l = 1; l < Lc; ++l) if (s_pot[l] < s_pot[bl]) bl = l;
-      }
-      ccx = s_seed[s_pick[bl]].x; ccy = s_seed[s_pick[bl]].y;
-      if (tid == 0) { s_par[8 * c + 6] = ccx; s_par[8 * c + 7] = ccy; }
-      __syncthreads();  // every thread has read the winning seed before any d2 is rewritten
-      part = 0.0;
+    unsigned long long* s_race = reinterpret_cast<unsigned long long*>(s_scr);             // [WARPS]
+    const unsigned hseed = (unsigned)splitmix64(p.seed ^ ((uint64_t)g * 0xD1342543DE82EF95ULL));
+    float ccx = 0.f, ccy = 0.f;
+    for (int c = 0; c < K; ++c) {
+      unsigned long long best = ~0ULL;
       for (int i = tid; i < ns; i += T) {
         float4 v = s_seed[i];
-        const float dx = v.x - ccx, dy = v.y - ccy;
-        v.w = fminf(v.w, fmaf(dx, dx, dy * dy));
-        s_seed[i] = v;
-        part += (double)(v.z * v.w);
+        float val = v.z;                                   // round 0: P(i) ~ w_i
+        if (c > 0) {
+          const float dx = v.x - ccx, dy = v.y - ccy;
+          const float d = fmaf(dx, dx, dy * dy);
+          v.w = c == 1 ? d : fminf(v.w, d);
+          s_seed[i].w = v.w;
+          val = v.z * v.w;                                 // P(i) ~ w_i * D_i^2
+        }
+        if (val > 0.f) {
+          unsigned h = hseed ^ ((unsigned)c * 0x85EBCA77u) ^ ((unsigned)i * 0xC2B2AE3Du);
+          h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+          const float u = (float)((h >> 8) + 1u) * 5.9604645e-8f;          // (0, 1]
+          const float key = -lg2_approx(u) * rcp_approx(val);                // Exp(1) / v_i, >= 0
+          const unsigned long long kk = ((unsigned long long)__float_as_uint(key) << 32) | (unsigned)i;
+          best = min(best, kk);
+        }
       }
-      __syncthreads();  // s_pick / s_pot are rewritten by the next round
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(FULL_MASK, best, o));
+      if (lane == 0) s_race[warp] = best;
+      __syncthreads();
+      best = s_race[0];
+#pragma unroll
+      for (int w = 1; w < WARPS; ++w) best = min(best, s_race[w]);
+      const int pick = best == ~0ULL ? 0 : (int)(unsigned)best;   // all remaining mass on chosen centres: reuse seed 0
+      const float4 pv = s_seed[pick];
+      ccx = pv.x; ccy = pv.y;
+      if (tid == 0) { s_par[8 * c + 6] = ccx; s_par[8 * c + 7] = ccy; }
+      __syncthreads();   // s_race is rewritten and s_seed[].w updated in the next round
     }
     if (tid < K) { s_d[L::D_MU + 2 * tid] = (double)s_par[8 * tid + 6]; s_d[L::D_MU + 2 * tid + 1] = (double)s_par[8 * tid + 7]; }
     __syncthreads();
 
+    EM_PROF(pf_seed)
     // tolerance of sklearn KMeans: tol * mean(var(X, axis=0)) with tol = 1e-4 (cluster/_kmeans.py _tolerance),
     // estimated on the seed subset
     const SeedSpots seed_src{s_seed};
@@ -867,20 +816,20 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
       __syncthreads();
       if (done) break;
     }
-    // assignment pass over all spots with second moments -> initial (w, mu, cov)
+    EM_PROF(pf_lloyd)
+    // assignment pass with second moments -> initial (w, mu, cov): one-hot responsibilities as sklearn's
+    // _initialize, evaluated on the seed subset (every stride-th spot) — the first EM iteration sees all spots
     {
       float cx[KT], cy[KT];
 #pragma unroll
       for (int j = 0; j < KT; ++j) { cx[j] = s_par[8 * (sub * KT + j) + 6]; cy[j] = s_par[8 * (sub * KT + j) + 7]; }
       for (int i = tid; i < NSTAT; i += T) s_d[L::D_STAT + i] = 0.0;
       __syncthreads();
-      for (int c0 = 0; c0 < n_spots; c0 += CHUNK) {
-        const int c1 = min(n_spots, c0 + CHUNK);
+      {
         float acc[NPAD];
 #pragma unroll
         for (int i = 0; i < NPAD; ++i) acc[i] = 0.f;
-        if (staged) assign_moments_sweep<KT, GS, T>(staged_src, c0, c1, grp, sub, cx, cy, acc);
-        else        assign_moments_sweep<KT, GS, T>(stream_src, c0, c1, grp, sub, cx, cy, acc);
+        assign_moments_sweep<KT, GS, T>(seed_src, 0, ns, grp, sub, cx, cy, acc);
         flush_stats<KT, GS, T, NPAD>(acc, s_d, s_red, tid);
       }
       if (tid < K) {
@@ -894,7 +843,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
         s_d[L::D_COV + 3 * k] = st[3] / n - ddx * ddx + p.reg_covar;
         s_d[L::D_COV + 3 * k + 1] = st[4] / n - ddx * ddy;
         s_d[L::D_COV + 3 * k + 2] = st[5] / n - ddy * ddy + p.reg_covar;
-        s_d[L::D_W + k] = n / N_total;                // weights /= n_samples, _gaussian_mixture.py:866
+        s_d[L::D_W + k] = n / fmax(vw, 1.0);          // weights /= n_samples (of the subset), _gaussian_mixture.py:866
       }
     }
   } else if (tid < K) {
@@ -915,6 +864,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   }
   __syncthreads();
 
+  EM_PROF(pf_assign)
   // ---- EM loop (sklearn mixture/_base.py:265-278) ---------------------------------------------
   double lb_prev = -INFINITY, lb = 0.0;
   int n_iter = 0, converged = 0;
@@ -1020,6 +970,12 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     if (fabs(change) < p.tol) { converged = 1; break; }
   }
 
+  EM_PROF(pf_em)
+#ifdef STM_EM_PROFILE
+  if (tid == 0 && (blockIdx.x % 997) == 3)
+    printf("[em prof] T=%d gene=%d ncol=%d n_spots=%d staged=%d n_iter=%d cycles: prologue %lld seed %lld lloyd %lld assign+refresh %lld em %lld (%.0f/iter)\n",
+           T, g, ncol, n_spots, (int)staged, n_iter, pf_pro, pf_seed, pf_lloyd, pf_assign, pf_em, (double)pf_em / max(n_iter, 1));
+#endif
   // ---- outputs --------------------------------------------------------------------------------
   if (failed) {
     for (int i = tid; i < K; i += T) o_w[i] = 0.0;
@@ -1206,9 +1162,9 @@ extern "C" int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_id
   a.out_w = out_w; a.out_mu = out_mu; a.out_cov = out_cov; a.out_n_iter = out_n_iter;
   a.out_converged = out_converged; a.out_lb = out_lower_bound; a.out_status = out_status;
   a.G = G; a.K = K; a.max_iter = max_iter; a.flags = flags; a.reg_covar = reg_covar; a.tol = tol; a.seed = seed;
-  const int user_lloyd = (int)((flags >> 8) & 0xff), user_cand = (int)((flags >> 16) & 0xf);
+  const int user_lloyd = (int)((flags >> 8) & 0xff);
   a.km_max_iter = user_lloyd ? (user_lloyd == 255 ? KM_MAX_ITER : user_lloyd) : STM_KM_DEFAULT_LLOYD;
-  a.km_cand = user_cand ? (user_cand == 15 ? 2 + (int)floor(log((double)K)) : user_cand) : STM_KM_DEFAULT_CAND;
+  a.km_cand = 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int n_active = 0;
   for (int b = 0; b < N_BUCKETS; ++b) n_active += counts[b] > 0;
