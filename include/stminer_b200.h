@@ -147,7 +147,7 @@ int stm_gmm_dist_one_vs_all(const double* qw, const double* qmu, const double* q
  *   tgt_ptr[G+1] int64, tgt_x, tgt_y int32, tgt_mass float64 (positive; normalised per target)
  *   max_tgt      largest target support in the batch; order[G] optional processing order (largest first)
  *   max_iter     pivot limit (reference: numItermax=200000); block_size: arcs priced per block search step,
- *                0 = max(sqrt(n*m), 32 per thread) (LEMON/POT use sqrt(n*m))
+ *                0 = about 32 arcs per thread rounded to whole target rows (LEMON/POT use sqrt(n*m))
  *   workspace    device scratch of at least stm_emd_workspace_bytes(n_src, max_tgt, n_ctas) bytes; n_ctas CTAs
  *                (one problem at a time each) pull problems from a queue
  *   out_cost[G] float64 = sum_ij G_ij * M_ij;  out_iters[G] (nullable) pivots;  out_status[G]:

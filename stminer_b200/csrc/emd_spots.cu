@@ -25,6 +25,7 @@ namespace {
 
 constexpr int EMD_PREP_THREADS = 256;
 constexpr int EMD_MAXPATH = 2048;
+constexpr int EMD_RMAX = 5;   // sources per thread kept in registers by the whole-row pricing path
 constexpr double EMD_SCALE = 1125899906842624.0;  // 2^50
 constexpr unsigned short NONE16 = 0xffffu;
 
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
   unsigned short* s_S = s_P + EMD_MAXPATH;
   __shared__ double s_scr[EMD_WARPS];
   __shared__ long long s_ll[3 * EMD_WARPS];
-  __shared__ long long s_key[EMD_WARPS];
+  __shared__ unsigned long long s_slot[2];
   __shared__ int s_i[16];
   __shared__ long long s_delta;
 
@@ -188,11 +189,16 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     // pricing block: LEMON uses sqrt(#arcs); a CTA prices in parallel, so larger blocks (fewer, better pivots and
     // fewer barriers per arc) win — 32 arcs per thread measured best on Visium-size problems
     int B = p.block_size > 0 ? p.block_size : max((int)sqrt((double)n_arcs), 32 * EMD_THREADS);
+    if (p.block_size <= 0 && n <= EMD_RMAX * EMD_THREADS) B = max(1, (B + n / 2) / n) * n;   // whole target rows
     if (B < 10) B = 10;
     if (B > n_arcs) B = n_arcs;
+    const bool whole_rows = B % n == 0 && n <= EMD_RMAX * EMD_THREADS;   // n_arcs and every block start are multiples of n
     int next_arc = 0;
     long long it = 0;
     int status = 0;
+    unsigned round = 0;
+    if (tid == 0) { s_slot[0] = ~0ULL; s_slot[1] = ~0ULL; }
+    __syncthreads();
 
 #ifdef STM_EMD_PROFILE
     long long c_price = 0, c_walk = 0, c_leave = 0, c_update = 0, n_scanned = 0, c_t0 = 0, sum_len = 0, sum_s = 0, sum_range = 0;
@@ -208,32 +214,69 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
       int scanned = 0, best_e = -1, best_rc = 0;
       while (scanned < n_arcs) {
         const int cnt = min(B, n_arcs - scanned);
+        // The block is arcs [next_arc, next_arc + cnt) of the j-major arc order (wrapping): a few target rows,
+        // each a contiguous range of sources.  Per row the target's terms stay in registers and the inner loop is
+        // two shared loads, two IMADs and a compare per arc.
         long long key = LLONG_MAX;
-        if (tid < cnt) {
-          int e = next_arc + tid;
-          if (e >= n_arcs) e -= n_arcs;
-          int j = e / n, i = e - j * n;
-          int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
-          int brc = 0, bk = -1;
-          for (int k = tid; k < cnt; k += EMD_THREADS) {
-            const int xy = s_xy[i];
-            const int rc = ((xy << 16) >> 16) * nx2 + ((xy >> 16) * ny2 + (s_pi[i] - bj));
-            if (rc < brc) { brc = rc; bk = k; }
-            i += EMD_THREADS;
-            if (i >= n) {   // next target row(s): reload the target's terms
-              do { i -= n; if (++j >= m) j = 0; } while (i >= n);
-              txy = s_xy[n + j]; nx2 = -2 * ((txy << 16) >> 16); ny2 = -2 * (txy >> 16); bj = s_pi[n + j];
+        {
+          int brc = 0, bi = -1, bj_best = 0;
+          if (whole_rows) {
+            // Fast path (the default block size is a whole number of target rows): every thread keeps ITS sources'
+            // terms in registers for the whole block and meets each target row with no shared-memory traffic
+            // beyond the row's three broadcast words — six integer instructions per arc.
+            int sx[EMD_RMAX], sy[EMD_RMAX], sp[EMD_RMAX];
+#pragma unroll
+            for (int r = 0; r < EMD_RMAX; ++r) {
+              const int i = tid + r * EMD_THREADS;
+              const int xy = i < n ? s_xy[i] : 0;
+              sx[r] = (xy << 16) >> 16; sy[r] = xy >> 16;
+              sp[r] = i < n ? s_pi[i] : INT_MAX / 2;     // never the minimum
+            }
+            int j = next_arc / n;
+            for (int rr = cnt / n; rr > 0; --rr) {
+              const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
+#pragma unroll
+              for (int r = 0; r < EMD_RMAX; ++r) {
+                const int rc = sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj));
+                if (rc < brc) { brc = rc; bi = tid + r * EMD_THREADS; bj_best = j; }
+              }
+              if (++j >= m) j = 0;
+            }
+          } else {
+            // general block: arcs [next_arc, next_arc + cnt) of the j-major order (wrapping) = a few target rows,
+            // each a contiguous range of sources
+            int left = cnt;
+            int j = next_arc / n, lo = next_arc - j * n;
+            while (left > 0) {
+              const int hi = min(n, lo + left);
+              const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
+              for (int i = lo + tid; i < hi; i += EMD_THREADS) {
+                const int xy = s_xy[i];
+                const int rc = ((xy << 16) >> 16) * nx2 + ((xy >> 16) * ny2 + (s_pi[i] - bj));
+                if (rc < brc) { brc = rc; bi = i; bj_best = j; }
+              }
+              left -= hi - lo;
+              lo = 0;
+              if (++j >= m) j = 0;
             }
           }
-          if (bk >= 0) key = ((long long)brc << 32) | (unsigned)bk;
+          if (bi >= 0) {
+            int k = bj_best * n + bi - next_arc;   // position in block order decides ties, as in the serial scan
+            if (k < 0) k += n_arcs;
+            key = ((long long)brc << 32) | (unsigned)k;
+          }
         }
         for (int o = 16; o > 0; o >>= 1) key = min(key, shfl_xor_ll(key, o));
-        if (lane == 0) s_key[warp] = key;
-        __syncthreads();
-        key = s_key[0];
-#pragma unroll
-        for (int w = 1; w < EMD_WARPS; ++w) key = min(key, s_key[w]);
-        __syncthreads();
+        // cross-warp minimum: one shared atomicMin per warp on a double-buffered slot (thread 0 re-arms the other
+        // slot before this round's barrier, so the next round's atomics always find it armed)
+        {
+          unsigned long long* slot = s_slot + (round & 1);
+          if (tid == 0) s_slot[(round + 1) & 1] = ~0ULL;
+          if (lane == 0) atomicMin(slot, (unsigned long long)key ^ 0x8000000000000000ULL);
+          __syncthreads();
+          key = (long long)(*slot ^ 0x8000000000000000ULL);
+          ++round;
+        }
         const int rc = (int)(key >> 32);
         const int start = next_arc;
         scanned += cnt;
