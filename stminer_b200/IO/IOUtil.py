@@ -19,56 +19,61 @@ from scipy import sparse
 
 
 class STMinerIOError(ValueError):
-    """IO layer error with actionable context for users."""
+    """Raised by the IO helpers; subclass of ValueError like the reference's (IOUtil.py:10)."""
 
 
-def format_io_error(message, *, path=None, operation=None, expected=None, actual=None, hint=None) -> str:
-    parts = [message]
-    for key, val in (("operation", operation), ("path", path), ("expected", expected), ("actual", actual),
-                     ("hint", hint)):
-        if val:
-            parts.append("%s=%s" % (key, val))
-    return " | ".join(parts)
+_FIELDS = ("operation", "path", "expected", "actual", "hint")
+
+
+def format_io_error(message, **context) -> str:
+    """``message | operation=... | path=... | expected=... | actual=... | hint=...`` — empty fields are skipped and
+    the field order is fixed, which is the text format of the reference's IO errors (IOUtil.py:14-34)."""
+    return " | ".join([message] + ["%s=%s" % (f, context[f]) for f in _FIELDS if context.get(f)])
+
+
+def _bad_parameter(name, path, expected, actual):
+    return STMinerIOError(format_io_error("Invalid parameter '%s'" % name, operation="validate parameter", path=path,
+                                          expected=expected, actual=actual))
 
 
 def require_positive_int(value, name: str, *, path=None) -> int:
-    def fail(expected, actual):
-        raise STMinerIOError(format_io_error("Invalid parameter '%s'" % name, operation="validate parameter",
-                                             path=path, expected=expected, actual=actual))
+    """Positive-integer parameter check with the reference's policy (IOUtil.py:37-96): bools are rejected, floats
+    are truncated with a UserWarning (non-finite ones rejected), anything else non-integral is rejected, and the
+    result must be > 0."""
+    kind = type(value).__name__
     if isinstance(value, bool):
-        fail("positive integer", "%s (%s)" % (value, type(value).__name__))
+        raise _bad_parameter(name, path, "positive integer", "%s (%s)" % (value, kind))
     if isinstance(value, (float, np.floating)):
         if not np.isfinite(value):
-            fail("finite positive integer", str(value))
-        as_int = int(value)
+            raise _bad_parameter(name, path, "finite positive integer", str(value))
+        truncated = int(value)
         warnings.warn(format_io_error("Float parameter '%s' converted to int" % name, operation="validate parameter",
-                                      path=path, expected="integer input", actual="%s -> %s" % (value, as_int),
+                                      path=path, expected="integer input", actual="%s -> %s" % (value, truncated),
                                       hint="Pass int explicitly to avoid implicit conversion"),
                       UserWarning, stacklevel=2)
-        value = as_int
+        value = truncated
     elif not isinstance(value, (int, np.integer)):
-        fail("> 0", "%s (%s)" % (value, type(value).__name__))
-    value = int(value)
-    if value <= 0:
-        fail("> 0", str(value))
-    return value
+        raise _bad_parameter(name, path, "> 0", "%s (%s)" % (value, kind))
+    if int(value) <= 0:
+        raise _bad_parameter(name, path, "> 0", str(int(value)))
+    return int(value)
 
 
 def validate_spatial_array(spatial, *, path=None, source="adata.obsm['spatial']") -> np.ndarray:
+    """Spatial coordinates must be a numeric (n, >=2) array with finite x / y (IOUtil.py:99-133)."""
     arr = np.asarray(spatial)
+    problem = None
     if arr.ndim != 2 or arr.shape[1] < 2:
-        raise STMinerIOError(format_io_error("Invalid spatial coordinates", operation="validate spatial", path=path,
-                                             expected="2D array with at least 2 columns", actual="shape=%s" % (arr.shape,),
-                                             hint="Ensure %s exists and stores x/y coordinates" % source))
-    if not np.issubdtype(arr.dtype, np.number):
-        raise STMinerIOError(format_io_error("Spatial coordinates must be numeric", operation="validate spatial",
-                                             path=path, expected="numeric array", actual=str(arr.dtype),
-                                             hint="Convert %s to numeric values before loading" % source))
-    xy = arr[:, :2].astype(np.float64)
-    if not np.isfinite(xy).all():
-        raise STMinerIOError(format_io_error("Spatial coordinates contain NaN/Inf", operation="validate spatial",
-                                             path=path, expected="finite numeric x/y values",
-                                             actual="contains NaN or Inf"))
+        problem = ("Invalid spatial coordinates", "2D array with at least 2 columns", "shape=%s" % (arr.shape,),
+                   "Ensure %s exists and stores x/y coordinates" % source)
+    elif not np.issubdtype(arr.dtype, np.number):
+        problem = ("Spatial coordinates must be numeric", "numeric array", str(arr.dtype),
+                   "Convert %s to numeric values before loading" % source)
+    elif not np.isfinite(arr[:, :2].astype(np.float64)).all():
+        problem = ("Spatial coordinates contain NaN/Inf", "finite numeric x/y values", "contains NaN or Inf", None)
+    if problem is not None:
+        raise STMinerIOError(format_io_error(problem[0], operation="validate spatial", path=path, expected=problem[1],
+                                             actual=problem[2], hint=problem[3]))
     return arr
 
 
