@@ -123,7 +123,7 @@ def fit_spot_matrix(dsm: DeviceSpotMatrix, n_comp: int, init=None, max_iter: int
     return out
 
 
-def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_chunks: int = 8, **kw) -> dict:
+def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_chunks: int = 4, **kw) -> dict:
     """Host buffers in, host buffers out — the call ``bench.py`` times end to end.
 
     The CSC matrix is uploaded in ``n_chunks`` nnz-balanced gene ranges on a copy stream while the previous
@@ -133,35 +133,46 @@ def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_
     torch = _lib.require_cuda()
     dev = torch.device(device if device is not None else "cuda")
     G, K = sm.n_genes, int(n_comp)
-    cuts = sm.nnz_balanced_chunks(n_chunks)
     if kw.pop("compact", True):
         sm = sm.compact()          # 4 B / value on the wire when the matrix allows it (no-op otherwise)
+    cuts = sm.nnz_balanced_chunks(n_chunks)
+    from ..staging import StreamedDeviceSpotMatrix
     with torch.cuda.device(dev):
         compute = torch.cuda.current_stream()
-        copy = torch.cuda.Stream()
+        copy = _copy_stream(dev)
         f64 = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
         i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
         full = FitResult(sm.genes, f64(G, K), f64(G, K, 2), f64(G, K, 2, 2), i32(G), i32(G), f64(G), i32(G))
-        keep, spots = [], None
+        whole = StreamedDeviceSpotMatrix(sm, dev)          # buffers allocated once, on the compute stream
         copy.wait_stream(compute)
+        keep = []
         for g0, g1 in zip(cuts[:-1], cuts[1:]):
-            part = sm.slice_genes(g0, g1)
             with torch.cuda.stream(copy):
-                dsm = DeviceSpotMatrix(part, device=dev, spots=spots)
-                order_buckets = dsm.plan(K, _lib.fit_flags(kw.get("remove_low_exp_spots", False), init is None,
-                                                        kw.get("lloyd_iters", 0), kw.get("kpp_candidates", 0),
-                                                        kw.get("seed_cap", 0), compact=dsm.compact))
-                spots = (dsm.spot_x, dsm.spot_y)
+                whole.upload_genes(g0, g1)
                 ready = torch.cuda.Event()
                 ready.record(copy)
+            view = whole.gene_view(g0, g1)
             compute.wait_event(ready)
-            out = FitResult(part.genes, full.weights[g0:g1], full.means[g0:g1], full.covariances[g0:g1],
+            out = FitResult(view.host.genes, full.weights[g0:g1], full.means[g0:g1], full.covariances[g0:g1],
                             full.n_iter[g0:g1], full.converged[g0:g1], full.lower_bound[g0:g1], full.status[g0:g1])
             sub_init = None if init is None else tuple(np.asarray(a)[g0:g1] for a in init)
-            fit_spot_matrix(dsm, K, init=sub_init, out=out, **kw)
-            keep.append((dsm, order_buckets, out))
+            fit_spot_matrix(view, K, init=sub_init, out=out, **kw)
+            keep.append((view, out))
         host = full.to_host()
+        compute.wait_stream(copy)
     return host
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    """One side stream per device for the chunked uploads (created once)."""
+    import torch
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
 
 
 def result_to_gmm_dict(genes: Sequence[str], host: dict) -> Dict[str, GMM]:

@@ -217,3 +217,60 @@ class DeviceSpotMatrix:
     @property
     def n_spots(self) -> int:
         return self.host.n_spots
+
+
+class StreamedDeviceSpotMatrix:
+    """Device buffers for the WHOLE matrix allocated once (on the caller's stream), filled gene range by gene range
+    on a copy stream.  ``gene_view(g0, g1)`` is what ``fit_spot_matrix`` needs to fit that range: the column
+    pointers of the range keep their absolute offsets into the full ``row_idx`` / ``val`` buffers, so no re-basing
+    and no per-chunk allocation is involved."""
+
+    def __init__(self, sm: SpotMatrix, device):
+        import torch
+        from . import _lib
+        _lib.require_cuda()
+        self.host, self.device, self.compact = sm, torch.device(device), sm.is_compact
+        pins = getattr(sm, "_pins", None)
+        as_t = lambda a: torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
+        self._src = pins if pins is not None else [as_t(np.ascontiguousarray(a)) for a in
+                                                   (sm.col_ptr, sm.row_idx, sm.val, sm.spot_x, sm.spot_y)]
+        empty = lambda t: torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        self.col_ptr, self.row_idx, self.val = empty(self._src[0]), empty(self._src[1]), empty(self._src[2])
+        self.spot_x = self._src[3].to(self.device, non_blocking=True)
+        self.spot_y = self._src[4].to(self.device, non_blocking=True)
+        self.col_ptr.copy_(self._src[0], non_blocking=True)
+        self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in self._src)
+
+    def upload_genes(self, g0: int, g1: int):
+        """Enqueue (on the current stream) the copy of the stored values of genes [g0, g1)."""
+        a, b = int(self.host.col_ptr[g0]), int(self.host.col_ptr[g1])
+        self.row_idx[a:b].copy_(self._src[1][a:b], non_blocking=True)
+        self.val[a:b].copy_(self._src[2][a:b], non_blocking=True)
+
+    def gene_view(self, g0: int, g1: int) -> "DeviceSpotMatrix":
+        view = DeviceSpotMatrix.__new__(DeviceSpotMatrix)
+        view.host = _GeneRange(self.host, g0, g1)
+        view.device, view.compact, view._plans = self.device, self.compact, {}
+        view.col_ptr, view.row_idx, view.val = self.col_ptr[g0:g1 + 1], self.row_idx, self.val
+        view.spot_x, view.spot_y = self.spot_x, self.spot_y
+        import torch
+        view._up = lambda a, k=None: torch.from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=True)
+        view.h2d_bytes = 0
+        return view
+
+
+class _GeneRange:
+    """The part of a SpotMatrix the launch plan needs for genes [g0, g1): counts, not values."""
+
+    def __init__(self, sm: SpotMatrix, g0: int, g1: int):
+        self.col_ptr = sm.col_ptr[g0:g1 + 1] - sm.col_ptr[g0]
+        self.genes = sm.genes[g0:g1]
+        self.spot_x = sm.spot_x
+
+    @property
+    def n_genes(self) -> int:
+        return len(self.col_ptr) - 1
+
+    @property
+    def n_spots(self) -> int:
+        return len(self.spot_x)
