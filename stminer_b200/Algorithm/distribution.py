@@ -216,13 +216,12 @@ def fit_gmms(adata, gene_name_list, n_comp=15, binary=False, threshold=95, max_i
     from ..adata_lite import spot_matrix_from_adata
     gene_name_list = list(gene_name_list)
     sm = spot_matrix_from_adata(adata, gene_name_list)
-    dsm = DeviceSpotMatrix(sm, device=device)
     init = None
     if init_params is not None:
         if isinstance(init_params, dict):
             init = tuple(np.stack([np.asarray(init_params[g][i], dtype=np.float64) for g in sm.genes]) for i in range(3))
         else:
             init = init_params
-    res = fit_spot_matrix(dsm, n_comp, init=init, max_iter=max_iter, reg_covar=reg_covar,
-                          remove_low_exp_spots=remove_low_exp_spots, seed=seed)
-    return result_to_gmm_dict(sm.genes, res.to_host())
+    host = fit_spot_matrix_host(sm, n_comp, init=init, device=device, max_iter=max_iter, reg_covar=reg_covar,
+                                remove_low_exp_spots=remove_low_exp_spots, seed=seed)
+    return result_to_gmm_dict(sm.genes, host)
