@@ -361,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
                   "unit": "pairs/s", "genes": Gp, "pairs": total_pairs, "ms": pairs_ms,
                   "sharding": "contiguous pair slices per rank + NCCL all-gather" if world > 1 else "single GPU"},
         "fit": {"mean_n_iter": float(n_iter[ok].mean()), "genes_ok": int(ok.sum()), "genes_dropped": int((~ok).sum()),
-                "bucket_counts_large_medium_small": buckets.tolist(), "wall_ms_per_step": 1e3 * t_wall / args.steps},
+                "bucket_counts_cluster16_8_4_2_large_medium_small": buckets.tolist(), "wall_ms_per_step": 1e3 * t_wall / args.steps},
         "emd": emd,
         "clocks": clocks,
     }

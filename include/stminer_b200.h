@@ -36,6 +36,8 @@ extern "C" {
 #define STM_GENE_ILL_CONDITIONED 2  /* a covariance lost positive-definiteness: sklearn raises ValueError
                                        (_gaussian_mixture.py:361-367 -> distribution.py:200-202) */
 
+#define STM_FIT_N_BUCKETS 7
+
 /* flags of stm_gmm_fit_batched */
 #define STM_FIT_REMOVE_LOW_EXP_SPOTS 1u /* AlgUtils.py:16-17: w <- round(max(w - mean(nonzero w), 0)) */
 #define STM_FIT_DEVICE_INIT 2u          /* ignore init_*; run the on-device weighted k-means++/Lloyd init
@@ -43,6 +45,8 @@ extern "C" {
 #define STM_FIT_COMPACT_INPUT 4u        /* row_idx points to uint16 and val to int16 (values already truncated by the
                                            host, AlgUtils.py:35); needs n_spots <= 65536.  4 B per stored value
                                            instead of 8: halves the host->device transfer the e2e path is bound by */
+#define STM_FIT_NO_CLUSTERS 8u          /* stm_gmm_fit_plan: never split a gene over a thread-block cluster (long genes
+                                           then stream from L2 inside one CTA) */
 /* optional tuning fields of the device init, 0 = library default */
 #define STM_FIT_LLOYD_ITERS(n) (((uint32_t)(n) & 0xffu) << 8)   /* Lloyd iteration cap (default 4; the EM that follows
                                                                     refines further), 255 = sklearn's 300 */
@@ -68,10 +72,14 @@ const char* stm_last_error_string(void);
  *   spot_x, spot_y [n_spots] int32 integer grid coordinates of each spot (adata.obs['x'], ['y'])
  *   gene_order[G]  int32   optional (NULL = 0..G-1): CTA b fits gene gene_order[b]; pass genes sorted by
  *                          decreasing nnz so long genes start first (LPT)
- *   bucket_counts_host[3]  HOST int32, optional (NULL = one bucket): how many leading entries of gene_order
- *                          belong to the large / medium / small nnz bucket, as stm_gmm_fit_plan computes them.
- *                          Each bucket is launched with a CTA size and shared-memory budget that keeps its
- *                          genes' spots staged on chip; the buckets of one call run concurrently.
+ *   bucket_counts_host[STM_FIT_N_BUCKETS]  HOST int32, optional (NULL = one bucket): how many consecutive entries
+ *                          of gene_order belong to each nnz bucket, longest genes first, as stm_gmm_fit_plan
+ *                          computes them: buckets 0..3 fit one gene per thread-block CLUSTER of 16 / 8 / 4 / 2 CTAs
+ *                          (each CTA stages a slice of the gene's spots in its shared memory; the per-iteration
+ *                          statistics are summed through distributed shared memory), buckets 4..6 one gene per
+ *                          CTA of 512 / 256 / 128 threads.  Each bucket's shared-memory budget keeps its genes'
+ *                          spots staged on chip; the buckets of one call run concurrently.  (The reference has
+ *                          no counterpart: it fits genes one after another, distribution.py:184.)
  * Initial parameters (ignored with STM_FIT_DEVICE_INIT; required otherwise), float64, original coordinates:
  *   init_w[G,K], init_mu[G,K,2], init_cov[G,K,2,2]
  * Outputs, float64, same layouts: out_w, out_mu, out_cov; plus per gene
@@ -93,7 +101,7 @@ int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_idx, const fl
 /*
  * Host-side launch plan for stm_gmm_fit_batched (no device work): sorts genes by decreasing nnz (the
  * reference fits them in list order, distribution.py:184; order only affects scheduling here) and splits
- * them into the three nnz buckets.  col_ptr_host[G+1], gene_order_host[G] and bucket_counts_host[3] are
+ * them into the nnz buckets.  col_ptr_host[G+1], gene_order_host[G] and bucket_counts_host[STM_FIT_N_BUCKETS] are
  * HOST arrays; upload gene_order_host and pass both to stm_gmm_fit_batched.  `flags` must be the flags
  * of the fit call (the device init reserves shared memory, which moves the bucket boundaries).
  */

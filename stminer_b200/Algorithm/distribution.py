@@ -78,18 +78,19 @@ class FitResult:
 def fit_spot_matrix(dsm: DeviceSpotMatrix, n_comp: int, init=None, max_iter: int = 100, reg_covar: float = 1e-3,
                     tol: float = 1e-3, remove_low_exp_spots: bool = False, seed: int = 0,
                     out: Optional[FitResult] = None, lloyd_iters: int = 0, kpp_candidates: int = 0,
-                    seed_cap: int = 0) -> FitResult:
+                    seed_cap: int = 0, no_clusters: bool = False) -> FitResult:
     """Enqueue the batched EM fit of every gene of ``dsm`` on the current CUDA stream.
 
     ``init`` is ``(weights[G,K], means[G,K,2], covariances[G,K,2,2])`` (numpy or CUDA tensors, float64);
-    ``None`` selects the on-device k-means++/Lloyd initialisation.
+    ``None`` selects the on-device k-means++/Lloyd initialisation.  Genes too long for one CTA's shared memory are
+    split over a thread-block cluster (``no_clusters=True`` keeps them on one CTA, streaming from L2).
     """
     torch = _lib.require_cuda()
     lib = _lib.load()
     G, K = dsm.n_genes, int(n_comp)
     dev = dsm.device
     flags = _lib.fit_flags(remove_low_exp_spots, init is None, lloyd_iters, kpp_candidates, seed_cap,
-                           compact=dsm.compact)
+                           compact=dsm.compact, no_clusters=no_clusters)
     if init is None:
         iw = imu = icov = None
     else:

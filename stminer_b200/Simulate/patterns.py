@@ -17,7 +17,7 @@ CSC layout (values truncated to int16 as AlgUtils.py:35 does before the fit).
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import pandas as pd
@@ -128,6 +128,39 @@ def simulate_spot_matrix(config: str = "V", seed: int = 0, n_templates: Optional
                     sx, sy, genes)
     assert sm.n_spots == n_spots
     return (sm, templates) if return_templates else sm
+
+
+def simulate_long_genes(n_genes: int, seed: int = 0, shape: Tuple[int, int] = (1000, 1000), nnz_lo: float = 1e3,
+                        nnz_hi: float = 5e5, nnz: Optional[Sequence[int]] = None) -> SpotMatrix:
+    """Stereo-seq bin10-shaped genes (BASELINE configs[3], SURVEY.md §8d "S10"): a 1000 x 1000 full grid, per-gene
+    distinct-spot counts log-uniform in [nnz_lo, nnz_hi] (or given by ``nnz``), counts 1 + Poisson(intensity).
+
+    A gene's support is the ``nnz_g`` cells with the largest ``intensity x Exp(1)`` — a thinned sample of a blob
+    mixture — so long genes cover most of the tissue and short ones only the blob cores.
+    """
+    R, C = shape
+    rng = np.random.default_rng(seed)
+    rr, cc = np.meshgrid(np.arange(R, dtype=np.float32), np.arange(C, dtype=np.float32), indexing="ij")
+    targets = (np.asarray(nnz, dtype=np.int64) if nnz is not None else
+               np.exp(rng.uniform(np.log(nnz_lo), np.log(nnz_hi), size=n_genes)).astype(np.int64))
+    targets = np.minimum(targets, R * C)
+    cols, rows, vals = [0], [], []
+    for n in targets:
+        lam = np.full((R, C), 0.05, dtype=np.float32)
+        for _b in range(int(rng.integers(2, 6))):
+            cx, cy = rng.uniform(0.1, 0.9) * R, rng.uniform(0.1, 0.9) * C
+            sx, sy = rng.uniform(0.05, 0.25) * R, rng.uniform(0.05, 0.25) * C
+            rho = rng.uniform(-0.7, 0.7)
+            dx, dy = (rr - cx) / sx, (cc - cy) / sy
+            lam += rng.uniform(1.0, 4.0) * np.exp(-0.5 * (dx * dx - 2 * rho * dx * dy + dy * dy) / (1 - rho * rho))
+        score = (lam * rng.exponential(size=lam.shape).astype(np.float32)).ravel()
+        idx = np.sort(np.argpartition(score, score.size - int(n))[score.size - int(n):])
+        rows.append(idx.astype(np.int32))
+        vals.append((1 + rng.poisson(lam.ravel()[idx])).astype(np.float32))
+        cols.append(cols[-1] + len(idx))
+    sx_all = (np.arange(R * C) // C).astype(np.int32); sy_all = (np.arange(R * C) % C).astype(np.int32)
+    return SpotMatrix(np.asarray(cols, dtype=np.int64), np.concatenate(rows), np.concatenate(vals), sx_all, sy_all,
+                      ["long_%d" % i for i in range(len(targets))])
 
 
 def simulate_adata(config: str = "T", seed: int = 0, **kw):

@@ -23,13 +23,16 @@ STM_GENE_ILL_CONDITIONED = 2
 STM_FIT_REMOVE_LOW_EXP_SPOTS = 1
 STM_FIT_DEVICE_INIT = 2
 STM_FIT_COMPACT_INPUT = 4
+STM_FIT_NO_CLUSTERS = 8
+STM_FIT_N_BUCKETS = 7     # cluster x16 / x8 / x4 / x2, then one CTA per gene: large / medium / small
 
 
 def fit_flags(remove_low_exp_spots=False, device_init=False, lloyd_iters=0, kpp_candidates=0, seed_cap=0,
-              compact=False):
+              compact=False, no_clusters=False):
     """Compose the ``flags`` word of ``stm_gmm_fit_batched`` / ``stm_gmm_fit_plan`` (0 = library default)."""
     f = (STM_FIT_REMOVE_LOW_EXP_SPOTS if remove_low_exp_spots else 0) | (STM_FIT_DEVICE_INIT if device_init else 0)
     f |= STM_FIT_COMPACT_INPUT if compact else 0
+    f |= STM_FIT_NO_CLUSTERS if no_clusters else 0
     f |= (int(lloyd_iters) & 0xff) << 8
     del kpp_candidates   # retired: the seeding is plain D^2 sampling by exponential race
     f |= ((int(seed_cap) + 255) // 256 & 0xff) << 20

@@ -31,7 +31,11 @@
 #include <numeric>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "stm_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace stm {
 namespace {
@@ -140,7 +144,9 @@ __device__ __forceinline__ void halving_reduce(float (&v)[NMAX], int lane, int& 
 
 constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-template <int KT, int GS, int T>
+// CL = a gene split over a thread-block cluster: every CTA keeps the same layout plus the cluster-wide totals
+// (D_TOT) and a small exchange area (D_XCH) that the other CTAs of the cluster read through DSMEM.
+template <int KT, int GS, int T, bool CL = false>
 struct EmLayout {
   static constexpr int KT_ = KT;
   static constexpr int KP = KT * GS;
@@ -154,7 +160,9 @@ struct EmLayout {
   static constexpr int D_LL = D_W + KP;          // [WARPS]   per-warp partials
   static constexpr int D_MISC = D_LL + WARPS;    // [8]
   static constexpr int D_SCR = D_MISC + 8;       // [WARPS * KM_LMAX + 2 * KM_LMAX] k-means++ scratch
-  static constexpr int D_END = round_up(D_SCR + WARPS * KM_LMAX + 2 * KM_LMAX, 2);
+  static constexpr int D_TOT = D_SCR + WARPS * KM_LMAX + 2 * KM_LMAX;   // [NSTAT + WARPS] cluster totals (CL only)
+  static constexpr int D_XCH = D_TOT + (CL ? NSTAT + WARPS : 0);         // [8] cluster exchange (CL only)
+  static constexpr int D_END = round_up(D_XCH + (CL ? 8 : 0), 2);
   // floats (after doubles)
   static constexpr int F_PAR = 0;                                   // [KP*8]
   static constexpr int F_PP = F_PAR + KP * 8;                       // [KP*6] E-step coefficients, pair-interleaved
@@ -517,9 +525,33 @@ __device__ __forceinline__ void flush_stats(float (&acc)[NPAD], double* s_d, flo
   __syncthreads();
 }
 
-template <int KT, int GS, int S, int T, int MINB>
+// Cluster-wide reduction of a few per-CTA scalars through DSMEM: every CTA publishes v[0..N) in its exchange
+// area, reads the areas of all ranks in rank order (so every CTA ends with bit-identical totals) and combines
+// entries [0, NSUM) by + and the rest by min.
+template <int N, int NSUM>
+__device__ __forceinline__ void cluster_combine(cg::cluster_group& cl, double* s_xch, double (&v)[N], int csize) {
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) s_xch[n] = v[n];
+  }
+  cl.sync();
+#pragma unroll
+  for (int n = 0; n < N; ++n) v[n] = n < NSUM ? 0.0 : INFINITY;
+  for (int r = 0; r < csize; ++r) {
+    const double* rx = cl.map_shared_rank(s_xch, r);
+#pragma unroll
+    for (int n = 0; n < N; ++n) v[n] = n < NSUM ? v[n] + rx[n] : fmin(v[n], rx[n]);
+  }
+  cl.sync();   // the exchange area may be rewritten after this point
+}
+
+// CL = true: the gene is split over the CTAs of a thread-block cluster (launch attribute, size 2..16).  CTA r of
+// the cluster owns a contiguous slice of the gene's column — staged in ITS shared memory — and the per-iteration
+// sufficient statistics (6K values + the log-likelihood) are summed across the cluster through distributed shared
+// memory, in rank order, so that every CTA holds bit-identical parameters and takes the same branches.
+template <int KT, int GS, int S, int T, int MINB, bool CL>
 __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
-  using L = EmLayout<KT, GS, T>;
+  using L = EmLayout<KT, GS, T, CL>;
   constexpr int KP = L::KP;
   constexpr int NSTAT = L::NSTAT;
   constexpr int WARPS = L::WARPS;
@@ -541,10 +573,21 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = tid % GS, grp = tid / GS;
   const int K = p.K;
-  const int slot = p.order_begin + (int)blockIdx.x;
+  [[maybe_unused]] cg::cluster_group cl = cg::this_cluster();
+  int crank = 0, csize = 1;
+  if constexpr (CL) { crank = (int)cl.block_rank(); csize = (int)cl.num_blocks(); }
+  [[maybe_unused]] double* s_xch = s_d + L::D_XCH;
+  const int slot = p.order_begin + (int)blockIdx.x / csize;
   const int g = p.gene_order ? p.gene_order[slot] : slot;
-  const int64_t p0 = p.col_ptr[g], p1 = p.col_ptr[g + 1];
-  const int ncol = (int)(p1 - p0);
+  int64_t p0 = p.col_ptr[g];
+  const int64_t p1_all = p.col_ptr[g + 1];
+  int ncol = (int)(p1_all - p0);
+  int slice = ncol;           // longest slice of the cluster (uniform over its CTAs)
+  if constexpr (CL) {
+    slice = ((ncol + csize - 1) / csize + 3) & ~3;
+    const int lo = min(ncol, crank * slice), hi = min(ncol, lo + slice);
+    p0 += lo; ncol = hi - lo;
+  }
   const bool compact = (p.flags & STM_FIT_COMPACT_INPUT) != 0;
   const Column col{compact ? static_cast<const void*>(reinterpret_cast<const unsigned short*>(p.row_idx) + p0)
                            : static_cast<const void*>(p.row_idx + p0),
@@ -573,8 +616,13 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     __syncthreads();
     double ts = 0, tc = 0;
     for (int w = 0; w < WARPS; ++w) { ts += s_d[L::D_LL + w]; tc += s_d[L::D_STAT + w]; }
-    mean_nz = tc > 0 ? ts / tc : 0.0;
     __syncthreads();
+    if constexpr (CL) {
+      double v[2] = {ts, tc};
+      cluster_combine<2, 2>(cl, s_xch, v, csize);
+      ts = v[0]; tc = v[1];
+    }
+    mean_nz = tc > 0 ? ts / tc : 0.0;
   }
   if (tid < 4) s_ext[tid] = (tid & 1) ? INT_MIN : INT_MAX;  // xmin, xmax, ymin, ymax
   __syncthreads();
@@ -583,7 +631,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   // A gene that fits the staging budget is read from global memory ONCE: the same pass gathers the statistics
   // and stages the positive spots (ordered ballot compaction) relative to a provisional origin — the first
   // entry's spot — which is shifted to the integer centroid afterwards, in shared memory.
-  const bool try_stage = ncol <= p.smem_spots;
+  const bool try_stage = slice <= p.smem_spots;
   const int x0 = ncol > 0 ? __ldg(p.spot_x + col.row(0)) : 0, y0 = ncol > 0 ? __ldg(p.spot_y + col.row(0)) : 0;
   int n_st = 0;
   if (try_stage) {
@@ -655,19 +703,28 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   }
   xmin = s_ext[0]; xmax = s_ext[1]; ymin = s_ext[2]; ymax = s_ext[3];
   __syncthreads();
+  if constexpr (CL) {   // totals and extent of the whole gene
+    double v[8] = {t_npos, t_sw, t_swx, t_swy, (double)xmin, -(double)xmax, (double)ymin, -(double)ymax};
+    cluster_combine<8, 4>(cl, s_xch, v, csize);
+    t_npos = v[0]; t_sw = v[1]; t_swx = v[2]; t_swy = v[3];
+    // an empty slice contributes +-INT_MAX/INT_MIN, which the doubles carry exactly
+    xmin = (int)v[4]; xmax = (int)-v[5]; ymin = (int)v[6]; ymax = (int)-v[7];
+  }
   const double N_total = t_sw;
 
   double* o_w = p.out_w + (size_t)g * K;
   double* o_mu = p.out_mu + (size_t)g * K * 2;
   double* o_cov = p.out_cov + (size_t)g * K * 4;
   if ((int)t_npos < K) {  // distribution.py:125,129-130 -> gene dropped
-    for (int i = tid; i < K; i += T) o_w[i] = 0.0;
-    for (int i = tid; i < 2 * K; i += T) o_mu[i] = 0.0;
-    for (int i = tid; i < 4 * K; i += T) o_cov[i] = 0.0;
-    if (tid == 0) {
-      p.out_n_iter[g] = 0; p.out_converged[g] = 0; p.out_lb[g] = 0.0; p.out_status[g] = STM_GENE_DROPPED;
+    if (crank == 0) {
+      for (int i = tid; i < K; i += T) o_w[i] = 0.0;
+      for (int i = tid; i < 2 * K; i += T) o_mu[i] = 0.0;
+      for (int i = tid; i < 4 * K; i += T) o_cov[i] = 0.0;
+      if (tid == 0) {
+        p.out_n_iter[g] = 0; p.out_converged[g] = 0; p.out_lb[g] = 0.0; p.out_status[g] = STM_GENE_DROPPED;
+      }
     }
-    return;
+    return;   // uniform over the cluster: t_npos is the cluster total
   }
   const int ox = (int)rint(t_swx / t_sw), oy = (int)rint(t_swy / t_sw);
   // the staged record holds origin-relative coordinates as int16
@@ -707,14 +764,38 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     // subset -> one assignment pass over ALL spots -> one-hot responsibilities -> (w, mu, cov) as
     // sklearn's GaussianMixture._initialize (_gaussian_mixture.py:849-881).
     // =========================================================================================
-    const int stride = (n_spots + p.seed_cap - 1) / p.seed_cap;
-    const int ns = (n_spots + stride - 1) / stride;
-    for (int j = tid; j < ns; j += T) {
-      float x, y, w;
-      if (staged) staged_src.get(j * stride, x, y, w); else stream_src.get(j * stride, x, y, w);
-      s_seed[j] = make_float4(x, y, w, 0.f);
+    int n_glob = n_spots, pos0 = 0;   // spots of the whole gene / position of this CTA's first spot among them
+    if constexpr (CL) {
+      if (tid == 0) s_xch[0] = (double)n_spots;
+      cl.sync();
+      n_glob = 0;
+      for (int r = 0; r < csize; ++r) {
+        const int nr = (int)*cl.map_shared_rank(s_xch, r);
+        if (r < crank) pos0 += nr;
+        n_glob += nr;
+      }
+      cl.sync();
     }
-    __syncthreads();
+    const int stride = (n_glob + p.seed_cap - 1) / p.seed_cap;
+    const int ns = (n_glob + stride - 1) / stride;
+    if constexpr (CL) {
+      // every CTA runs the (cheap, deterministic) seeding + Lloyd on its own full copy of the seed subset:
+      // the owner of a seed spot writes it into the seed array of every CTA of the cluster
+      for (int j = (pos0 + stride - 1) / stride + tid; j * stride < pos0 + n_spots; j += T) {
+        float x, y, w;
+        if (staged) staged_src.get(j * stride - pos0, x, y, w); else stream_src.get(j * stride - pos0, x, y, w);
+        const float4 v = make_float4(x, y, w, 0.f);
+        for (int r = 0; r < csize; ++r) cl.map_shared_rank(s_seed, r)[j] = v;
+      }
+      cl.sync();
+    } else {
+      for (int j = tid; j < ns; j += T) {
+        float x, y, w;
+        if (staged) staged_src.get(j * stride, x, y, w); else stream_src.get(j * stride, x, y, w);
+        s_seed[j] = make_float4(x, y, w, 0.f);
+      }
+      __syncthreads();
+    }
     // k-means++ (D^2 sampling, Arthur & Vassilvitskii) by an exponential race: drawing index i with probability
     // v_i / sum(v) is arg-min_i E_i / v_i with E_i ~ Exp(1), so one pass updates the squared distances to the
     // centre just chosen AND races for the next centre, and the draw is a single block arg-min — no prefix
@@ -789,7 +870,6 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
         ax[j] = 2.f * cx; ay[j] = 2.f * cy; bb[j] = -fmaf(cx, cx, cy * cy);
       }
       for (int i = tid; i < NSTAT; i += T) s_d[L::D_STAT + i] = 0.0;
-      if (tid == 0) s_d[L::D_MISC + 2] = 0.0;
       __syncthreads();
       {
         float acc[NPAD];
@@ -798,21 +878,27 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
         lloyd_sweep<KT, GS, T>(seed_src, 0, ns, grp, sub, ax, ay, bb, acc);
         flush_stats<KT, GS, T, NPAD>(acc, s_d, s_red, tid);
       }
-      if (tid < K) {
+      if (tid < 64) {   // K <= 64: warps 0 and 1; the centre shift is summed in a fixed order (no atomics), so the
+                        // iteration count is reproducible — and identical on every CTA of a cluster
         const int k = tid;
-        const double* st = s_d + L::D_STAT + 6 * k;
-        if (st[0] > 0.0) {
-          const double nx = st[1] / st[0], ny = st[2] / st[0];
-          const double ddx = nx - s_d[L::D_MU + 2 * k], ddy = ny - s_d[L::D_MU + 2 * k + 1];
-          s_d[L::D_MU + 2 * k] = nx;
-          s_d[L::D_MU + 2 * k + 1] = ny;
-          s_par[8 * k + 6] = (float)nx;
-          s_par[8 * k + 7] = (float)ny;
-          atomicAdd(&s_d[L::D_MISC + 2], ddx * ddx + ddy * ddy);
+        double shift2 = 0.0;
+        if (k < K) {
+          const double* st = s_d + L::D_STAT + 6 * k;
+          if (st[0] > 0.0) {
+            const double nx = st[1] / st[0], ny = st[2] / st[0];
+            const double ddx = nx - s_d[L::D_MU + 2 * k], ddy = ny - s_d[L::D_MU + 2 * k + 1];
+            s_d[L::D_MU + 2 * k] = nx;
+            s_d[L::D_MU + 2 * k + 1] = ny;
+            s_par[8 * k + 6] = (float)nx;
+            s_par[8 * k + 7] = (float)ny;
+            shift2 = ddx * ddx + ddy * ddy;
+          }
         }
+        shift2 = warp_sum(shift2);
+        if (lane == 0) s_d[L::D_MISC + 2 + warp] = shift2;
       }
       __syncthreads();
-      const bool done = s_d[L::D_MISC + 2] <= km_tol;
+      const bool done = s_d[L::D_MISC + 2] + s_d[L::D_MISC + 3] <= km_tol;
       __syncthreads();
       if (done) break;
     }
@@ -930,14 +1016,29 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     }
     ll = warp_sum(sub == 0 ? ll : 0.0);
     if (lane == 0) s_d[L::D_LL + warp] = ll;
-    __syncthreads();
+    const double* st_all = s_d + L::D_STAT;   // statistics of the whole gene
+    const double* ll_all = s_d + L::D_LL;
+    if constexpr (CL) {
+      cl.sync();   // every CTA's partial statistics are complete and visible cluster-wide
+      for (int i = tid; i < NSTAT + WARPS; i += T) {
+        const double* src = i < NSTAT ? s_d + L::D_STAT + i : s_d + L::D_LL + (i - NSTAT);
+        double t = 0.0;
+        for (int r = 0; r < csize; ++r) t += *cl.map_shared_rank(src, r);   // rank order: identical on every CTA
+        s_d[L::D_TOT + i] = t;
+      }
+      cl.sync();   // all remote reads done before any CTA zeroes its partials for the next iteration
+      st_all = s_d + L::D_TOT;
+      ll_all = s_d + L::D_TOT + NSTAT;
+    } else {
+      __syncthreads();
+    }
     // M-step finalize: whitened moments -> (w, mu, cov) (sklearn _gaussian_mixture.py:282-320,883-901)
     if (tid < K) {
       const int k = tid;
-      const double* st = s_d + L::D_STAT + 6 * k;
+      const double* st = st_all + 6 * k;
       const double n = st[0] + 10.0 * DBL_EPSILON;  // _gaussian_mixture.py:312
       double tot = 0.0;                             // weights_ /= weights_.sum(), :898
-      for (int j = 0; j < K; ++j) tot += s_d[L::D_STAT + 6 * j] + 10.0 * DBL_EPSILON;
+      for (int j = 0; j < K; ++j) tot += st_all[6 * j] + 10.0 * DBL_EPSILON;
       const double inv_n = 1.0 / n;
       const double m0 = st[1] * inv_n, m1 = st[2] * inv_n;
       const double C00 = st[3] * inv_n - m0 * m0;
@@ -958,7 +1059,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     }
     if (tid == T - 1) {
       double t = 0.0;
-      for (int w = 0; w < WARPS; ++w) t += s_d[L::D_LL + w];
+      for (int w = 0; w < WARPS; ++w) t += ll_all[w];
       // log2 domain -> natural log; mean over the N replicated rows (_base.py:332)
       s_d[L::D_MISC + 1] = t * 0.69314718055994530942 / N_total;
     }
@@ -977,6 +1078,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
            T, g, ncol, n_spots, (int)staged, n_iter, pf_pro, pf_seed, pf_lloyd, pf_assign, pf_em, (double)pf_em / max(n_iter, 1));
 #endif
   // ---- outputs --------------------------------------------------------------------------------
+  if (crank != 0) return;   // every CTA of a cluster holds the same result; no remote access is pending
   if (failed) {
     for (int i = tid; i < K; i += T) o_w[i] = 0.0;
     for (int i = tid; i < 2 * K; i += T) o_mu[i] = 0.0;
@@ -1000,10 +1102,16 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Launch configurations.  Bucket b of a component class uses CTA size T_b with MINB_b CTAs per SM;
-// its staging capacity follows from the 228 KB of shared memory an SM has.
+// Launch configurations.  Genes are sorted by decreasing nnz and cut into STM_FIT_N_BUCKETS contiguous buckets:
+//   0..3  cluster buckets: one gene per thread-block cluster of 16 / 8 / 4 / 2 CTAs (512 threads, 1 CTA per SM);
+//         a gene goes to the smallest cluster whose CTAs can each stage their slice, genes beyond 16 slices run
+//         in bucket 0 and stream their slices from L2;
+//   4..6  one CTA per gene: large (512 threads x 1 CTA/SM), medium (256 x 2), small (128 x 4).
+// The staging capacity of a bucket follows from the 228 KB of shared memory an SM has.
 // ------------------------------------------------------------------------------------------------
-constexpr int N_BUCKETS = 3;  // 0: largest genes ... 2: smallest
+constexpr int N_BUCKETS = STM_FIT_N_BUCKETS;
+constexpr int N_CLUSTER_BUCKETS = 4;
+constexpr int CLUSTER_SIZE[N_CLUSTER_BUCKETS] = {16, 8, 4, 2};
 constexpr int SPOT_BYTES = 8, SEED_BYTES = 16;
 constexpr int DEFAULT_MAX_OPTIN = 232448;  // sm_100: 227 KB per CTA
 
@@ -1015,32 +1123,36 @@ inline int32_t cap_for(size_t fixed, int minb, int max_optin, int seed_cap) {
   return (int32_t)(((per_cta - need) / SPOT_BYTES) & ~(size_t)3);
 }
 
+// c[0] describes the cluster buckets (same CTA shape for every cluster size), c[1..3] the one-CTA buckets
 struct BucketCfg { int T, minb; size_t fixed; int seed_cap; };
+constexpr int N_CFG = 4;
 
 template <int KT, int GS>
-inline void fill_cfg(BucketCfg (&c)[N_BUCKETS]) {
-  c[0] = {512, 1, EmLayout<KT, GS, 512>::fixed_bytes(), 2048};
-  c[1] = {256, 2, EmLayout<KT, GS, 256>::fixed_bytes(), 1024};
-  c[2] = {128, STM_EM_MINB_SMALL, EmLayout<KT, GS, 128>::fixed_bytes(), 1024};
+inline void fill_cfg(BucketCfg (&c)[N_CFG]) {
+  c[0] = {512, 1, EmLayout<KT, GS, 512, true>::fixed_bytes(), 2048};
+  c[1] = {512, 1, EmLayout<KT, GS, 512>::fixed_bytes(), 2048};
+  c[2] = {256, 2, EmLayout<KT, GS, 256>::fixed_bytes(), 1024};
+  c[3] = {128, STM_EM_MINB_SMALL, EmLayout<KT, GS, 128>::fixed_bytes(), 1024};
 }
 
-inline void class_cfg(int K, uint32_t flags, BucketCfg (&c)[N_BUCKETS]) {
+inline void class_cfg(int K, uint32_t flags, BucketCfg (&c)[N_CFG]) {
   if (K <= 5) fill_cfg<5, 1>(c);
   else if (K <= 10) fill_cfg<5, 2>(c);
   else if (K <= 20) fill_cfg<5, 4>(c);
   else if (K <= 40) fill_cfg<5, 8>(c);
-  else for (int b = 0; b < N_BUCKETS; ++b) c[b] = {128, 3, EmLayout<8, 8, 128>::fixed_bytes(), 1024};
+  else for (int b = 0; b < N_CFG; ++b) c[b] = {128, 3, EmLayout<8, 8, 128>::fixed_bytes(), 1024};
   const int user = (int)((flags >> 20) & 0xff) * 256;  // seed-cap field of the flags
-  for (int b = 0; b < N_BUCKETS; ++b) {
+  for (int b = 0; b < N_CFG; ++b) {
     if (!(flags & STM_FIT_DEVICE_INIT)) c[b].seed_cap = 0;
     else if (user) c[b].seed_cap = user;
   }
 }
+inline bool class_has_clusters(int K) { return K <= 40; }   // K in (40, 64] has a single kernel shape
 
-template <int KT, int GS, int S, int T, int MINB>
-int launch_em(EmArgs a, const BucketCfg& cfg, int n_genes, cudaStream_t stream) {
-  using L = EmLayout<KT, GS, T>;
-  auto kern = gmm_em_kernel<KT, GS, S, T, MINB>;
+template <int KT, int GS, int S, int T, int MINB, bool CL>
+int launch_em(EmArgs a, const BucketCfg& cfg, int n_genes, int cluster, cudaStream_t stream) {
+  using L = EmLayout<KT, GS, T, CL>;
+  auto kern = gmm_em_kernel<KT, GS, S, T, MINB, CL>;
   int dev = 0, max_optin = 0;
   STM_CHECK_CUDA(cudaGetDevice(&dev));
   STM_CHECK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -1053,33 +1165,63 @@ int launch_em(EmArgs a, const BucketCfg& cfg, int n_genes, cudaStream_t stream) 
   }
   const size_t smem = fixed + (size_t)a.seed_cap * SEED_BYTES + (size_t)a.smem_spots * SPOT_BYTES;
   STM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<n_genes, T, smem, stream>>>(a);
-  STM_CHECK_CUDA(cudaGetLastError());
-  return STM_OK;
+  if constexpr (!CL) {
+    kern<<<n_genes, T, smem, stream>>>(a);
+    STM_CHECK_CUDA(cudaGetLastError());
+    return STM_OK;
+  } else {
+    // clusters above the portable size of 8 need an opt-in and may not be schedulable at this shared-memory
+    // footprint (one CTA per SM, a cluster lives inside one GPC): fall back to the next smaller size, whose
+    // slices are then longer than the staging capacity and stream from L2
+    STM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t lc{};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    lc.blockDim = dim3(T, 1, 1);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    for (; cluster >= 2; cluster /= 2) {
+      at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.gridDim = dim3((unsigned)n_genes * cluster, 1, 1);
+      int n_active = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_active, kern, &lc) == cudaSuccess && n_active >= 1) break;
+      (void)cudaGetLastError();
+    }
+    if (cluster < 2) {
+      set_last_error("stm_gmm_fit_batched: no thread-block cluster size is schedulable");
+      return STM_ERR_UNSUPPORTED;
+    }
+    STM_CHECK_CUDA(cudaLaunchKernelEx(&lc, kern, a));
+    return STM_OK;
+  }
 }
 
 template <int KT, int GS>
-int launch_bucket(const EmArgs& a, const BucketCfg (&c)[N_BUCKETS], int bucket, int n_genes, cudaStream_t st) {
-  if (bucket == 0) return launch_em<KT, GS, 2, 512, 1>(a, c[0], n_genes, st);
-  if (bucket == 1) return launch_em<KT, GS, 2, 256, 2>(a, c[1], n_genes, st);
-  return launch_em<KT, GS, STM_EM_S_SMALL, 128, STM_EM_MINB_SMALL>(a, c[2], n_genes, st);
+int launch_bucket(const EmArgs& a, const BucketCfg (&c)[N_CFG], int bucket, int n_genes, cudaStream_t st) {
+  if (bucket < N_CLUSTER_BUCKETS) return launch_em<KT, GS, 2, 512, 1, true>(a, c[0], n_genes, CLUSTER_SIZE[bucket], st);
+  if (bucket == 4) return launch_em<KT, GS, 2, 512, 1, false>(a, c[1], n_genes, 1, st);
+  if (bucket == 5) return launch_em<KT, GS, 2, 256, 2, false>(a, c[2], n_genes, 1, st);
+  return launch_em<KT, GS, STM_EM_S_SMALL, 128, STM_EM_MINB_SMALL, false>(a, c[3], n_genes, 1, st);
 }
 
 int launch_class(const EmArgs& a, int bucket, int n_genes, cudaStream_t st) {
   const int K = a.K;
-  BucketCfg c[N_BUCKETS];
+  BucketCfg c[N_CFG];
   class_cfg(K, a.flags, c);
   if (K <= 5) return launch_bucket<5, 1>(a, c, bucket, n_genes, st);
   if (K <= 10) return launch_bucket<5, 2>(a, c, bucket, n_genes, st);
   if (K <= 20) return launch_bucket<5, 4>(a, c, bucket, n_genes, st);
   if (K <= 40) return launch_bucket<5, 8>(a, c, bucket, n_genes, st);
-  return launch_em<8, 8, 1, 128, 3>(a, c[bucket], n_genes, st);
+  return launch_em<8, 8, 1, 128, 3, false>(a, c[3], n_genes, 1, st);
 }
 
-// auxiliary streams so the buckets of one call overlap (fork/join on the caller's stream)
+// auxiliary streams so the buckets of one call overlap (fork/join on the caller's stream); the buckets with the
+// longest genes get the highest priority so their (multi-SM) clusters are placed first
 struct AuxStreams {
-  cudaStream_t s[N_BUCKETS - 1] = {nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[N_BUCKETS - 1] = {nullptr, nullptr};
+  cudaStream_t s[N_BUCKETS - 1] = {};
+  cudaEvent_t fork = nullptr, join[N_BUCKETS - 1] = {};
   int dev = -1;
 };
 thread_local AuxStreams g_aux[16];
@@ -1089,8 +1231,11 @@ int get_aux(AuxStreams** out) {
   STM_CHECK_CUDA(cudaGetDevice(&dev));
   AuxStreams& a = g_aux[dev & 15];
   if (a.dev != dev) {
+    int least = 0, greatest = 0;   // numerically lower = higher priority
+    STM_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     for (int i = 0; i < N_BUCKETS - 1; ++i) {
-      STM_CHECK_CUDA(cudaStreamCreateWithFlags(&a.s[i], cudaStreamNonBlocking));
+      const int prio = std::min(least, greatest + i);
+      STM_CHECK_CUDA(cudaStreamCreateWithPriority(&a.s[i], cudaStreamNonBlocking, prio));
       STM_CHECK_CUDA(cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming));
     }
     STM_CHECK_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
@@ -1114,17 +1259,25 @@ extern "C" int stm_gmm_fit_plan(const int64_t* col_ptr_host, int32_t G, int32_t 
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
     return (col_ptr_host[a + 1] - col_ptr_host[a]) > (col_ptr_host[b + 1] - col_ptr_host[b]);
   });
-  BucketCfg cfg[N_BUCKETS];
+  BucketCfg cfg[N_CFG];
   class_cfg(K, flags, cfg);
-  const int32_t cap1 = cap_for(cfg[1].fixed, cfg[1].minb, DEFAULT_MAX_OPTIN, cfg[1].seed_cap);
-  const int32_t cap2 = cap_for(cfg[2].fixed, cfg[2].minb, DEFAULT_MAX_OPTIN, cfg[2].seed_cap);
-  int32_t n0 = 0, n1 = 0, n2 = 0;
+  int64_t cap[N_CFG];
+  for (int b = 0; b < N_CFG; ++b) cap[b] = cap_for(cfg[b].fixed, cfg[b].minb, DEFAULT_MAX_OPTIN, cfg[b].seed_cap);
+  const bool clusters = class_has_clusters(K) && !(flags & STM_FIT_NO_CLUSTERS);
+  for (int b = 0; b < N_BUCKETS; ++b) bucket_counts_host[b] = 0;
   for (int32_t i = 0; i < G; ++i) {
     const int64_t n = col_ptr_host[order[i] + 1] - col_ptr_host[order[i]];
-    if (n <= cap2) ++n2; else if (n <= cap1) ++n1; else ++n0;
+    int b;
+    if (n <= cap[3]) b = 6;
+    else if (n <= cap[2]) b = 5;
+    else if (n <= cap[1] || !clusters) b = 4;
+    else if (n <= 2 * cap[0]) b = 3;
+    else if (n <= 4 * cap[0]) b = 2;
+    else if (n <= 8 * cap[0]) b = 1;
+    else b = 0;
+    ++bucket_counts_host[b];
     gene_order_host[i] = order[i];
   }
-  bucket_counts_host[0] = n0; bucket_counts_host[1] = n1; bucket_counts_host[2] = n2;
   return STM_OK;
 }
 
@@ -1149,12 +1302,15 @@ extern "C" int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_id
                 "null output pointer");
   STM_CHECK_ARG((flags & STM_FIT_DEVICE_INIT) || (init_w && init_mu && init_cov),
                 "init_* required without STM_FIT_DEVICE_INIT");
-  int32_t counts[N_BUCKETS] = {0, 0, G};
+  int32_t counts[N_BUCKETS] = {};
+  counts[N_BUCKETS - 1] = G;
   if (bucket_counts_host) {
     STM_CHECK_ARG(gene_order != nullptr, "bucket_counts_host needs gene_order");
     int64_t s = 0;
     for (int b = 0; b < N_BUCKETS; ++b) { counts[b] = bucket_counts_host[b]; STM_CHECK_ARG(counts[b] >= 0, "negative bucket"); s += counts[b]; }
     STM_CHECK_ARG(s == G, "bucket counts do not sum to G");
+    for (int b = 0; b < N_CLUSTER_BUCKETS; ++b)
+      STM_CHECK_ARG(counts[b] == 0 || class_has_clusters(K), "cluster buckets need K <= 40");
   }
   EmArgs a{};
   a.col_ptr = col_ptr; a.row_idx = row_idx; a.val = val; a.spot_x = spot_x; a.spot_y = spot_y;
@@ -1174,15 +1330,16 @@ extern "C" int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_id
     if (rc != STM_OK) return rc;
     STM_CHECK_CUDA(cudaEventRecord(aux->fork, st));
   }
-  int begin = 0, used_aux = 0;
-  bool first = true;
+  // buckets in order of decreasing gene length; the LAST active one runs on the caller's stream, the earlier
+  // ones on the (higher-priority) auxiliary streams
+  int begin = 0, left = n_active;
   for (int b = 0; b < N_BUCKETS; ++b) {
     if (counts[b] == 0) continue;
     a.order_begin = begin;
+    --left;
     cudaStream_t s = st;
-    int my_aux = -1;
-    if (!first) {
-      my_aux = used_aux++;
+    const int my_aux = left > 0 ? b : -1;   // b < N_BUCKETS - 1 whenever another bucket follows
+    if (my_aux >= 0) {
       s = aux->s[my_aux];
       STM_CHECK_CUDA(cudaStreamWaitEvent(s, aux->fork, 0));
     }
@@ -1192,7 +1349,6 @@ extern "C" int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_id
       STM_CHECK_CUDA(cudaEventRecord(aux->join[my_aux], s));
       STM_CHECK_CUDA(cudaStreamWaitEvent(st, aux->join[my_aux], 0));
     }
-    first = false;
     begin += counts[b];
   }
   return STM_OK;

@@ -195,15 +195,15 @@ class DeviceSpotMatrix:
         self.h2d_bytes += 0 if spots is not None else sm.spot_x.nbytes + sm.spot_y.nbytes
 
     def plan(self, K: int, flags: int = 0):
-        """(gene_order CUDA tensor, bucket_counts host int32[3]) from ``stm_gmm_fit_plan`` for K components."""
+        """(gene_order CUDA tensor, bucket_counts host int32[STM_FIT_N_BUCKETS]) from ``stm_gmm_fit_plan`` for K components."""
         from . import _lib
-        key = (K, flags & ~5)   # the device-init fields move the bucket boundaries
+        key = (K, flags & ~5)   # (remove_low / compact do not move boundaries)   # the device-init fields move the bucket boundaries
         if key not in self._plans:
             lib = _lib.load()
             G = self.host.n_genes
             col = np.ascontiguousarray(self.host.col_ptr, dtype=np.int64)
             order = np.empty(max(G, 1), dtype=np.int32)
-            buckets = np.zeros(3, dtype=np.int32)
+            buckets = np.zeros(_lib.STM_FIT_N_BUCKETS, dtype=np.int32)
             _lib.check(lib.stm_gmm_fit_plan(col.ctypes.data, G, int(K), int(flags), order.ctypes.data,
                                             buckets.ctypes.data), "stm_gmm_fit_plan")
             self._plans[key] = (self._up(order[:G]), buckets)

@@ -51,15 +51,22 @@ def test_fit_plan_orders_by_nnz_and_buckets():
     nnz = np.array([10, 30000, 500, 6000, 4000, 0, 12000, 100000], dtype=np.int64)
     col = np.concatenate([[0], np.cumsum(nnz)]).astype(np.int64)
     order = np.empty(len(nnz), dtype=np.int32)
-    buckets = np.zeros(3, dtype=np.int32)
+    buckets = np.zeros(_lib.STM_FIT_N_BUCKETS, dtype=np.int32)
     assert lib.stm_gmm_fit_plan(col.ctypes.data, len(nnz), 20, 0, order.ctypes.data, buckets.ctypes.data) == 0
     assert (np.diff(nnz[order]) <= 0).all()
     assert sorted(order.tolist()) == list(range(len(nnz)))
     assert buckets.sum() == len(nnz)
     # 8-byte staged records: the small bucket (4 CTAs/SM) holds ~6.5k spots, the medium one (2 CTAs/SM) ~13k
-    assert buckets.tolist() == [2, 1, 5]
+    # 30,000 and 100,000 spots exceed one CTA's staging budget (~27.5k): clusters of 2 and 4 CTAs
+    assert buckets.tolist() == [0, 0, 1, 1, 0, 1, 5]
     assert set(nnz[order[:2]].tolist()) == {30000, 100000} and nnz[order[2]] == 12000
     # with the device init a seed area is reserved, which lowers the boundaries (6000 no longer fits 4 CTAs/SM)
     assert lib.stm_gmm_fit_plan(col.ctypes.data, len(nnz), 20, _lib.fit_flags(device_init=True),
                                 order.ctypes.data, buckets.ctypes.data) == 0
-    assert buckets.tolist() == [3, 1, 4]
+    assert buckets.tolist() == [0, 1, 0, 1, 1, 1, 4]
+    assert lib.stm_gmm_fit_plan(col.ctypes.data, len(nnz), 20, _lib.fit_flags(device_init=True, no_clusters=True),
+                                order.ctypes.data, buckets.ctypes.data) == 0
+    assert buckets.tolist() == [0, 0, 0, 0, 3, 1, 4]
+    # K > 40 has one kernel shape and no cluster buckets
+    assert lib.stm_gmm_fit_plan(col.ctypes.data, len(nnz), 64, 0, order.ctypes.data, buckets.ctypes.data) == 0
+    assert buckets[:4].sum() == 0 and buckets.sum() == len(nnz)

@@ -133,15 +133,19 @@ def test_long_gene_buckets_and_streaming(cuda_device):
                     sx, sy, list("abcd"))
     K = 20
     dsm = DeviceSpotMatrix(sm)
+    from stminer_b200 import _lib
+    _, buckets = dsm.plan(K, _lib.fit_flags(no_clusters=True))
+    assert buckets.tolist() == [0, 0, 0, 0, 2, 1, 1]
     _, buckets = dsm.plan(K)
-    assert buckets.tolist() == [2, 1, 1]
+    assert buckets.tolist() == [0, 0, 0, 1, 1, 1, 1]      # 30,000 spots: a cluster of 2 CTAs
     W, MU, COV, ok = oracle_inits(sm, K, seed=2)
-    res = _fit(sm, K, (W, MU, COV))
     ref = oracle_fit_all(sm, K, W, MU, COV, ok)
-    for g in range(4):
-        assert res["status"][g] == 0
-        assert res["n_iter"][g] == ref[g]["n_iter"], g
-        assert_gmm_close(res, g, ref[g], what="gene %d" % g)
+    for no_clusters in (True, False):
+        res = _fit(sm, K, (W, MU, COV), no_clusters=no_clusters)
+        for g in range(4):
+            assert res["status"][g] == 0
+            assert res["n_iter"][g] == ref[g]["n_iter"], g
+            assert_gmm_close(res, g, ref[g], what="gene %d" % g)
 
 
 @pytest.mark.parametrize("config,K", [("T", 10), ("V", 20)])
@@ -207,12 +211,13 @@ def test_very_long_gene_chunked_accumulation(cuda_device):
     # cheap deterministic init (k-means on 150k x ~2.4 replicated rows would dominate the test): blobs on a lattice
     gx, gy = np.meshgrid(np.linspace(100, 900, 5), np.linspace(125, 875, 4), indexing="ij")
     mu0 = np.column_stack([gx.ravel(), gy.ravel()]); w0 = np.full(K, 1 / K); cov0 = np.tile(np.eye(2) * 150.0 ** 2, (K, 1, 1))
-    res = _fit(sm, K, (w0[None], mu0[None], cov0[None]), max_iter=12)
     xy, c = sm.gene_spots(0)
     ref = go.weighted_em(xy, c, w0, mu0, cov0, max_iter=12)
-    assert res["status"][0] == 0 and res["n_iter"][0] == ref["n_iter"]
-    assert abs(res["lower_bound"][0] - ref["lower_bound"]) < 1e-4
-    assert_gmm_close(res, 0, ref, what="long gene")
+    for no_clusters in (True, False):   # one CTA streaming from L2 / a cluster of 8 CTAs with staged slices
+        res = _fit(sm, K, (w0[None], mu0[None], cov0[None]), max_iter=12, no_clusters=no_clusters)
+        assert res["status"][0] == 0 and res["n_iter"][0] == ref["n_iter"]
+        assert abs(res["lower_bound"][0] - ref["lower_bound"]) < 1e-4
+        assert_gmm_close(res, 0, ref, what="long gene")
 
 
 def test_pipelined_host_fit_matches_resident_fit(cuda_device):
@@ -236,3 +241,66 @@ def test_pipelined_host_fit_matches_resident_fit(cuda_device):
     c = fit_spot_matrix_host(sm, K, init=None, n_chunks=3, seed=2)
     d = fit_spot_matrix_host(sm, K, init=None, n_chunks=3, seed=2)
     assert (c["status"] == 0).all() and np.array_equal(c["means"], d["means"])
+
+
+def _lattice_init(K, R):
+    nx = int(np.ceil(np.sqrt(K)))
+    gx, gy = np.meshgrid(np.linspace(0.1, 0.9, nx) * R, np.linspace(0.1, 0.9, (K + nx - 1) // nx) * R, indexing="ij")
+    mu0 = np.column_stack([gx.ravel(), gy.ravel()])[:K]
+    return np.full(K, 1.0 / K), mu0, np.tile(np.eye(2) * (0.15 * R) ** 2, (K, 1, 1))
+
+
+@pytest.mark.parametrize("K", [20, 8, 33])
+def test_cluster_split_genes_match_oracle(cuda_device, K):
+    """Stereo-seq bin10-shaped long genes (BASELINE configs[3]): one gene per thread-block cluster of 2 / 4 / 8 / 16
+    CTAs, slices staged in each CTA's shared memory, statistics summed through DSMEM — against the float64 oracle from
+    fixed initial parameters; the last gene (480k spots) exceeds 16 staged slices and streams its slices."""
+    from stminer_b200.Simulate import simulate_long_genes
+    from stminer_b200.staging import DeviceSpotMatrix
+    from oracle import gmm_oracle as go
+    nnz = [30000, 70000, 150000, 300000, 480000] if K == 20 else [40000, 130000, 250000]
+    sm = simulate_long_genes(len(nnz), seed=K, nnz=nnz)
+    _, buckets = DeviceSpotMatrix(sm).plan(K)
+    assert buckets[:4].sum() == len(nnz) and (buckets[:4] > 0).sum() >= 3
+    w0, mu0, cov0 = _lattice_init(K, 1000)
+    G = sm.n_genes
+    init = (np.tile(w0, (G, 1)), np.tile(mu0, (G, 1, 1)), np.tile(cov0, (G, 1, 1, 1)))
+    res = _fit(sm, K, init, max_iter=10)
+    for g in range(G):
+        xy, c = sm.gene_spots(g)
+        ref = go.weighted_em(xy, c, w0, mu0, cov0, max_iter=10)
+        assert res["status"][g] == 0 and res["n_iter"][g] == ref["n_iter"], g
+        assert abs(res["lower_bound"][g] - ref["lower_bound"]) < 1e-4
+        assert_gmm_close(res, g, ref, what="cluster gene %d (%d spots)" % (g, nnz[g]))
+
+
+def test_cluster_device_init_remove_low_and_dropped(cuda_device):
+    """Cluster path corner cases: on-device init (every CTA seeds from the same subset, so the cluster stays in
+    lock-step), remove_low_exp_spots (cluster-wide mean), a long column with no positive value (dropped)."""
+    from stminer_b200.Simulate import simulate_long_genes
+    from stminer_b200.staging import SpotMatrix
+    from oracle import gmm_oracle as go
+    sm = simulate_long_genes(3, seed=5, nnz=[50000, 100000, 35000])
+    val = sm.val.copy()
+    val[sm.col_ptr[2]:sm.col_ptr[3]] = 0.5            # truncates to 0 everywhere: fewer than K positive spots
+    sm = SpotMatrix(sm.col_ptr, sm.row_idx, val, sm.spot_x, sm.spot_y, sm.genes)
+    K = 20
+    a = _fit(sm, K, None, seed=3)
+    b = _fit(sm, K, None, seed=3)
+    c = _fit(sm, K, None, seed=3, no_clusters=True)
+    assert a["status"].tolist() == [0, 0, 1] and c["status"].tolist() == [0, 0, 1]
+    for k in ("weights", "means", "covariances", "n_iter", "lower_bound"):
+        assert np.array_equal(a[k], b[k]), k                   # bit-reproducible per seed
+    # same seed subset (all stored values are positive) -> same start as the one-CTA path; only summation order differs
+    assert np.abs(a["lower_bound"][:2] - c["lower_bound"][:2]).max() < 2e-3
+    # remove_low_exp_spots: weights w - mean(nonzero w) with the mean taken over the whole gene
+    w0, mu0, cov0 = _lattice_init(K, 1000)
+    init = (np.tile(w0, (3, 1)), np.tile(mu0, (3, 1, 1)), np.tile(cov0, (3, 1, 1, 1)))
+    r = _fit(sm, K, init, max_iter=8, remove_low_exp_spots=True)
+    for g in range(2):
+        a0, a1 = int(sm.col_ptr[g]), int(sm.col_ptr[g + 1])
+        rr = sm.row_idx[a0:a1]
+        xy, cnt = go.gene_column_to_counts(sm.spot_x[rr], sm.spot_y[rr], sm.val[a0:a1], remove_low_exp_spots=True)
+        ref = go.weighted_em(xy, cnt, w0, mu0, cov0, max_iter=8)
+        assert r["status"][g] == 0 and r["n_iter"][g] == ref["n_iter"]
+        assert_gmm_close(r, g, ref, what="remove_low cluster gene %d" % g)
