@@ -582,9 +582,8 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   int64_t p0 = p.col_ptr[g];
   const int64_t p1_all = p.col_ptr[g + 1];
   int ncol = (int)(p1_all - p0);
-  int slice = ncol;           // longest slice of the cluster (uniform over its CTAs)
   if constexpr (CL) {
-    slice = ((ncol + csize - 1) / csize + 3) & ~3;
+    const int slice = ((ncol + csize - 1) / csize + 3) & ~3;
     const int lo = min(ncol, crank * slice), hi = min(ncol, lo + slice);
     p0 += lo; ncol = hi - lo;
   }
@@ -628,23 +627,24 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   __syncthreads();
   long long npos = 0, sw = 0, swx = 0, swy = 0;
   int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
-  // A gene that fits the staging budget is read from global memory ONCE: the same pass gathers the statistics
-  // and stages the positive spots (ordered ballot compaction) relative to a provisional origin — the first
-  // entry's spot — which is shifted to the integer centroid afterwards, in shared memory.
-  const bool try_stage = slice <= p.smem_spots;
+  // The column (slice) is read from global memory ONCE when it fits the staging budget: the same pass gathers the
+  // statistics and stages the positive spots (ordered ballot compaction) relative to a provisional origin — the
+  // first entry's spot — which is shifted to the integer centroid afterwards, in shared memory.  Of a longer
+  // column the first `smem_spots` entries are staged and only the remainder streams from L2 on every sweep.
+  const int n_head = min(ncol, p.smem_spots);
   const int x0 = ncol > 0 ? __ldg(p.spot_x + col.row(0)) : 0, y0 = ncol > 0 ? __ldg(p.spot_y + col.row(0)) : 0;
   int n_st = 0;
-  if (try_stage) {
+  {
     // 4 consecutive entries per thread and step: 8 independent loads + 8 gathers in flight per thread, and a
     // quarter of the barriers of a one-entry-per-thread compaction (the loop is global-latency bound)
     constexpr int E = 4;
-    for (int base = 0; base < ncol; base += E * T) {
+    for (int base = 0; base < n_head; base += E * T) {
       int w[E], x[E], y[E];
       int cnt = 0;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const int i = base + E * tid + e;
-        w[e] = i < ncol ? col.weight(i, remove_low, mean_nz) : 0;
+        w[e] = i < n_head ? col.weight(i, remove_low, mean_nz) : 0;
       }
 #pragma unroll
       for (int e = 0; e < E; ++e) {
@@ -674,8 +674,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
       n_st += tot;
       __syncthreads();
     }
-  } else {
-    for (int i = tid; i < ncol; i += T) {
+    for (int i = n_head + tid; i < ncol; i += T) {
       const int w = col.weight(i, remove_low, mean_nz);
       if (w > 0) {
         const int r = col.row(i);
@@ -729,12 +728,13 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   const int ox = (int)rint(t_swx / t_sw), oy = (int)rint(t_swy / t_sw);
   // the staged record holds origin-relative coordinates as int16
   const bool packable = (xmax - xmin) < 32768 && (ymax - ymin) < 32768;
-  const bool staged = try_stage && packable;
-  int n_spots = ncol;
+  const bool staged = packable;
+  if (!staged) n_st = 0;
+  const int s_lo = staged ? n_head : 0;      // column entries [s_lo, ncol) stream from L2 on every sweep
+  const int n_spots = n_st + (ncol - s_lo);  // positions: the staged spots, then the streamed entries
   if (staged) {
-    n_spots = n_st;
     const int dx = ox - x0, dy = oy - y0;   // provisional origin -> integer centroid
-    for (int i = tid; i < n_spots; i += T) {
+    for (int i = tid; i < n_st; i += T) {
       const int pk = s_spot[i].x;
       s_spot[i].x = pack_xy(((pk << 16) >> 16) - dx, (pk >> 16) - dy);
     }
@@ -783,7 +783,8 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
       // the owner of a seed spot writes it into the seed array of every CTA of the cluster
       for (int j = (pos0 + stride - 1) / stride + tid; j * stride < pos0 + n_spots; j += T) {
         float x, y, w;
-        if (staged) staged_src.get(j * stride - pos0, x, y, w); else stream_src.get(j * stride - pos0, x, y, w);
+        const int pos = j * stride - pos0;
+        if (pos < n_st) staged_src.get(pos, x, y, w); else stream_src.get(s_lo + pos - n_st, x, y, w);
         const float4 v = make_float4(x, y, w, 0.f);
         for (int r = 0; r < csize; ++r) cl.map_shared_rank(s_seed, r)[j] = v;
       }
@@ -791,7 +792,8 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     } else {
       for (int j = tid; j < ns; j += T) {
         float x, y, w;
-        if (staged) staged_src.get(j * stride, x, y, w); else stream_src.get(j * stride, x, y, w);
+        const int pos = j * stride;
+        if (pos < n_st) staged_src.get(pos, x, y, w); else stream_src.get(s_lo + pos - n_st, x, y, w);
         s_seed[j] = make_float4(x, y, w, 0.f);
       }
       __syncthreads();
@@ -982,8 +984,11 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     for (int i = tid; i < NSTAT; i += T) s_d[L::D_STAT + i] = 0.0;
     __syncthreads();
     double ll = 0.0;
-    for (int c0 = 0; c0 < n_spots; c0 += CHUNK) {
-      const int c1 = min(n_spots, c0 + CHUNK);
+    // part 0: the staged spots (shared memory); part 1: the column entries that did not fit (L2)
+    for (int part = 0; part < 2; ++part) {
+     const int lo = part == 0 ? 0 : s_lo, hi = part == 0 ? n_st : ncol;
+     for (int c0 = lo; c0 < hi; c0 += CHUNK) {
+      const int c1 = min(hi, c0 + CHUNK);
       float acc[NPAD];
 #pragma unroll
       for (int i = 0; i < NPAD; ++i) acc[i] = 0.f;
@@ -997,8 +1002,8 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
       }
 #pragma unroll
       for (int c = 0; c < 6; ++c) as[c] = 0.f;
-      if (staged) em_sweep_packed<KT, GS, S, T>(staged_src, c0, c1, grp, sub, pp, ps, ap, as, ll);
-      else        em_sweep_packed<KT, GS, S, T>(stream_src, c0, c1, grp, sub, pp, ps, ap, as, ll);
+      if (part == 0) em_sweep_packed<KT, GS, S, T>(staged_src, c0, c1, grp, sub, pp, ps, ap, as, ll);
+      else           em_sweep_packed<KT, GS, S, T>(stream_src, c0, c1, grp, sub, pp, ps, ap, as, ll);
 #pragma unroll
       for (int q = 0; q < NP; ++q) {
 #pragma unroll
@@ -1009,10 +1014,11 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
         for (int c = 0; c < 6; ++c) acc[(KT - 1) * 6 + c] = as[c];
       }
 #else
-      if (staged) em_sweep<KT, GS, S, T>(staged_src, c0, c1, grp, sub, par, acc, ll);
-      else        em_sweep<KT, GS, S, T>(stream_src, c0, c1, grp, sub, par, acc, ll);
+      if (part == 0) em_sweep<KT, GS, S, T>(staged_src, c0, c1, grp, sub, par, acc, ll);
+      else           em_sweep<KT, GS, S, T>(stream_src, c0, c1, grp, sub, par, acc, ll);
 #endif
       flush_stats<KT, GS, T, NPAD>(acc, s_d, s_red, tid);
+     }
     }
     ll = warp_sum(sub == 0 ? ll : 0.0);
     if (lane == 0) s_d[L::D_LL + warp] = ll;
@@ -1105,7 +1111,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
 // Launch configurations.  Genes are sorted by decreasing nnz and cut into STM_FIT_N_BUCKETS contiguous buckets:
 //   0..3  cluster buckets: one gene per thread-block cluster of 16 / 8 / 4 / 2 CTAs (512 threads, 1 CTA per SM);
 //         a gene goes to the smallest cluster whose CTAs can each stage their slice, genes beyond 16 slices run
-//         in bucket 0 and stream their slices from L2;
+//         in bucket 0 and stream the part of each slice that does not fit from L2;
 //   4..6  one CTA per gene: large (512 threads x 1 CTA/SM), medium (256 x 2), small (128 x 4).
 // The staging capacity of a bucket follows from the 228 KB of shared memory an SM has.
 // ------------------------------------------------------------------------------------------------
