@@ -56,6 +56,9 @@ constexpr int KM_LMAX = 6;                // greedy k-means++ candidates: 2 + fl
 #ifndef STM_EM_MAGIC_I2F
 #define STM_EM_MAGIC_I2F 0    // int16 -> float by magic-number add instead of I2F (XU pipe)
 #endif
+#ifndef STM_EM_PREFETCH
+#define STM_EM_PREFETCH 0     // load the next step's spots before computing the current one (manual software pipelining)
+#endif
 #ifndef STM_EM_LL_BATCH
 #define STM_EM_LL_BATCH 0     // fold the FP32 log-likelihood partial into FP64 every 8 steps instead of every step
 #endif
@@ -340,14 +343,34 @@ __device__ __forceinline__ void em_sweep_packed(const Src& src, int i_begin, int
   constexpr int NPA = NP > 0 ? NP : 1;
   [[maybe_unused]] float wl_acc = 0.f;
   [[maybe_unused]] int step = 0;
+#if STM_EM_PREFETCH
+  float xn[S], yn[S], wn[S];   // the spots of the NEXT step, loaded while this step computes
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int i = i_begin + grp + s * NG;
+    xn[s] = 0.f; yn[s] = 0.f; wn[s] = 0.f;
+    if (i < i_end) src.get(i, xn[s], yn[s], wn[s]);
+  }
+#endif
   for (int base = i_begin; base < i_end; base += NG * S) {
     float x[S], y[S], w[S];
+#if STM_EM_PREFETCH
+#pragma unroll
+    for (int s = 0; s < S; ++s) { x[s] = xn[s]; y[s] = yn[s]; w[s] = wn[s]; }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int i = base + NG * S + grp + s * NG;
+      xn[s] = 0.f; yn[s] = 0.f; wn[s] = 0.f;
+      if (i < i_end) src.get(i, xn[s], yn[s], wn[s]);
+    }
+#else
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const int i = base + grp + s * NG;
       x[s] = 0.f; y[s] = 0.f; w[s] = 0.f;
       if (i < i_end) src.get(i, x[s], y[s], w[s]);
     }
+#endif
     f2 t0p[S][NPA], t1p[S][NPA], lpp[S][NPA];
     float t0s[S], t1s[S], lps[S], m[S], sum[S];
 #pragma unroll
@@ -523,6 +546,67 @@ __device__ __forceinline__ void flush_stats(float (&acc)[NPAD], double* s_d, flo
     s_d[L::D_STAT + i] += t;
   }
   __syncthreads();
+}
+
+// One chunk of the fused E+M sweep: coefficients from shared memory -> registers, sweep over spots [c0, c1) of this
+// CTA, accumulators folded into s_d[D_STAT..] (ends with a __syncthreads()).  Returns this thread's share of
+// sum_i w_i * log2-sum-exp_i.  Deliberately NOT inlined: compiled on its own, the instruction schedule of the hot loop
+// does not depend on the surrounding kernel (inlined, ptxas interleaved the two in-flight spots differently from one
+// kernel variant to the next, worth 3-6 % of the sweep).
+template <int KT, int GS, int S, int T, typename Src>
+__device__ __noinline__ double em_chunk(const Src src, int c0, int c1, double* s_d, float* s_f) {
+  using L = EmLayout<KT, GS, T>;   // the float offsets and D_STAT do not depend on the cluster flag
+  constexpr int NPAD = round_up(KT * 6, 32 / GS);
+  const int tid = threadIdx.x, sub = tid % GS, grp = tid / GS;
+  float* s_par = s_f + L::F_PAR;
+  float* s_red = s_f + L::F_RED;
+  double ll = 0.0;
+  float acc[NPAD];
+#pragma unroll
+  for (int i = 0; i < NPAD; ++i) acc[i] = 0.f;
+#if STM_EM_PACKED
+  constexpr int NP = KT / 2, NPA = NP > 0 ? NP : 1;
+  f2 pp[NPA][6];
+  float ps[6];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    const float2* qa = reinterpret_cast<const float2*>(s_f + L::F_PP) + (sub * NP + q) * 6;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) pp[q][c] = qa[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) ps[c] = s_par[8 * (sub * KT + KT - 1) + c];
+  f2 ap[NPA][6];
+  float as[6];
+#pragma unroll
+  for (int q = 0; q < NPA; ++q) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ap[q][c] = f2_make(0.f, 0.f);
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) as[c] = 0.f;
+  em_sweep_packed<KT, GS, S, T>(src, c0, c1, grp, sub, pp, ps, ap, as, ll);
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { acc[(2 * q) * 6 + c] = ap[q][c].x; acc[(2 * q + 1) * 6 + c] = ap[q][c].y; }
+  }
+  if constexpr (KT % 2 == 1) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[(KT - 1) * 6 + c] = as[c];
+  }
+#else
+  float par[KT][6];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) {
+    const float4 q0 = *reinterpret_cast<const float4*>(s_par + 8 * (sub * KT + j));
+    const float2 q1 = *reinterpret_cast<const float2*>(s_par + 8 * (sub * KT + j) + 4);
+    par[j][0] = q0.x; par[j][1] = q0.y; par[j][2] = q0.z; par[j][3] = q0.w; par[j][4] = q1.x; par[j][5] = q1.y;
+  }
+  em_sweep<KT, GS, S, T>(src, c0, c1, grp, sub, par, acc, ll);
+#endif
+  flush_stats<KT, GS, T, NPAD>(acc, s_d, s_red, tid);
+  return ll;
 }
 
 // Cluster-wide reduction of a few per-CTA scalars through DSMEM: every CTA publishes v[0..N) in its exchange
@@ -960,66 +1044,14 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
 
   while (!failed && n_iter < p.max_iter) {
     ++n_iter;
-#if STM_EM_PACKED
-    constexpr int NP = KT / 2, NPA = NP > 0 ? NP : 1;
-    f2 pp[NPA][6];
-    float ps[6];
-#pragma unroll
-    for (int q = 0; q < NP; ++q) {
-      const float2* qa = reinterpret_cast<const float2*>(s_f + L::F_PP) + (sub * NP + q) * 6;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) pp[q][c] = qa[c];
-    }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) ps[c] = s_par[8 * (sub * KT + KT - 1) + c];
-#else
-    float par[KT][6];
-#pragma unroll
-    for (int j = 0; j < KT; ++j) {
-      const float4 q0 = *reinterpret_cast<const float4*>(s_par + 8 * (sub * KT + j));
-      const float2 q1 = *reinterpret_cast<const float2*>(s_par + 8 * (sub * KT + j) + 4);
-      par[j][0] = q0.x; par[j][1] = q0.y; par[j][2] = q0.z; par[j][3] = q0.w; par[j][4] = q1.x; par[j][5] = q1.y;
-    }
-#endif
     for (int i = tid; i < NSTAT; i += T) s_d[L::D_STAT + i] = 0.0;
     __syncthreads();
     double ll = 0.0;
     // part 0: the staged spots (shared memory); part 1: the column entries that did not fit (L2)
-    for (int part = 0; part < 2; ++part) {
-     const int lo = part == 0 ? 0 : s_lo, hi = part == 0 ? n_st : ncol;
-     for (int c0 = lo; c0 < hi; c0 += CHUNK) {
-      const int c1 = min(hi, c0 + CHUNK);
-      float acc[NPAD];
-#pragma unroll
-      for (int i = 0; i < NPAD; ++i) acc[i] = 0.f;
-#if STM_EM_PACKED
-      f2 ap[NPA][6];
-      float as[6];
-#pragma unroll
-      for (int q = 0; q < NPA; ++q) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) ap[q][c] = f2_make(0.f, 0.f);
-      }
-#pragma unroll
-      for (int c = 0; c < 6; ++c) as[c] = 0.f;
-      if (part == 0) em_sweep_packed<KT, GS, S, T>(staged_src, c0, c1, grp, sub, pp, ps, ap, as, ll);
-      else           em_sweep_packed<KT, GS, S, T>(stream_src, c0, c1, grp, sub, pp, ps, ap, as, ll);
-#pragma unroll
-      for (int q = 0; q < NP; ++q) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) { acc[(2 * q) * 6 + c] = ap[q][c].x; acc[(2 * q + 1) * 6 + c] = ap[q][c].y; }
-      }
-      if constexpr (KT % 2 == 1) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) acc[(KT - 1) * 6 + c] = as[c];
-      }
-#else
-      if (part == 0) em_sweep<KT, GS, S, T>(staged_src, c0, c1, grp, sub, par, acc, ll);
-      else           em_sweep<KT, GS, S, T>(stream_src, c0, c1, grp, sub, par, acc, ll);
-#endif
-      flush_stats<KT, GS, T, NPAD>(acc, s_d, s_red, tid);
-     }
-    }
+    for (int c0 = 0; c0 < n_st; c0 += CHUNK)
+      ll += em_chunk<KT, GS, S, T>(staged_src, c0, min(n_st, c0 + CHUNK), s_d, s_f);
+    for (int c0 = s_lo; c0 < ncol; c0 += CHUNK)
+      ll += em_chunk<KT, GS, S, T>(stream_src, c0, min(ncol, c0 + CHUNK), s_d, s_f);
     ll = warp_sum(sub == 0 ? ll : 0.0);
     if (lane == 0) s_d[L::D_LL + warp] = ll;
     const double* st_all = s_d + L::D_STAT;   // statistics of the whole gene
@@ -1223,8 +1255,8 @@ int launch_class(const EmArgs& a, int bucket, int n_genes, cudaStream_t st) {
   return launch_em<8, 8, 1, 128, 3, false>(a, c[3], n_genes, 1, st);
 }
 
-// auxiliary streams so the buckets of one call overlap (fork/join on the caller's stream); the buckets with the
-// longest genes get the highest priority so their (multi-SM) clusters are placed first
+// auxiliary streams so the buckets of one call overlap (fork/join on the caller's stream); stream priorities
+// were measured to make no difference
 struct AuxStreams {
   cudaStream_t s[N_BUCKETS - 1] = {};
   cudaEvent_t fork = nullptr, join[N_BUCKETS - 1] = {};
@@ -1237,11 +1269,8 @@ int get_aux(AuxStreams** out) {
   STM_CHECK_CUDA(cudaGetDevice(&dev));
   AuxStreams& a = g_aux[dev & 15];
   if (a.dev != dev) {
-    int least = 0, greatest = 0;   // numerically lower = higher priority
-    STM_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     for (int i = 0; i < N_BUCKETS - 1; ++i) {
-      const int prio = std::min(least, greatest + i);
-      STM_CHECK_CUDA(cudaStreamCreateWithPriority(&a.s[i], cudaStreamNonBlocking, prio));
+      STM_CHECK_CUDA(cudaStreamCreateWithFlags(&a.s[i], cudaStreamNonBlocking));
       STM_CHECK_CUDA(cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming));
     }
     STM_CHECK_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
@@ -1336,15 +1365,14 @@ extern "C" int stm_gmm_fit_batched(const int64_t* col_ptr, const int32_t* row_id
     if (rc != STM_OK) return rc;
     STM_CHECK_CUDA(cudaEventRecord(aux->fork, st));
   }
-  // buckets in order of decreasing gene length; the LAST active one runs on the caller's stream, the earlier
-  // ones on the (higher-priority) auxiliary streams
-  int begin = 0, left = n_active;
+  // buckets in order of decreasing gene length; the first active one runs on the caller's stream, the others on
+  // auxiliary streams (measured on B200: 0.4 ms per S50 step better than the other way round)
+  int begin = 0, used_aux = 0;
   for (int b = 0; b < N_BUCKETS; ++b) {
     if (counts[b] == 0) continue;
     a.order_begin = begin;
-    --left;
     cudaStream_t s = st;
-    const int my_aux = left > 0 ? b : -1;   // b < N_BUCKETS - 1 whenever another bucket follows
+    const int my_aux = begin > 0 ? used_aux++ : -1;
     if (my_aux >= 0) {
       s = aux->s[my_aux];
       STM_CHECK_CUDA(cudaStreamWaitEvent(s, aux->fork, 0));
