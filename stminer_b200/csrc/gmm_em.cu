@@ -56,6 +56,9 @@ constexpr int KM_LMAX = 6;                // greedy k-means++ candidates: 2 + fl
 #ifndef STM_EM_MAGIC_I2F
 #define STM_EM_MAGIC_I2F 0    // int16 -> float by magic-number add instead of I2F (XU pipe)
 #endif
+#ifndef STM_EM_QMOMENT
+#define STM_EM_QMOMENT 0      // accumulate sum r*(t0^2+t1^2) instead of sum r*t1^2 (one FMA-pipe operation less per component)
+#endif
 #ifndef STM_EM_PREFETCH
 #define STM_EM_PREFETCH 0     // load the next step's spots before computing the current one (manual software pipelining)
 #endif
@@ -224,9 +227,12 @@ __device__ __forceinline__ float unpack_y(int p) { return (float)(p >> 16); }
 
 // spots staged in shared memory: {int16 x | int16 y, float w}
 struct PackedSpots {
-  const int2* s;
+  unsigned s;   // shared-window address of the record array: the struct travels by value into the non-inlined sweep,
+                // where a generic pointer would turn every LDS into a generic LD
+  __device__ __forceinline__ explicit PackedSpots(const int2* p) : s((unsigned)__cvta_generic_to_shared(p)) {}
   __device__ __forceinline__ void get(int i, float& xo, float& yo, float& wo) const {
-    const int2 v = s[i];
+    int2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(s + 8u * (unsigned)i));
     xo = unpack_x(v.x); yo = unpack_y(v.x); wo = __int_as_float(v.y);
   }
 };
@@ -373,6 +379,10 @@ __device__ __forceinline__ void em_sweep_packed(const Src& src, int i_begin, int
 #endif
     f2 t0p[S][NPA], t1p[S][NPA], lpp[S][NPA];
     float t0s[S], t1s[S], lps[S], m[S], sum[S];
+#if STM_EM_QMOMENT
+    f2 qp[S][NPA];
+    float qs[S];
+#endif
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const f2 xx = f2_make(x[s], x[s]), yy = f2_make(y[s], y[s]);
@@ -381,13 +391,23 @@ __device__ __forceinline__ void em_sweep_packed(const Src& src, int i_begin, int
       for (int q = 0; q < NP; ++q) {
         t0p[s][q] = f2_fma(xx, pp[q][0], pp[q][1]);
         t1p[s][q] = f2_fma(xx, pp[q][2], f2_fma(yy, pp[q][3], pp[q][4]));
+#if STM_EM_QMOMENT
+        qp[s][q] = f2_fma(t0p[s][q], t0p[s][q], f2_mul(t1p[s][q], t1p[s][q]));
+        lpp[s][q] = f2_sub(pp[q][5], qp[s][q]);
+#else
         lpp[s][q] = f2_sub(pp[q][5], f2_fma(t0p[s][q], t0p[s][q], f2_mul(t1p[s][q], t1p[s][q])));
+#endif
         m[s] = fmaxf(m[s], fmaxf(lpp[s][q].x, lpp[s][q].y));
       }
       if constexpr (R == 1) {
         t0s[s] = fmaf(x[s], ps[0], ps[1]);
         t1s[s] = fmaf(x[s], ps[2], fmaf(y[s], ps[3], ps[4]));
+#if STM_EM_QMOMENT
+        qs[s] = fmaf(t0s[s], t0s[s], t1s[s] * t1s[s]);
+        lps[s] = ps[5] - qs[s];
+#else
         lps[s] = fmaf(-t0s[s], t0s[s], fmaf(-t1s[s], t1s[s], ps[5]));
+#endif
         m[s] = fmaxf(m[s], lps[s]);
       }
     }
@@ -424,24 +444,36 @@ __device__ __forceinline__ void em_sweep_packed(const Src& src, int i_begin, int
       for (int q = 0; q < NP; ++q) {
         const f2 r = f2_mul(lpp[s][q], ss);
         const f2 rt0 = f2_mul(r, t0p[s][q]);
-        const f2 rt1 = f2_mul(r, t1p[s][q]);
         ap[q][0] = f2_add(ap[q][0], r);
         ap[q][1] = f2_add(ap[q][1], rt0);
-        ap[q][2] = f2_add(ap[q][2], rt1);
         ap[q][3] = f2_fma(rt0, t0p[s][q], ap[q][3]);
         ap[q][4] = f2_fma(rt0, t1p[s][q], ap[q][4]);
+#if STM_EM_QMOMENT
+        // sum r*t1 by FMA, and sum r*(t0^2 + t1^2) — q is already there from the E-step — in the slot of
+        // sum r*t1^2 (recovered as a difference when the accumulators are flushed): 8 instead of 9 operations
+        ap[q][2] = f2_fma(r, t1p[s][q], ap[q][2]);
+        ap[q][5] = f2_fma(r, qp[s][q], ap[q][5]);
+#else
+        const f2 rt1 = f2_mul(r, t1p[s][q]);
+        ap[q][2] = f2_add(ap[q][2], rt1);
         ap[q][5] = f2_fma(rt1, t1p[s][q], ap[q][5]);
+#endif
       }
       if constexpr (R == 1) {
         const float r = lps[s] * scale;
         const float rt0 = r * t0s[s];
-        const float rt1 = r * t1s[s];
         as[0] += r;
         as[1] += rt0;
-        as[2] += rt1;
         as[3] = fmaf(rt0, t0s[s], as[3]);
         as[4] = fmaf(rt0, t1s[s], as[4]);
+#if STM_EM_QMOMENT
+        as[2] = fmaf(r, t1s[s], as[2]);
+        as[5] = fmaf(r, qs[s], as[5]);
+#else
+        const float rt1 = r * t1s[s];
+        as[2] += rt1;
         as[5] = fmaf(rt1, t1s[s], as[5]);
+#endif
       }
     }
 #if STM_EM_LL_BATCH
@@ -595,6 +627,10 @@ __device__ __noinline__ double em_chunk(const Src src, int c0, int c1, double* s
 #pragma unroll
     for (int c = 0; c < 6; ++c) acc[(KT - 1) * 6 + c] = as[c];
   }
+#if STM_EM_QMOMENT
+#pragma unroll
+  for (int j = 0; j < KT; ++j) acc[j * 6 + 5] -= acc[j * 6 + 3];   // sum r*t1^2 = sum r*q - sum r*t0^2
+#endif
 #else
   float par[KT][6];
 #pragma unroll
