@@ -171,6 +171,26 @@ int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y, const doub
                           void* workspace, int64_t workspace_bytes, int32_t n_ctas,
                           double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream);
 
+/*
+ * Metric MDS by SMACOF on a precomputed dissimilarity matrix, float64, whole iteration loop on the device.
+ *
+ * Replaces: the MDS half of cluster()   STMiner/Algorithm/algorithm.py:54-55
+ *           (sklearn.manifold.MDS(n_components, dissimilarity='precomputed').fit_transform -> smacof ->
+ *            _smacof_single, scikit-learn 1.3.0 manifold/_mds.py; one call here = one _smacof_single run from a
+ *            caller-supplied initial configuration, the n_init restarts are the caller's loop)
+ *
+ *   dissim[n,n]  symmetric, zero diagonal (the gene x gene distance matrix);  x_init[n,d] row-major start
+ *   max_iter, eps as sklearn (MDS defaults 300 / 1e-3);  d = n_components <= 32
+ *   rule 0: stopping rule of scikit-learn <= 1.6 (the version the reference pins):
+ *           stress(X_it) / sum_i ||X_{it+1,i}|| decreased by less than eps
+ *   rule 1: scikit-learn >= 1.7: (stress(X_it) - stress(X_{it+1})) / (sum_ij dis_ij^2 / 2) < eps
+ *   workspace    device scratch of stm_mds_workspace_bytes(n, d) bytes
+ *   x_out[n,d], out_stress (raw stress, sklearn's `stress_`), out_n_iter — device pointers
+ */
+int64_t stm_mds_workspace_bytes(int32_t n, int32_t d);
+int stm_mds_smacof(const double* dissim, int32_t n, int32_t d, const double* x_init, int32_t max_iter,
+                   double eps, int32_t rule, void* workspace, int64_t workspace_bytes,
+                   double* x_out, double* out_stress, int32_t* out_n_iter, void* stream);
 
 /*
  * Measurement utility: FP32 FMA-pipe peak micro-benchmark used as the roofline denominator of the EM

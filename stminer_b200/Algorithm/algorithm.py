@@ -1,5 +1,5 @@
-"""Host mirror of ``STMiner/Algorithm/algorithm.py``: ``linear_sum`` on the device LSAP kernel, ``cluster``
-(MDS + KMeans / spectral) on the host with scikit-learn exactly as the reference calls it."""
+"""Host mirror of ``STMiner/Algorithm/algorithm.py``: ``linear_sum`` on the device LSAP kernel, ``cluster`` =
+device SMACOF MDS (scikit-learn 1.3.0 semantics, the version the reference pins) + scikit-learn KMeans / spectral."""
 from __future__ import annotations
 
 import numpy as np
@@ -34,30 +34,78 @@ def linear_sum(cost) -> float:
     return v
 
 
+def mds_smacof(dissimilarities, init, max_iter: int = 300, eps: float = 1e-3, rule: int = 0, device=None):
+    """One SMACOF run on the device from the start configuration ``init`` [n, d] — sklearn's ``_smacof_single``
+    (metric MDS on a precomputed matrix).  Returns CUDA tensors ``(X[n, d], stress[1], n_iter[1])``; nothing is
+    synchronised.  ``rule`` 0 = stopping rule of scikit-learn <= 1.6 (the reference pins 1.3.0), 1 = scikit-learn >= 1.7."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else "cuda")
+
+    def dv(a):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+        return t.to(device=dev, dtype=torch.float64).contiguous()
+    D, X0 = dv(dissimilarities), dv(init)
+    n, d = int(X0.shape[0]), int(X0.shape[1])
+    if tuple(D.shape) != (n, n):
+        raise ValueError("dissimilarities must be [n, n] with n = init.shape[0]; got %s" % (tuple(D.shape),))
+    nbytes = int(lib.stm_mds_workspace_bytes(n, d))
+    if nbytes < 0:
+        raise ValueError("n_components must be in [1, 32]")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    X = torch.empty((n, d), dtype=torch.float64, device=dev)
+    stress = torch.empty(1, dtype=torch.float64, device=dev)
+    n_iter = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib.stm_mds_smacof(_lib.ptr(D), n, d, _lib.ptr(X0), int(max_iter), float(eps), int(rule), _lib.ptr(ws),
+                                nbytes, _lib.ptr(X), _lib.ptr(stress), _lib.ptr(n_iter), _lib.current_stream_ptr())
+    _lib.check(st, "stm_mds_smacof")
+    X._keepalive = (D, X0, ws)
+    return X, stress, n_iter
+
+
+def mds_fit_transform(dissimilarities, n_components: int = 2, n_init: int = 4, max_iter: int = 300, eps: float = 1e-3,
+                      random_state=None, rule: int = 0, device=None):
+    """``MDS(n_components, dissimilarity='precomputed').fit_transform(D)`` with the defaults of the scikit-learn the
+    reference pins (1.3.0: metric, n_init=4, max_iter=300, eps=1e-3; algorithm.py:54-55): every restart draws its
+    start configuration from the same RandomState — numpy's global one when ``random_state`` is None, so
+    ``np.random.seed`` fixes the result as it does for the reference — the runs execute on the device and the
+    lowest final stress wins.  Returns ``(embedding ndarray [n, d], stress, n_iter)``."""
+    D = np.asarray(dissimilarities, dtype=np.float64)
+    n = D.shape[0]
+    if D.ndim != 2 or D.shape[1] != n:
+        raise ValueError("expected a square dissimilarity matrix")
+    if isinstance(random_state, (int, np.integer)):
+        random_state = np.random.RandomState(int(random_state))
+    rs = np.random.mtrand._rand if random_state is None else random_state
+    torch = _lib.require_cuda()
+    Dd = torch.from_numpy(np.ascontiguousarray(D)).to(device if device is not None else "cuda")
+    runs = []
+    for _ in range(n_init):
+        X0 = rs.uniform(size=n * n_components).reshape((n, n_components))
+        runs.append(mds_smacof(Dd, X0, max_iter=max_iter, eps=eps, rule=rule, device=Dd.device))
+    best = None
+    for X, stress, n_iter in runs:      # first-lowest wins, as `if best_stress is None or stress < best_stress`
+        s = float(stress.cpu().numpy()[0])
+        if best is None or s < best[1]:
+            best = (X, s, int(n_iter.cpu().numpy()[0]))
+    return best[0].cpu().numpy(), best[1], best[2]
+
+
 def cluster(distance_array: pd.DataFrame, mds_components: int = 20, n_clusters: int = 10, method: str = "kmeans"):
     """Drop-in for ``cluster`` (algorithm.py:29-61): MDS on the precomputed distances, then KMeans
     (``random_state=0, max_iter=1000, n_init=20``) or spectral clustering; returns
-    ``(DataFrame[gene_id, labels], fit_result, embedding)``.  Runs on the host with scikit-learn — the
-    'next' row of SURVEY.md §8f; MDS is unseeded in the reference too (``np.random.seed`` fixes it)."""
+    ``(DataFrame[gene_id, labels], fit_result, embedding)``.  The MDS (SMACOF, O(G^2 d) per iteration) runs on the
+    device with the semantics of the scikit-learn version the reference pins; it is unseeded in the reference too
+    (``np.random.seed`` fixes it).  KMeans on the G x d embedding stays scikit-learn on the host."""
     from sklearn.cluster import KMeans, SpectralClustering
-    from sklearn.manifold import MDS
-    import inspect
+    if method not in ("kmeans", "spectral"):
+        raise ValueError("method should be kmeans or spectral")
     index = distance_array.index
-    kw = {"n_components": mds_components}
-    params = inspect.signature(MDS.__init__).parameters
-    if "metric" in params and "dissimilarity" in params and params["metric"].default is not True:
-        kw["metric"] = "precomputed"          # sklearn >= 1.8 spelling
-    else:
-        kw["dissimilarity"] = "precomputed"   # the reference's sklearn 1.3 spelling (algorithm.py:54)
-    import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        embedding_position = MDS(**kw).fit_transform(np.asarray(distance_array))
+    embedding_position, _, _ = mds_fit_transform(np.asarray(distance_array, dtype=np.float64), mds_components)
     if method == "kmeans":
         fit_result = KMeans(n_clusters=n_clusters, random_state=0, max_iter=1000, n_init=20).fit(embedding_position)
-    elif method == "spectral":
-        fit_result = SpectralClustering(n_clusters=n_clusters, random_state=0, affinity="rbf").fit(embedding_position)
     else:
-        raise ValueError("method should be kmeans or spectral")
+        fit_result = SpectralClustering(n_clusters=n_clusters, random_state=0, affinity="rbf").fit(embedding_position)
     result = pd.DataFrame(dict(gene_id=list(index), labels=list(fit_result.labels_)))
     return result, fit_result, embedding_position
