@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="genes in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--emd-genes", type=int, default=148, help="Visium-size spot-EMD problems in the emd leg (0 = skip)")
+    ap.add_argument("--s10-genes", type=int, default=296, help="long (Stereo-seq bin10-shaped) genes in the s10 leg (0 = skip)")
+    ap.add_argument("--no-mds", action="store_true", help="skip the MDS (cluster_gene) leg")
     return ap.parse_args()
 
 
@@ -322,6 +324,70 @@ def run_ours(args, rank, world, local_rank):
                "seconds": t_e, "mean_pivots": float(eiters.mean()), "optimal": int((estatus == 0).sum()),
                "note": "exact network simplex, numItermax=200000 as the reference; includes H2D/D2H of the problem data"}
 
+    # ---- the step after the distance matrix: cluster() = SMACOF MDS (4 restarts, 20 components) on the G x G matrix ----
+    mds = None
+    if rank == 0 and not args.no_mds and Gp >= 64:
+        from stminer_b200.Algorithm.algorithm import mds_fit_transform
+        from stminer_b200.Algorithm.distance import pairs_to_square
+        local_all = gmm_pair_distances(W, MU, COV, 0, total_pairs, device=dev)
+        square = pairs_to_square(local_all, Gp)
+        torch.cuda.synchronize()
+        Dh = square.cpu().numpy()
+        mds_fit_transform(Dh[:256, :256], 20, random_state=0, device=dev)       # warm-up
+        torch.cuda.synchronize()
+        t_m = time.perf_counter()
+        emb, stress, n_it = mds_fit_transform(Dh, 20, random_state=0, device=dev)
+        t_m = time.perf_counter() - t_m
+        mds = {"metric": "mds_smacof_seconds", "genes": Gp, "n_components": 20, "n_init": 4, "seconds": t_m,
+               "best_stress": stress, "n_iter_best": n_it,
+               "note": "cluster() MDS half (algorithm.py:54-55), sklearn 1.3.0 semantics, host matrix in / embedding out"}
+        if not args.no_cpu_baseline:
+            from oracle import mds_oracle as mo
+            Ds = Dh[:1000, :1000]
+            t_c = time.perf_counter()
+            mo.smacof_single(Ds, np.random.RandomState(0).uniform(size=(1000, 20)), max_iter=3, eps=-np.inf)
+            t_c = (time.perf_counter() - t_c) / 3
+            mds["cpu_seconds_per_iteration_1000_genes"] = t_c
+
+    # ---- long genes (BASELINE configs[3], Stereo-seq bin10-shaped): one gene per thread-block cluster ----------------
+    s10 = None
+    if rank == 0 and args.s10_genes > 0:
+        from stminer_b200.Simulate import simulate_long_genes
+        from stminer_b200.staging import SpotMatrix
+        path = "/tmp/stm_bench_S10_%d.npz" % args.s10_genes
+        if os.path.exists(path):
+            z = np.load(path)
+            lsm = SpotMatrix(z["col_ptr"], z["row_idx"], z["val"], z["spot_x"], z["spot_y"],
+                             ["long_%d" % i for i in range(len(z["col_ptr"]) - 1)])
+        else:
+            lsm = simulate_long_genes(args.s10_genes, seed=0)
+            try:
+                np.savez(path, col_ptr=lsm.col_ptr, row_idx=lsm.row_idx, val=lsm.val, spot_x=lsm.spot_x, spot_y=lsm.spot_y)
+            except OSError:
+                pass
+        ldsm = DeviceSpotMatrix(lsm, device=dev)
+        _, lb = ldsm.plan(K_COMP, _lib.fit_flags(device_init=True))
+        lres = None
+        for _ in range(2):
+            lres = fit_spot_matrix(ldsm, K_COMP, init=None, seed=1, out=lres)
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(3):
+            lres = fit_spot_matrix(ldsm, K_COMP, init=None, seed=1, out=lres)
+        l1.record()
+        torch.cuda.synchronize()
+        lms = l0.elapsed_time(l1) / 3
+        lh = lres.to_host()
+        lflops = FLOP_PER_SPOT_COMP_ITER * K_COMP * float((lsm.nnz_per_gene() * lh["n_iter"] * (lh["status"] == 0)).sum())
+        s10 = {"metric": "genes_per_sec_gmm_fit_long_genes", "value": lsm.n_genes / (lms / 1e3), "unit": "genes/s",
+               "genes": lsm.n_genes, "grid": "1000 x 1000", "nnz": int(lsm.nnz), "max_nnz": int(lsm.nnz_per_gene().max()),
+               "ms": lms, "spots_per_sec": lsm.nnz / (lms / 1e3), "em_tflops": lflops / (lms / 1e3) / 1e12,
+               "bucket_counts_cluster16_8_4_2_large_medium_small": lb.tolist(), "genes_ok": int((lh["status"] == 0).sum()),
+               "note": "subset of BASELINE configs[3] (distinct-spot counts log-uniform in [1e3, 5e5]); genes beyond one "
+                       "CTA's shared memory are split over thread-block clusters"}
+        del ldsm, lres
+
     # ---- FP32 FMA peak measured on this GPU (roofline denominator) --------------------------------
     scratch = torch.zeros(4, dtype=torch.float32, device=dev)
     blocks, iters = 148 * 8, 20000
@@ -363,6 +429,8 @@ def run_ours(args, rank, world, local_rank):
         "fit": {"mean_n_iter": float(n_iter[ok].mean()), "genes_ok": int(ok.sum()), "genes_dropped": int((~ok).sum()),
                 "bucket_counts_cluster16_8_4_2_large_medium_small": buckets.tolist(), "wall_ms_per_step": 1e3 * t_wall / args.steps},
         "emd": emd,
+        "mds": mds,
+        "s10": s10,
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -1147,7 +1147,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
 
   EM_PROF(pf_em)
 #ifdef STM_EM_PROFILE
-  if (tid == 0 && (blockIdx.x % 997) == 3)
+  if (tid == 0 && ((blockIdx.x % 997) == 3 || (CL && blockIdx.x % 61 == 0)))
     printf("[em prof] T=%d gene=%d ncol=%d n_spots=%d staged=%d n_iter=%d cycles: prologue %lld seed %lld lloyd %lld assign+refresh %lld em %lld (%.0f/iter)\n",
            T, g, ncol, n_spots, (int)staged, n_iter, pf_pro, pf_seed, pf_lloyd, pf_assign, pf_em, (double)pf_em / max(n_iter, 1));
 #endif
