@@ -68,7 +68,10 @@ def build_gmm_distance_array(gmm_dict, device=None):
     G = len(genes)
     if G == 0:
         return pd.DataFrame(np.zeros((0, 0)), index=genes, columns=genes)
-    pairs = gmm_pair_distances(W, MU, COV, device=device)
+    from ..sharding import gmm_pairs_sharded      # pair slices per rank + all-gather under a process group
+    torch = _lib.require_cuda()
+    pairs = gmm_pairs_sharded(W, MU, COV, device=device)
+    pairs = pairs.to(torch.device(device if device is not None else "cuda"))
     square = pairs_to_square(pairs, G).cpu().numpy()
     return pd.DataFrame(square, index=genes, columns=genes)
 
@@ -167,7 +170,8 @@ def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, devic
 
 def ot_distances_to_source(source, targets, max_iter: int = 200000, device=None):
     """EMD from one sparse image to each image of ``targets`` (the loop of SPFinder.py:285-299)."""
-    return emd_batched(csr_to_support(source), [csr_to_support(t) for t in targets], max_iter=max_iter, device=device)
+    from ..sharding import emd_sharded            # targets dealt over the ranks under a process group
+    return emd_sharded(csr_to_support(source), [csr_to_support(t) for t in targets], max_iter=max_iter, device=device)
 
 
 def calculate_ot_distance(source, target, device=None) -> float:

@@ -223,6 +223,8 @@ def fit_gmms(adata, gene_name_list, n_comp=15, binary=False, threshold=95, max_i
             init = tuple(np.stack([np.asarray(init_params[g][i], dtype=np.float64) for g in sm.genes]) for i in range(3))
         else:
             init = init_params
-    host = fit_spot_matrix_host(sm, n_comp, init=init, device=device, max_iter=max_iter, reg_covar=reg_covar,
-                                remove_low_exp_spots=remove_low_exp_spots, seed=seed)
+    # with a torch.distributed process group (one process per GPU) the genes are sharded over the ranks
+    from ..sharding import fit_genes_sharded
+    host = fit_genes_sharded(sm, n_comp, init=init, device=device, max_iter=max_iter, reg_covar=reg_covar,
+                             remove_low_exp_spots=remove_low_exp_spots, seed=seed)
     return result_to_gmm_dict(sm.genes, host)

@@ -702,6 +702,8 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   int64_t p0 = p.col_ptr[g];
   const int64_t p1_all = p.col_ptr[g + 1];
   int ncol = (int)(p1_all - p0);
+  const int64_t p0_all = p0;
+  const int ncol_all = ncol;
   if constexpr (CL) {
     const int slice = ((ncol + csize - 1) / csize + 3) & ~3;
     const int lo = min(ncol, crank * slice), hi = min(ncol, lo + slice);
@@ -924,7 +926,22 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     // sums, no inverse-CDF walk.  E_i comes from a counter-based hash of (seed, gene, round, i).
     double* s_scr = s_d + L::D_SCR;
     unsigned long long* s_race = reinterpret_cast<unsigned long long*>(s_scr);             // [WARPS]
-    const unsigned hseed = (unsigned)splitmix64(p.seed ^ ((uint64_t)g * 0xD1342543DE82EF95ULL));
+    // the per-gene random stream is keyed by the gene's DATA (length, first / last stored entry), not by its index in
+    // this call: the same gene gets the same start whether it is fitted alone, in an upload chunk, on another rank
+    // of a sharded job or split over a cluster
+    uint64_t gkey = (uint64_t)(unsigned)ncol_all;
+    if (ncol_all > 0) {
+      const Column whole{compact ? static_cast<const void*>(reinterpret_cast<const unsigned short*>(p.row_idx) + p0_all)
+                                 : static_cast<const void*>(p.row_idx + p0_all),
+                         compact ? static_cast<const void*>(reinterpret_cast<const short*>(p.val) + p0_all)
+                                 : static_cast<const void*>(p.val + p0_all),
+                         compact};
+      gkey ^= (uint64_t)(unsigned)whole.row(0) << 32;
+      gkey ^= (uint64_t)(unsigned)whole.row(ncol_all - 1) * 0x9E3779B97F4A7C15ULL;
+      gkey ^= (uint64_t)(unsigned)whole.trunc_value(0) << 20;
+      gkey ^= (uint64_t)(unsigned)whole.row(ncol_all / 2) * 0xC2B2AE3D27D4EB4FULL;
+    }
+    const unsigned hseed = (unsigned)splitmix64(p.seed ^ (gkey * 0xD1342543DE82EF95ULL));
     float ccx = 0.f, ccy = 0.f;
     for (int c = 0; c < K; ++c) {
       unsigned long long best = ~0ULL;

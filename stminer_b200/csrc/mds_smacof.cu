@@ -76,22 +76,30 @@ __global__ void __launch_bounds__(MDS_T) mds_rows_kernel(const double* __restric
     }
     __syncthreads();
     if (!row_ok) continue;
-#pragma unroll 2
-    for (int t = lane; t < MDS_TJ; t += 32) {
-      const int j = j0 + t;
-      if (j >= n) break;
-      double diff[DP], d2 = 0.0;
+    // the tile's dissimilarities first: MDS_TJ / 32 independent coalesced loads in flight per lane (the pass is
+    // otherwise bound by the latency of this one global load per pair)
+    double dj[MDS_TJ / 32];
 #pragma unroll
-      for (int c = 0; c < DP; ++c) { diff[c] = xi[c] - Xs[c * MDS_TJ + t]; d2 = fma(diff[c], diff[c], d2); }
+    for (int u = 0; u < MDS_TJ / 32; ++u) {
+      const int j = j0 + lane + 32 * u;
+      dj[u] = j < n ? __ldg(Drow + j) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < MDS_TJ / 32; ++u) {
+      const int t = lane + 32 * u;
+      if (j0 + t >= n) break;
+      double d2 = 0.0;
+#pragma unroll
+      for (int c = 0; c < DP; ++c) { const double df = xi[c] - Xs[c * MDS_TJ + t]; d2 = fma(df, df, d2); }
       double dis = sqrt(d2);
-      const double dij = Drow[j];
-      const double e = dis - dij;
+      const double e = dis - dj[u];
       stress = fma(e, e, stress);
       ssd += d2;
       if (dis == 0.0) dis = 1e-5;
-      const double ratio = dij / dis;
+      const double ratio = dj[u] / dis;
+      // the differences are recomputed rather than kept: 2*DP fewer live registers -> two CTAs per SM
 #pragma unroll
-      for (int c = 0; c < DP; ++c) acc[c] = fma(ratio, diff[c], acc[c]);
+      for (int c = 0; c < DP; ++c) acc[c] = fma(ratio, xi[c] - Xs[c * MDS_TJ + t], acc[c]);
     }
   }
   if (!row_ok) return;

@@ -72,3 +72,80 @@ def allgather_pairs(local, total_pairs: int, group=None):
         b, e = pair_slice(total_pairs, r, world)
         parts.append(gathered[r * n_max:r * n_max + (e - b)])
     return torch.cat(parts)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Stage drivers: what the host API calls when a process group exists (one process per GPU).  `compute(...)`
+# arguments let the world-size-2 gloo tests on CPU exercise the sharding / gathering with a stand-in for the kernels.
+# ------------------------------------------------------------------------------------------------------------
+def group_rank_world(group=None) -> Tuple[int, int]:
+    """(rank, world_size) of the process group, (0, 1) when torch.distributed is not initialised."""
+    try:
+        import torch.distributed as dist
+    except ImportError:      # pragma: no cover
+        return 0, 1
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _collective_device(group=None):
+    """Tensors handed to the collectives live on the current CUDA device under NCCL, on the host under gloo."""
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def fit_genes_sharded(sm, n_comp: int, init=None, group=None, compute=None, **kw) -> dict:
+    """GMM fit of every gene of the SpotMatrix ``sm`` with the genes dealt LPT-wise over the ranks:
+    each rank uploads and fits only its own columns, one all-gather per output array replicates the result.
+    Returns the same host dict as ``fit_spot_matrix_host``, in ``sm`` gene order, on every rank."""
+    import torch
+    rank, world = group_rank_world(group)
+    if compute is None:
+        from .Algorithm.distribution import fit_spot_matrix_host as compute
+    if world == 1:
+        return compute(sm, n_comp, init=init, **kw)
+    owned = shard_genes_lpt(sm.nnz_per_gene(), world)
+    mine = owned[rank]
+    sub_init = None if init is None else tuple(np.asarray(a)[mine] for a in init)
+    local = compute(sm.select(mine), n_comp, init=sub_init, **kw)
+    dev = _collective_device(group)
+    out = {}
+    for k, v in local.items():
+        out[k] = allgather_rows(torch.from_numpy(np.ascontiguousarray(v)).to(dev), owned, group=group).cpu().numpy()
+    return out
+
+
+def gmm_pairs_sharded(W, MU, COV, group=None, device=None, compute=None):
+    """All pair distances of G mixtures with the linearised upper triangle cut into one contiguous slice per rank;
+    returns the full pair vector (tensor on the collective's device) on every rank."""
+    import torch
+    rank, world = group_rank_world(group)
+    if compute is None:
+        from .Algorithm.distance import gmm_pair_distances as compute
+    G = int(W.shape[0])
+    total = G * (G - 1) // 2
+    if world == 1:
+        return compute(W, MU, COV, 0, total, device=device)
+    b, e = pair_slice(total, rank, world)
+    local = compute(W, MU, COV, b, e, device=device)
+    return allgather_pairs(local.to(_collective_device(group)), total, group=group)
+
+
+def emd_sharded(src, targets, group=None, compute=None, **kw):
+    """Spot-level EMD of one source against every target, targets dealt LPT-wise by support size; (cost, status)
+    numpy arrays in target order on every rank."""
+    import torch
+    rank, world = group_rank_world(group)
+    if compute is None:
+        from .Algorithm.distance import emd_batched as compute
+    if world == 1:
+        return compute(src, targets, **kw)
+    sizes = np.array([len(t[0]) for t in targets], dtype=np.int64)
+    owned = shard_genes_lpt(sizes, world)
+    cost, status = compute(src, [targets[i] for i in owned[rank]], **kw)[:2]
+    dev = _collective_device(group)
+    cost = allgather_rows(torch.from_numpy(np.ascontiguousarray(cost, dtype=np.float64)).to(dev), owned, group=group)
+    status = allgather_rows(torch.from_numpy(np.ascontiguousarray(status, dtype=np.int32)).to(dev), owned, group=group)
+    return cost.cpu().numpy(), status.cpu().numpy()

@@ -54,3 +54,56 @@ def _worker(rank, world, port, G, total_pairs):
 def test_allgather_world_size_2_gloo(G, total_pairs):
     port = 29500 + (os.getpid() + G) % 2000
     mp.spawn(_worker, args=(2, port, G, total_pairs), nprocs=2, join=True)
+
+
+def _stage_worker(rank, world, port):
+    """The stage drivers with stand-ins for the kernels: sharded result == unsharded result on every rank."""
+    from stminer_b200.sharding import emd_sharded, fit_genes_sharded, gmm_pairs_sharded
+    from stminer_b200.Simulate import simulate_spot_matrix
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sm = simulate_spot_matrix("T", seed=1, n_templates=3, replicas=3)
+        K = 3
+
+        def fake_fit(m, n_comp, init=None, **kw):       # per-gene values that depend only on the gene's own data
+            nnz = m.nnz_per_gene().astype(np.float64)
+            tot = np.array([m.val[m.col_ptr[g]:m.col_ptr[g + 1]].sum() for g in range(m.n_genes)], dtype=np.float64)
+            extra = 0.0 if init is None else np.asarray(init[0]).sum(axis=1)
+            return {"weights": np.repeat((nnz + extra)[:, None], n_comp, axis=1), "means": np.tile(tot[:, None, None], (1, n_comp, 2)),
+                    "status": (nnz > 0).astype(np.int32)}
+        init = (np.arange(sm.n_genes * K, dtype=np.float64).reshape(sm.n_genes, K),)
+        for ini in (None, init):
+            a = fit_genes_sharded(sm, K, init=ini, compute=fake_fit)
+            b = fake_fit(sm, K, init=ini)
+            for k in b:
+                assert np.array_equal(a[k], b[k]), k
+
+        G = 11
+        W = torch.arange(G * K, dtype=torch.float64).reshape(G, K)
+
+        def fake_pairs(W, MU, COV, b, e, device=None):
+            return torch.arange(b, e, dtype=torch.float64) * 3.0 + W[0, 0]
+        full = gmm_pairs_sharded(W, None, None, compute=fake_pairs)
+        assert torch.equal(full, torch.arange(G * (G - 1) // 2, dtype=torch.float64) * 3.0)
+
+        targets = [(np.zeros(n), np.zeros(n), np.full(n, float(n))) for n in (5, 1, 9, 3, 7, 2, 8)]
+
+        def fake_emd(src, tg, **kw):
+            return (np.array([t[2].sum() for t in tg], dtype=np.float64), np.array([len(t[0]) % 3 for t in tg], dtype=np.int32))
+        cost, status = emd_sharded(None, targets, compute=fake_emd)
+        c0, s0 = fake_emd(None, targets)
+        assert np.array_equal(cost, c0) and np.array_equal(status, s0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stage_drivers_world_size_2_gloo():
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_stage_worker, args=(2, port), nprocs=2, join=True)
+
+
+def test_stage_drivers_without_process_group():
+    from stminer_b200.sharding import group_rank_world
+    assert group_rank_world() == (0, 1)
