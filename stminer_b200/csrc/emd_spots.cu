@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
   unsigned short* s_S = s_P + EMD_MAXPATH;
   __shared__ double s_scr[EMD_WARPS];
   __shared__ long long s_ll[3 * EMD_WARPS];
-  __shared__ unsigned long long s_slot[2];
+  __shared__ unsigned long long s_slot[3];
   __shared__ int s_i[16];
   __shared__ long long s_delta;
 
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     long long it = 0;
     int status = 0;
     unsigned round = 0;
-    if (tid == 0) { s_slot[0] = ~0ULL; s_slot[1] = ~0ULL; }
+    if (tid == 0) { s_slot[0] = ~0ULL; s_slot[1] = ~0ULL; s_slot[2] = ~0ULL; }
     __syncthreads();
 
 #ifdef STM_EMD_PROFILE
@@ -267,11 +267,12 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
           }
         }
         for (int o = 16; o > 0; o >>= 1) key = min(key, shfl_xor_ll(key, o));
-        // cross-warp minimum: one shared atomicMin per warp on a double-buffered slot (thread 0 re-arms the other
-        // slot before this round's barrier, so the next round's atomics always find it armed)
+        // cross-warp minimum: one shared atomicMin per warp on a rotating slot.  Thread 0 re-arms the NEXT round's slot
+        // before this round's barrier; with three slots that one was last read two rounds ago, i.e. before the
+        // barrier every thread has already passed (two slots would race with a slow reader of the previous round)
         {
-          unsigned long long* slot = s_slot + (round & 1);
-          if (tid == 0) s_slot[(round + 1) & 1] = ~0ULL;
+          unsigned long long* slot = s_slot + round % 3;
+          if (tid == 0) s_slot[(round + 1) % 3] = ~0ULL;
           if (lane == 0) atomicMin(slot, (unsigned long long)key ^ 0x8000000000000000ULL);
           __syncthreads();
           key = (long long)(*slot ^ 0x8000000000000000ULL);

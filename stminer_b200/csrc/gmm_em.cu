@@ -943,6 +943,58 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     }
     const unsigned hseed = (unsigned)splitmix64(p.seed ^ (gkey * 0xD1342543DE82EF95ULL));
     float ccx = 0.f, ccy = 0.f;
+    constexpr int SEED_R = 8;   // seeds per thread that can stay in registers over the K rounds
+    if (ns <= SEED_R * T) {
+      // Register-resident rounds: a thread keeps ITS seeds (x, y, w, running D^2) in registers, the warp arg-min is two
+      // REDUX instructions, the CTA arg-min one shared atomicMin per warp on a double-buffered slot — one barrier and no
+      // seed traffic per round (the rounds are latency-bound: 2.7k -> ~1k cycles each).  Same keys, same (key, index)
+      // order, hence the same picks as the generic loop below.
+      __shared__ unsigned long long s_slot3[3];   // three rotating slots: the one re-armed in round c was last read in
+                                                  // round c - 2, i.e. before the barrier every thread passed to get here
+      float px[SEED_R], py[SEED_R], pw[SEED_R], pd[SEED_R];
+#pragma unroll
+      for (int r = 0; r < SEED_R; ++r) {
+        const int i = tid + r * T;
+        const float4 v = i < ns ? s_seed[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        px[r] = v.x; py[r] = v.y; pw[r] = v.z; pd[r] = 0.f;
+      }
+      if (tid == 0) { s_slot3[0] = ~0ULL; s_slot3[1] = ~0ULL; s_slot3[2] = ~0ULL; }
+      __syncthreads();
+      for (int c = 0; c < K; ++c) {
+        unsigned bk = 0xffffffffu;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < SEED_R; ++r) {
+          const int i = tid + r * T;
+          float val = pw[r];                                   // round 0: P(i) ~ w_i   (0 beyond ns)
+          if (c > 0) {
+            const float dx = px[r] - ccx, dy = py[r] - ccy;
+            const float d = fmaf(dx, dx, dy * dy);
+            pd[r] = c == 1 ? d : fminf(pd[r], d);
+            val = pw[r] * pd[r];                               // P(i) ~ w_i * D_i^2
+          }
+          if (val > 0.f) {
+            unsigned h = hseed ^ ((unsigned)c * 0x85EBCA77u) ^ ((unsigned)i * 0xC2B2AE3Du);
+            h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+            const float u = (float)((h >> 8) + 1u) * 5.9604645e-8f;          // (0, 1]
+            const unsigned kb = __float_as_uint(-lg2_approx(u) * rcp_approx(val));   // Exp(1) / v_i >= 0: bits order as uint
+            if (kb < bk) { bk = kb; bi = i; }                  // r ascending: the lowest index wins ties
+          }
+        }
+        const unsigned wk = __reduce_min_sync(FULL_MASK, bk);
+        const int wi = __reduce_min_sync(FULL_MASK, bk == wk ? bi : 0x7fffffff);
+        unsigned long long* slot = s_slot3 + c % 3;
+        if (tid == 0) s_slot3[(c + 1) % 3] = ~0ULL;            // re-arm the next round's slot
+        if (lane == 0 && wk != 0xffffffffu) atomicMin(slot, ((unsigned long long)wk << 32) | (unsigned)wi);
+        __syncthreads();
+        const unsigned long long best = *slot;
+        const int pick = best == ~0ULL ? 0 : (int)(unsigned)best;   // all remaining mass on chosen centres: reuse seed 0
+        const float4 pv = s_seed[pick];
+        ccx = pv.x; ccy = pv.y;
+        if (tid == 0) { s_par[8 * c + 6] = ccx; s_par[8 * c + 7] = ccy; }
+      }
+      __syncthreads();
+    } else {
     for (int c = 0; c < K; ++c) {
       unsigned long long best = ~0ULL;
       for (int i = tid; i < ns; i += T) {
@@ -976,6 +1028,7 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
       ccx = pv.x; ccy = pv.y;
       if (tid == 0) { s_par[8 * c + 6] = ccx; s_par[8 * c + 7] = ccy; }
       __syncthreads();   // s_race is rewritten and s_seed[].w updated in the next round
+    }
     }
     if (tid < K) { s_d[L::D_MU + 2 * tid] = (double)s_par[8 * tid + 6]; s_d[L::D_MU + 2 * tid + 1] = (double)s_par[8 * tid + 7]; }
     __syncthreads();
