@@ -32,15 +32,17 @@ LOG_2PI = np.log(2.0 * np.pi)
 
 
 # --------------------------------------------------------------------------- staging
-def gene_column_to_counts(x, y, values, remove_low_exp_spots: bool = False):
+def gene_column_to_counts(x, y, values, remove_low_exp_spots: bool = False, binary: bool = False, cut: bool = False,
+                          threshold: float = 95):
     """Gene column -> (xy[nnz,2] int64, counts[nnz] int64) on DISTINCT positive spots.
 
     Follows ``AlgUtils._preprocess`` (AlgUtils.py:26-36): the column is cast to
     int16 by ``coo_matrix(..., dtype=np.int16)`` (truncation toward zero),
     ``todense()`` sums duplicate (x, y) (AlgUtils.py:15); optional
     ``max(dense - mean(nonzero), 0)`` (AlgUtils.py:16-17) and ``np.round`` ->
-    int16 (AlgUtils.py:22-23).  ``array_to_list`` (distribution.py:369-373) then
-    keeps cells ``> 0`` in row-major (x, y) order.
+    int16 (AlgUtils.py:22-23); optional ``binary`` / ``cut`` of ``preprocess_array``
+    (distribution.py:133-145: percentile over the whole dense grid).  ``array_to_list``
+    (distribution.py:369-373) then keeps cells ``> 0`` in row-major (x, y) order.
     """
     x = np.asarray(x).astype(np.int64)
     y = np.asarray(y).astype(np.int64)
@@ -52,6 +54,13 @@ def gene_column_to_counts(x, y, values, remove_low_exp_spots: bool = False):
         nz = dense[dense != 0]
         d = np.maximum(dense - np.mean(nz), 0)
         dense = np.array(np.round(d), dtype=np.int16)
+    if binary:                                          # preprocess_array, distribution.py:135-140
+        if threshold > 100 or threshold < 0:
+            threshold = 100
+        dense = np.where(dense > np.percentile(dense, threshold), 1, 0)
+    elif cut:                                           # distribution.py:142-143
+        dense = dense.copy()
+        dense[dense < np.percentile(dense, threshold)] = 0
     xs, ys = np.where(dense > 0)
     counts = dense[xs, ys].astype(np.int64)
     return np.column_stack([xs, ys]).astype(np.int64), counts

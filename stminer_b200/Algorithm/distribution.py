@@ -209,14 +209,16 @@ def fit_gmms(adata, gene_name_list, n_comp=15, binary=False, threshold=95, max_i
 
     ``init_params`` (optional, not in the reference) is ``{gene: (weights, means, covariances)}`` or a
     tuple of stacked arrays; without it the on-device initialisation replaces sklearn's KMeans.
-    ``binary`` / ``cut`` (distribution.py:133-145) are not exposed by ``SPFinder.fit_pattern`` and are
-    not implemented on the device path.
+    ``binary`` / ``cut`` / ``threshold`` (``preprocess_array``, distribution.py:133-145) transform the staged counts on
+    the host (a per-gene percentile over the dense grid) before the upload.
     """
-    if binary or cut:
-        raise NotImplementedError("binary/cut preprocessing is outside the B200 hot path (SURVEY.md §8 a3)")
     from ..adata_lite import spot_matrix_from_adata
     gene_name_list = list(gene_name_list)
     sm = spot_matrix_from_adata(adata, gene_name_list)
+    if binary or cut:
+        sm = sm.preprocess_array(binary=binary, cut=cut and not binary, threshold=threshold,
+                                 remove_low_exp_spots=remove_low_exp_spots)
+        remove_low_exp_spots = False          # already applied, in the reference's order
     init = None
     if init_params is not None:
         if isinstance(init_params, dict):

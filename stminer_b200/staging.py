@@ -128,6 +128,38 @@ class SpotMatrix:
         return SpotMatrix(col_ptr, self.row_idx[take], self.val[take], self.spot_x, self.spot_y,
                           [self.genes[g] for g in idx])
 
+    def preprocess_array(self, binary: bool = False, cut: bool = False, threshold: float = 95,
+                         remove_low_exp_spots: bool = False) -> "SpotMatrix":
+        """``preprocess_array`` (distribution.py:133-145) on the staged columns: the optional ``binary`` (cells above the
+        ``threshold`` percentile become 1, the rest 0) and ``cut`` (cells below the percentile become 0) transforms.
+        The percentile is taken over the WHOLE dense count grid of ``get_exp_array`` — shape (max x + 1, max y + 1),
+        empty cells included (AlgUtils.py:35,15) — after the optional ``remove_low_exp_spots`` step (AlgUtils.py:16-17),
+        which is therefore applied here too: fit the returned matrix WITHOUT the remove-low flag."""
+        if not (binary or cut):
+            return self
+        if binary and (threshold > 100 or threshold < 0):
+            import logging
+            logging.getLogger(__name__).warning("the threshold is illegal, the value in [0, 100] is accepted.")
+            threshold = 100
+        n_cells = (int(self.spot_x.max()) + 1) * (int(self.spot_y.max()) + 1)
+        val = np.empty(len(self.val), dtype=np.float32)
+        for g in range(self.n_genes):
+            a, b = int(self.col_ptr[g]), int(self.col_ptr[g + 1])
+            v = _wrap_i16(np.trunc(np.asarray(self.val[a:b], dtype=np.float64)).astype(np.int64)).astype(np.int64)
+            if remove_low_exp_spots:
+                nz = v[v != 0]
+                mean = nz.mean() if len(nz) else 0.0
+                if mean < 0:
+                    raise NotImplementedError("negative mean expression: empty cells would become positive")
+                v = np.round(np.maximum(v - mean, 0)).astype(np.int64)
+            dense = np.zeros(max(n_cells, b - a), dtype=np.int64)
+            dense[:b - a] = v
+            thr = np.percentile(dense, threshold)
+            if thr < 0:
+                raise NotImplementedError("negative percentile: empty cells would pass the threshold")
+            val[a:b] = (v > thr).astype(np.float32) if binary else np.where(v < thr, 0, v).astype(np.float32)
+        return SpotMatrix(self.col_ptr, self.row_idx, val, self.spot_x, self.spot_y, self.genes)
+
     # ------------------------------------------------------------------ constructors
     @classmethod
     def from_matrix(cls, X, x, y, genes: Sequence[str], columns: Optional[Sequence[int]] = None,

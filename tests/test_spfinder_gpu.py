@@ -92,3 +92,31 @@ def test_fit_gmms_host_api_errors(finder):
         fit_gmms(finder.adata, ["not_a_gene"], n_comp=3)
     few = fit_gmms(finder.adata, list(finder.adata.var_names[:4]), n_comp=64)   # more components than spots
     assert isinstance(few, dict)
+
+
+@pytest.mark.parametrize("binary,cut", [(True, False), (False, True)])
+def test_fit_gmms_binary_and_cut_match_reference_path(finder, binary, cut):
+    """fit_gmms(binary=..., cut=..., threshold=...) (distribution.py:133-156): the transformed counts are fitted on the
+    device; from injected initial parameters the result equals the oracle EM on the reference's dense-grid path."""
+    from oracle import gmm_oracle as go
+    from stminer_b200.Algorithm.distribution import fit_gmms
+    from stminer_b200.Simulate import simulate_adata
+    adata = simulate_adata("T", seed=8, n_templates=3, replicas=2)
+    genes = list(adata.var_names[:5])
+    K, thr = 4, 80
+    X = adata.X.tocsc()
+    x, y = np.asarray(adata.obs["x"]), np.asarray(adata.obs["y"])
+    init, refs = {}, {}
+    for g in genes:
+        j = list(adata.var_names).index(g)
+        col = np.asarray(X[:, j].todense()).ravel()
+        xy, c = go.gene_column_to_counts(x, y, col, binary=binary, cut=cut, threshold=thr)
+        assert len(c) >= K
+        init[g] = go.kmeans_init(xy, c, K, seed=1)
+        refs[g] = go.weighted_em(xy, c, *init[g])
+    out = fit_gmms(adata, genes, n_comp=K, binary=binary, cut=cut, threshold=thr, init_params=init)
+    assert list(out.keys()) == genes
+    for g in genes:
+        assert out[g].n_iter_ == refs[g]["n_iter"]
+        np.testing.assert_allclose(out[g].means_, refs[g]["means"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(out[g].weights_, refs[g]["weights"], rtol=1e-4, atol=1e-6)

@@ -70,3 +70,21 @@ def test_compact_wire_format_round_trip():
     assert floats.compact() is floats
     cuts = sm.nnz_balanced_chunks(4)
     assert cuts[0] == 0 and cuts[-1] == sm.n_genes and cuts == sorted(cuts)
+
+
+@pytest.mark.parametrize("binary,cut,remove_low,thr", [(True, False, False, 95), (False, True, False, 97.5), (True, True, True, 90),
+                                                       (False, True, True, 99), (True, False, False, 150)])
+def test_preprocess_array_binary_cut_matches_reference_dense_path(binary, cut, remove_low, thr):
+    """SpotMatrix.preprocess_array (host transform of the staged columns) against the oracle's dense-grid restatement of
+    get_exp_array + preprocess_array (AlgUtils.py:8-36, distribution.py:133-145)."""
+    from oracle import gmm_oracle as go
+    from stminer_b200.Simulate import simulate_spot_matrix
+    sm = simulate_spot_matrix("T", seed=2, n_templates=3, replicas=3, truncate_int16=False)
+    out = sm.preprocess_array(binary=binary, cut=cut and not binary, threshold=thr, remove_low_exp_spots=remove_low)
+    for g in range(sm.n_genes):
+        a, b = int(sm.col_ptr[g]), int(sm.col_ptr[g + 1])
+        r = sm.row_idx[a:b]
+        xy_ref, c_ref = go.gene_column_to_counts(sm.spot_x[r], sm.spot_y[r], sm.val[a:b], remove_low_exp_spots=remove_low,
+                                                 binary=binary, cut=cut, threshold=thr)
+        xy, c = out.gene_spots(g)
+        assert np.array_equal(xy, xy_ref) and np.array_equal(c, c_ref), g
