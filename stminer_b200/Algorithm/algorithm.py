@@ -81,9 +81,16 @@ def mds_fit_transform(dissimilarities, n_components: int = 2, n_init: int = 4, m
     torch = _lib.require_cuda()
     Dd = torch.from_numpy(np.ascontiguousarray(D)).to(device if device is not None else "cuda")
     runs = []
-    for _ in range(n_init):
-        X0 = rs.uniform(size=n * n_components).reshape((n, n_components))
-        runs.append(mds_smacof(Dd, X0, max_iter=max_iter, eps=eps, rule=rule, device=Dd.device))
+    # the restarts are independent: each goes to its own stream so that their passes (n/8 CTAs each) fill the GPU together
+    main = torch.cuda.current_stream(Dd.device)
+    streams = [torch.cuda.Stream(device=Dd.device) for _ in range(n_init)] if n_init > 1 else [main]
+    for r in range(n_init):
+        X0 = rs.uniform(size=n * n_components).reshape((n, n_components))     # drawn in restart order, as sklearn does
+        streams[r].wait_stream(main)
+        with torch.cuda.stream(streams[r]):
+            runs.append(mds_smacof(Dd, X0, max_iter=max_iter, eps=eps, rule=rule, device=Dd.device))
+    for st in streams:
+        main.wait_stream(st)
     best = None
     for X, stress, n_iter in runs:      # first-lowest wins, as `if best_stress is None or stress < best_stress`
         s = float(stress.cpu().numpy()[0])
