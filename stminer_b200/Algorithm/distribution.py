@@ -124,7 +124,7 @@ def fit_spot_matrix(dsm: DeviceSpotMatrix, n_comp: int, init=None, max_iter: int
     return out
 
 
-def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_chunks: int = 4, **kw) -> dict:
+def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_chunks: int = 6, **kw) -> dict:
     """Host buffers in, host buffers out — the call ``bench.py`` times end to end.
 
     The CSC matrix is uploaded in ``n_chunks`` gene ranges (``chunk_fractions`` = cumulative shares of the stored values)
@@ -136,9 +136,10 @@ def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_
     G, K = sm.n_genes, int(n_comp)
     if kw.pop("compact", True):
         sm = sm.compact()          # 4 B / value on the wire when the matrix allows it (no-op otherwise)
-    # default: growing chunks — a small first one so the fit starts after 5 % of the upload, then fewer, larger ones
-    # (every chunk boundary costs a launch tail); measured on B200 / S50: 26.8 ms against 28.8 ms for four equal chunks
-    fractions = kw.pop("chunk_fractions", (0.05, 0.2, 0.5, 1.0) if n_chunks == 4 else None)
+    # default: growing chunks — a small first one so the fit starts after 3 % of the upload — on two alternating
+    # compute lanes; measured on B200 / S50: 25.5 ms against 28.8 ms for four equal chunks on one lane (23.9 ms resident)
+    fractions = kw.pop("chunk_fractions", (0.03, 0.1, 0.25, 0.5, 0.75, 1.0) if n_chunks == 6 else None)
+    two_lanes = kw.pop("two_lanes", True)
     cuts = sm.nnz_balanced_chunks(n_chunks, fractions=fractions)
     from ..staging import StreamedDeviceSpotMatrix
     with torch.cuda.device(dev):
@@ -149,19 +150,28 @@ def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_
         full = FitResult(sm.genes, f64(G, K), f64(G, K, 2), f64(G, K, 2, 2), i32(G), i32(G), f64(G), i32(G))
         whole = StreamedDeviceSpotMatrix(sm, dev)          # buffers allocated once, on the compute stream
         copy.wait_stream(compute)
+        # the chunks are independent: they alternate between two compute lanes, so the kernels of chunk i + 1 start
+        # while the last (shortest) genes of chunk i are still running instead of waiting behind its join
+        lanes = [compute, _copy_stream(dev, 1)] if two_lanes else [compute]
+        for lane in lanes[1:]:
+            lane.wait_stream(compute)
         keep = []
-        for g0, g1 in zip(cuts[:-1], cuts[1:]):
+        for ci, (g0, g1) in enumerate(zip(cuts[:-1], cuts[1:])):
             with torch.cuda.stream(copy):
                 whole.upload_genes(g0, g1)
                 ready = torch.cuda.Event()
                 ready.record(copy)
             view = whole.gene_view(g0, g1)
-            compute.wait_event(ready)
+            lane = lanes[ci % len(lanes)]
+            lane.wait_event(ready)
             out = FitResult(view.host.genes, full.weights[g0:g1], full.means[g0:g1], full.covariances[g0:g1],
                             full.n_iter[g0:g1], full.converged[g0:g1], full.lower_bound[g0:g1], full.status[g0:g1])
             sub_init = None if init is None else tuple(np.asarray(a)[g0:g1] for a in init)
-            fit_spot_matrix(view, K, init=sub_init, out=out, **kw)
+            with torch.cuda.stream(lane):
+                fit_spot_matrix(view, K, init=sub_init, out=out, **kw)
             keep.append((view, out))
+        for lane in lanes[1:]:
+            compute.wait_stream(lane)
         host = full.to_host()
         compute.wait_stream(copy)
     return host
@@ -170,10 +180,10 @@ def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_
 _COPY_STREAMS = {}
 
 
-def _copy_stream(dev):
-    """One side stream per device for the chunked uploads (created once)."""
+def _copy_stream(dev, which: int = 0):
+    """Side streams per device (created once): 0 = the chunked uploads, 1 = the second compute lane."""
     import torch
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), which)
     if key not in _COPY_STREAMS:
         _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
     return _COPY_STREAMS[key]
