@@ -56,6 +56,12 @@ constexpr int KM_LMAX = 6;                // greedy k-means++ candidates: 2 + fl
 #ifndef STM_EM_MAGIC_I2F
 #define STM_EM_MAGIC_I2F 0    // int16 -> float by magic-number add instead of I2F (XU pipe)
 #endif
+#ifndef STM_EM_T_LARGE
+#define STM_EM_T_LARGE 512    // CTA size of the one-CTA large bucket (1 CTA per SM)
+#endif
+#ifndef STM_EM_S_LARGE
+#define STM_EM_S_LARGE 2      // spots in flight per thread group, large bucket
+#endif
 #ifndef STM_EM_QMOMENT
 #define STM_EM_QMOMENT 0      // accumulate sum r*(t0^2+t1^2) instead of sum r*t1^2 (one FMA-pipe operation less per component)
 #endif
@@ -1274,7 +1280,7 @@ constexpr int N_CFG = 4;
 template <int KT, int GS>
 inline void fill_cfg(BucketCfg (&c)[N_CFG]) {
   c[0] = {512, 1, EmLayout<KT, GS, 512, true>::fixed_bytes(), 2048};
-  c[1] = {512, 1, EmLayout<KT, GS, 512>::fixed_bytes(), 2048};
+  c[1] = {STM_EM_T_LARGE, 1, EmLayout<KT, GS, STM_EM_T_LARGE>::fixed_bytes(), 2048};
   c[2] = {256, 2, EmLayout<KT, GS, 256>::fixed_bytes(), 1024};
   c[3] = {128, STM_EM_MINB_SMALL, EmLayout<KT, GS, 128>::fixed_bytes(), 1024};
 }
@@ -1345,7 +1351,7 @@ int launch_em(EmArgs a, const BucketCfg& cfg, int n_genes, int cluster, cudaStre
 template <int KT, int GS>
 int launch_bucket(const EmArgs& a, const BucketCfg (&c)[N_CFG], int bucket, int n_genes, cudaStream_t st) {
   if (bucket < N_CLUSTER_BUCKETS) return launch_em<KT, GS, 2, 512, 1, true>(a, c[0], n_genes, CLUSTER_SIZE[bucket], st);
-  if (bucket == 4) return launch_em<KT, GS, 2, 512, 1, false>(a, c[1], n_genes, 1, st);
+  if (bucket == 4) return launch_em<KT, GS, STM_EM_S_LARGE, STM_EM_T_LARGE, 1, false>(a, c[1], n_genes, 1, st);
   if (bucket == 5) return launch_em<KT, GS, 2, 256, 2, false>(a, c[2], n_genes, 1, st);
   return launch_em<KT, GS, STM_EM_S_SMALL, 128, STM_EM_MINB_SMALL, false>(a, c[3], n_genes, 1, st);
 }
