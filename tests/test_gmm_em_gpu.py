@@ -140,12 +140,17 @@ def test_long_gene_buckets_and_streaming(cuda_device):
     assert buckets.tolist() == [0, 0, 0, 1, 1, 1, 1]      # 30,000 spots: a cluster of 2 CTAs
     W, MU, COV, ok = oracle_inits(sm, K, seed=2)
     ref = oracle_fit_all(sm, K, W, MU, COV, ok)
+    smc = sm.compact()                    # 4 B / value wire format (uint16 spot, int16 value): same results, bit for bit
+    assert smc.is_compact
     for no_clusters in (True, False):
         res = _fit(sm, K, (W, MU, COV), no_clusters=no_clusters)
         for g in range(4):
             assert res["status"][g] == 0
             assert res["n_iter"][g] == ref[g]["n_iter"], g
             assert_gmm_close(res, g, ref[g], what="gene %d" % g)
+        resc = _fit(smc, K, (W, MU, COV), no_clusters=no_clusters)
+        for k in ("weights", "means", "covariances", "n_iter", "lower_bound"):
+            assert np.array_equal(res[k], resc[k]), (k, no_clusters)
 
 
 @pytest.mark.parametrize("config,K", [("T", 10), ("V", 20)])
