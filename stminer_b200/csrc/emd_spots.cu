@@ -18,6 +18,8 @@
 #include <limits.h>
 #include <math.h>
 
+#include <algorithm>
+
 #include "stm_common.cuh"
 
 namespace stm {
@@ -33,6 +35,7 @@ struct EmdArgs {
   const int32_t* src_x; const int32_t* src_y; const double* src_mass; int32_t n_src;
   const int64_t* tgt_ptr; const int32_t* tgt_x; const int32_t* tgt_y; const double* tgt_mass;
   int32_t G; int32_t cap_nodes;   // shared-memory capacity in nodes
+  int32_t flow_smem_nodes;        // arc flows of nodes below this index live in shared memory, the rest in flow_ws
   int64_t max_iter; int32_t block_size;
   int64_t* src_int;               // [n_src] integer source masses (prep kernel)
   int64_t* flow_ws;               // [gridDim.x][cap_nodes]
@@ -111,7 +114,12 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
   // s_pi holds ADJUSTED potentials: pi_i + |x_i|^2 for sources, pi_j - |x_j|^2 for sinks, so that the reduced
   // cost of arc (i, j) is  s_pi[i] - s_pi[j] - 2 x_i.x_j  (one subtraction + two IMAD per arc); a subtree shift
   // adds the same constant to either form.
-  int* s_pi = reinterpret_cast<int*>(smem_raw);                          // [cap]
+  // arc flows (int64): nodes [0, fcap) in shared memory — whatever is left of the CTA's budget once the tree is
+  // placed — the others in the per-CTA global slice; the leaving-arc search and the flow update then run at
+  // shared-memory instead of L2 latency
+  const int fcap = p.flow_smem_nodes;
+  long long* s_flow = reinterpret_cast<long long*>(smem_raw);           // [fcap]
+  int* s_pi = reinterpret_cast<int*>(s_flow + fcap);                     // [cap]
   int* s_xy = s_pi + cap;                                                // [cap] {int16 x | int16 y}
   unsigned short* s_parent = reinterpret_cast<unsigned short*>(s_xy + cap);
   unsigned short* s_pos = s_parent + cap;
@@ -131,6 +139,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.n_src;
   int64_t* flow = p.flow_ws + (size_t)blockIdx.x * cap;
+  auto FL = [&](int v) -> long long& { return v < fcap ? s_flow[v] : *reinterpret_cast<long long*>(flow + v); };
 
   for (;;) {
     __syncthreads();
@@ -183,6 +192,8 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
       s_order[0] = (unsigned short)root; s_pos[root] = 0; s_size[root] = (unsigned short)N; s_parent[root] = NONE16;
       s_pi[root] = 0; flow[root] = 0; s_i[4] = 0;
     }
+    __syncthreads();
+    for (int v = tid; v < min(fcap, N); v += EMD_THREADS) s_flow[v] = flow[v];
     __syncthreads();
 
     const int n_arcs = n * m;
@@ -325,11 +336,11 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
         int seq = -1;
         for (int a = lane; a < lenA; a += 32) {
           const int v = s_pathA[a];
-          if (v < n) { const long long f = flow[v]; const int sq = lenA - 1 - a; if (f < dmin || (f == dmin && sq > seq)) { dmin = f; seq = sq; } }
+          if (v < n) { const long long f = FL(v); const int sq = lenA - 1 - a; if (f < dmin || (f == dmin && sq > seq)) { dmin = f; seq = sq; } }
         }
         for (int b = lane; b < lenB; b += 32) {
           const int v = s_pathB[b];
-          if (v >= n) { const long long f = flow[v]; const int sq = lenA + b; if (f < dmin || (f == dmin && sq > seq)) { dmin = f; seq = sq; } }
+          if (v >= n) { const long long f = FL(v); const int sq = lenA + b; if (f < dmin || (f == dmin && sq > seq)) { dmin = f; seq = sq; } }
         }
         for (int o = 16; o > 0; o >>= 1) {
           const long long od = shfl_xor_ll(dmin, o);
@@ -355,8 +366,8 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
       const int ptr = pt < a0 ? pt : pt - s;
       const int shift = side == 0 ? -best_rc : best_rc;
       // ---- flow update along the cycle + old flows / positions / sizes of the reversed path --------
-      for (int a = tid; a < lenA; a += EMD_THREADS) { const int v = s_pathA[a]; flow[v] += (v < n) ? -delta : delta; }
-      for (int b = tid; b < lenB; b += EMD_THREADS) { const int v = s_pathB[b]; flow[v] += (v >= n) ? -delta : delta; }
+      for (int a = tid; a < lenA; a += EMD_THREADS) { const int v = s_pathA[a]; FL(v) += (v < n) ? -delta : delta; }
+      for (int b = tid; b < lenB; b += EMD_THREADS) { const int v = s_pathB[b]; FL(v) += (v >= n) ? -delta : delta; }
       for (int t = tid; t <= k; t += EMD_THREADS) { const int v = pathX[t]; s_P[t] = s_pos[v]; s_S[t] = s_size[v]; }
       // potential shift of the re-hung subtree (a contiguous preorder segment)
       for (int x = a0 + tid; x < a0 + s; x += EMD_THREADS) s_pi[s_order[x]] += shift;
@@ -372,7 +383,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
 #pragma unroll
         for (int r = 0; r < MAXT; ++r) {
           const int t = tid + r * EMD_THREADS;
-          fo[r] = (t >= 1 && t <= k) ? flow[pathX[t - 1]] : 0;
+          fo[r] = (t >= 1 && t <= k) ? FL(pathX[t - 1]) : 0;
         }
         __syncthreads();
 #pragma unroll
@@ -380,8 +391,8 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
           const int t = tid + r * EMD_THREADS;
           if (t <= k) {
             const int v = pathX[t];
-            if (t == 0) { s_parent[v] = (unsigned short)t_in; flow[v] = delta; s_size[v] = (unsigned short)s; }
-            else { s_parent[v] = pathX[t - 1]; flow[v] = fo[r]; s_size[v] = (unsigned short)(s - s_S[t - 1]); }
+            if (t == 0) { s_parent[v] = (unsigned short)t_in; FL(v) = delta; s_size[v] = (unsigned short)s; }
+            else { s_parent[v] = pathX[t - 1]; FL(v) = fo[r]; s_size[v] = (unsigned short)(s - s_S[t - 1]); }
           }
         }
       }
@@ -424,7 +435,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     double part = 0.0;
     for (int v = tid; v < n + m; v += EMD_THREADS) {
       const int pr = s_parent[v];
-      const long long f = flow[v];
+      const long long f = FL(v);
       if (pr != root && f != 0) {
         const int i = v < n ? v : pr, j = v < n ? pr : v;
         const int a = s_xy[i], b = s_xy[j];
@@ -441,8 +452,8 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
   }
 }
 
-inline size_t emd_smem_bytes(int64_t cap_nodes) {
-  return (size_t)cap_nodes * (4 + 2 + 2 + 5 * 2) + 4 * (size_t)EMD_MAXPATH * 2 + 64;
+inline size_t emd_smem_bytes(int64_t cap_nodes, int64_t flow_nodes = 0) {
+  return (size_t)flow_nodes * 8 + (size_t)cap_nodes * (4 + 2 + 2 + 5 * 2) + 4 * (size_t)EMD_MAXPATH * 2 + 64;
 }
 inline int64_t emd_ws_cap(int64_t n_src, int64_t max_tgt) { return (n_src + max_tgt + 1 + 7) & ~7LL; }
 
@@ -488,11 +499,19 @@ extern "C" int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y,
   STM_CHECK_CUDA(cudaMemsetAsync(a.counter, 0, 256, st));
   emd_prep_kernel<<<1, EMD_PREP_THREADS, 0, st>>>(src_mass, n_src, a.src_int);
   STM_CHECK_CUDA(cudaGetLastError());
-  const size_t smem = emd_smem_bytes((int)cap);
+  const size_t tree_smem = emd_smem_bytes((int)cap);
   const int grid = n_ctas < G ? n_ctas : G;
   // Problems that leave room for only one CTA per SM get 1,024 threads (pricing is the dominant phase and
   // scales with the thread count); small problems run several 256-thread CTAs per SM.
-  if (smem * 2 + 2048 > (size_t)max_optin) {
+  const bool one_per_sm = tree_smem * 2 + 2048 > (size_t)max_optin;
+  // what is left of a CTA's share of the SM's shared memory (without lowering the CTAs per SM) holds arc flows
+  const int64_t per_sm = one_per_sm ? 1 : std::min<int64_t>(8, (int64_t)max_optin / (int64_t)(tree_smem + 1024));
+  const int64_t share = one_per_sm ? (int64_t)max_optin - 4096 : (int64_t)max_optin / per_sm - 1024 - 256;
+  int64_t fcap = (share - (int64_t)tree_smem) / 8;
+  fcap = std::max<int64_t>(0, std::min<int64_t>(fcap, cap)) & ~1LL;
+  a.flow_smem_nodes = (int32_t)fcap;
+  const size_t smem = emd_smem_bytes((int)cap, fcap);
+  if (one_per_sm) {
     STM_CHECK_CUDA(cudaFuncSetAttribute(emd_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     emd_kernel<1024><<<grid, 1024, smem, st>>>(a);
   } else {
