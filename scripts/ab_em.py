@@ -1,6 +1,6 @@
 """A/B timing of library variants (STM_LIB_PATH): full fit (device init + EM) on S50 and on an S10 subset."""
 import os, sys, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, '.')
 import torch
 from bench import workload
 from stminer_b200.Algorithm.distribution import fit_spot_matrix

@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, '.')
 from oracle import dist_oracle as do
 from stminer_b200.Algorithm.distance import gmm_pair_distances, pairs_to_square, gmm_one_vs_all
 import torch

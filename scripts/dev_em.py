@@ -1,5 +1,5 @@
 import numpy as np, time, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, '.')
 from stminer_b200.Simulate import simulate_spot_matrix
 from tests.helpers import *
 from oracle import gmm_oracle as go

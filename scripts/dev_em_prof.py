@@ -1,5 +1,5 @@
 import sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, '.')
 import torch
 from bench import workload
 from stminer_b200.Algorithm.distribution import fit_spot_matrix

@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, '.')
 from oracle import emd_oracle as eo
 from stminer_b200.Algorithm.distance import emd_batched
 rng = np.random.default_rng(0)

@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, '.')
 from stminer_b200.Algorithm.distance import emd_batched
 from stminer_b200.Simulate import simulate_spot_matrix
 from scipy import sparse

@@ -1,6 +1,6 @@
 """Experiment driver (one process per library variant): EM-only and device-init timings + fit quality."""
 import os, sys, time, json, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, '.')
 import torch
 from bench import workload
 from stminer_b200.Algorithm.distribution import fit_spot_matrix

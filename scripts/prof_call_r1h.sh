@@ -1,0 +1,13 @@
+# Final round-1 captures: launch list + full capture of the bench step, then the distance, EMD and MDS kernels.
+set -x
+B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --emd-genes 0 --no-mds --s10-genes 0 --pairs-genes 500"
+$B > gpurun_out/r1h_plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1h_launches_bench.csv $B > gpurun_out/r1h_ncu_a.log 2>&1
+$B > gpurun_out/r1h_plain_bench2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gmm_em_kernel -s 6 -c 2 -f -o gpurun_out/r1h_bench_step $B > gpurun_out/r1h_ncu_b.log 2>&1
+D="python scripts/prof_dist.py 1500"
+$D > gpurun_out/r1h_plain_dist.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gmm_dist_kernel -s 1 -c 1 -f -o gpurun_out/r1h_dist $D > gpurun_out/r1h_ncu_c.log 2>&1
+E="python scripts/prof_emd.py"
+$E > gpurun_out/r1h_plain_emd.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:emd_kernel -s 1 -c 1 -f -o gpurun_out/r1h_emd $E > gpurun_out/r1h_ncu_d.log 2>&1
+M="python scripts/prof_mds.py 4000 6"
+$M > gpurun_out/r1h_plain_mds.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:mds_rows -s 2 -c 1 -f -o gpurun_out/r1h_mds $M > gpurun_out/r1h_ncu_e.log 2>&1
+cat gpurun_out/r1h_plain_dist.log gpurun_out/r1h_plain_emd.log gpurun_out/r1h_plain_mds.log | grep -v Warn
+ls -la gpurun_out/r1h_*.ncu-rep

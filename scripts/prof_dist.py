@@ -1,5 +1,5 @@
 import sys, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, '.')
 import torch
 from oracle import dist_oracle as do
 from stminer_b200.Algorithm.distance import gmm_pair_distances

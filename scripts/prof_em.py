@@ -1,6 +1,6 @@
 """Profiling driver: V-config fit with device init, then EM-only from fixed parameters (for ncu / timing)."""
 import sys, time, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, '.')
 import torch
 from bench import workload
 from stminer_b200.Algorithm.distribution import fit_spot_matrix

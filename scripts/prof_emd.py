@@ -1,5 +1,5 @@
 import sys, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, '.')
 import torch
 from stminer_b200.Algorithm.distance import emd_batched
 rng = np.random.default_rng(0)

@@ -28,6 +28,30 @@ def test_lsap_random_and_adversarial(cuda_device, K):
     np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-9)
 
 
+@pytest.mark.parametrize("K", [2, 5, 20, 40])
+def test_lsap_forbidden_entries(cuda_device, K):
+    """+inf entries are forbidden assignments (scipy accepts them); a matrix without a finite perfect matching is
+    infeasible: scipy raises ValueError, the kernel reports NaN."""
+    from stminer_b200.Algorithm.algorithm import linear_sum_batched
+    rng = np.random.default_rng(100 + K)
+    mats = []
+    for _ in range(30):
+        C = rng.random((K, K))
+        C[rng.random((K, K)) < 0.4] = np.inf
+        perm = rng.permutation(K)
+        C[np.arange(K), perm] = rng.random(K)          # one finite perfect matching is guaranteed
+        mats.append(C)
+    got = linear_sum_batched(np.stack(mats)).cpu().numpy()
+    ref = np.array([_ref(C) for C in mats])
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12)
+    bad = rng.random((K, K)); bad[:, 0] = np.inf       # column 0 cannot be used by anyone
+    bad2 = rng.random((K, K)); bad2[0, :] = np.inf
+    out = linear_sum_batched(np.stack([bad, bad2])).cpu().numpy()
+    assert np.isnan(out).all()
+    with pytest.raises(ValueError):
+        linear_sum_assignment(bad)
+
+
 def test_linear_sum_drop_in(cuda_device):
     from stminer_b200.Algorithm.algorithm import linear_sum
     C = np.array([[4.0, 1, 3], [2, 0, 5], [3, 2, 2]])
