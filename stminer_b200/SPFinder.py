@@ -317,6 +317,15 @@ class SPFinder:
         else:
             raise ValueError("mode should be vote or test")
 
+    def get_pattern_of_given_genes(self, gene_list: List[str], n_comp: int = 20) -> None:
+        """SPFinder.py:572-598: pattern of a user-provided gene list; genes absent from ``adata.var.index`` are silently
+        ignored, the result is stored by ``get_custom_pattern`` (``self.custom_pattern``)."""
+        if self.adata is None:
+            raise ValueError("Please load ST data first.")
+        var_index = set(self.adata.var.index)
+        _genes = [gene for gene in gene_list if gene in var_index]
+        self.get_custom_pattern(gene_list=_genes, n_components=n_comp, vote_rate=0)
+
     def get_all_labels(self) -> None:
         """SPFinder.py:556-570: nearest voted pattern (by GMM distance) of every fitted gene."""
         df_list = []

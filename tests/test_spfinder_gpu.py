@@ -82,6 +82,13 @@ def test_fit_distance_cluster_pattern_flow(finder):
     assert df.index[0] == genes[0] and df.shape == (len(genes), 1)
     sp.get_custom_pattern(genes[:3], n_components=4, vote_rate=0, mode="vote")
     assert sp.custom_pattern is not None and sp.custom_pattern.weights_.shape == (4,)
+    first = sp.custom_pattern.means_.copy()
+    sp.custom_pattern = None
+    sp.get_pattern_of_given_genes(genes[:3] + ["not_a_gene"], n_comp=4)      # unknown genes are silently ignored
+    assert np.array_equal(sp.custom_pattern.means_, first)
+    from stminer_b200.SPFinder import SPFinder
+    with pytest.raises(ValueError, match="load ST data"):
+        SPFinder().get_pattern_of_given_genes(["a"])
     sp.get_all_labels()
     assert set(sp.all_labels.columns) == {"label", "value"} and len(sp.all_labels) == len(genes)
 
