@@ -25,7 +25,13 @@
 namespace stm {
 namespace {
 
-constexpr int MDS_T = 256;       // threads per CTA of the row pass: 8 warps = 8 rows
+#ifndef STM_MDS_T
+#define STM_MDS_T 256
+#endif
+#ifndef STM_MDS_MINB
+#define STM_MDS_MINB 2   // 2 CTAs per SM (128 registers, a few spills) beat 1 CTA at 166 registers: 0.27 vs 0.34 ms per pass
+#endif
+constexpr int MDS_T = STM_MDS_T;  // threads per CTA of the row pass: one row per warp
 constexpr int MDS_TJ = 256;      // columns j per shared-memory tile
 
 struct MdsState {
@@ -53,7 +59,7 @@ __global__ void mds_unpack_kernel(const double* __restrict__ XT0, const double* 
 }
 
 template <int DP>
-__global__ void __launch_bounds__(MDS_T) mds_rows_kernel(const double* __restrict__ D, const double* __restrict__ Xin,
+__global__ void __launch_bounds__(MDS_T, STM_MDS_MINB) mds_rows_kernel(const double* __restrict__ D, const double* __restrict__ Xin,
                                                          double* __restrict__ Xout, int n,
                                                          double* __restrict__ row_stress, double* __restrict__ row_ssd,
                                                          const MdsState* st) {
