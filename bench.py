@@ -412,9 +412,9 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": args.steps * n_launch,
         "roofline": {"bound": "fp32_fma", "achieved": em_tflops, "peak": fma_peak, "unit": "TFLOP/s",
                      "frac": em_tflops / fma_peak,
-                     # ncu --set full of this command's step launches (profiles/r1g_ncu_r1g_bench_step.txt):
-                     # dram__bytes_read+write = 376.1 MB (large bucket) + 150.8 MB (medium) vs 506 MB of input
-                     "traffic": 526.9e6 if (args.workload == "S50" and not args.genes and sm.is_compact) else None,
+                     # ncu --set full of this command's step launches (profiles/r1h_ncu_bench_step.txt):
+                     # dram__bytes_read+write = 374.3 MB (large bucket) + 150.4 MB (medium) vs 506 MB of input
+                     "traffic": 524.6e6 if (args.workload == "S50" and not args.genes and sm.is_compact) else None,
                      "traffic_unit": "bytes per step (sum over the step's bucket launches)",
                      "kernel": "gmm_em_kernel (%d nnz-bucket launches per step, run concurrently)" % n_launch,
                      "peak_source": "measured here with stm_bench_fma (FFMA chains); nominal %.1f TFLOP/s; "
