@@ -13,7 +13,9 @@
  *   - calls only enqueue work on `stream`; there is no host synchronisation inside,
  *   - return value: 0 on success, <0 on error (STM_ERR_*); the message of the
  *     last error of the calling thread is available from stm_last_error_string(),
- *   - the library is stateless and thread-compatible (one caller thread per GPU rank).
+ *   - the library keeps no state between calls except, per calling thread and device, a few auxiliary CUDA
+ *     streams / events created on first use (the nnz buckets of one fit run concurrently on them, forked from and
+ *     joined back into `stream`); it is thread-compatible (one caller thread per GPU rank).
  */
 #ifndef STMINER_B200_H_
 #define STMINER_B200_H_

@@ -28,6 +28,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <map>
 #include <numeric>
 #include <vector>
 
@@ -1374,12 +1375,13 @@ struct AuxStreams {
   cudaEvent_t fork = nullptr, join[N_BUCKETS - 1] = {};
   int dev = -1;
 };
-thread_local AuxStreams g_aux[16];
+thread_local std::map<int, AuxStreams> g_aux;   // per calling thread and device, created on first use, kept for the
+                                                // life of the thread (a rank drives one device)
 
 int get_aux(AuxStreams** out) {
   int dev = 0;
   STM_CHECK_CUDA(cudaGetDevice(&dev));
-  AuxStreams& a = g_aux[dev & 15];
+  AuxStreams& a = g_aux[dev];
   if (a.dev != dev) {
     for (int i = 0; i < N_BUCKETS - 1; ++i) {
       STM_CHECK_CUDA(cudaStreamCreateWithFlags(&a.s[i], cudaStreamNonBlocking));
