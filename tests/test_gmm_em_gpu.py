@@ -323,3 +323,35 @@ def test_cluster_device_init_remove_low_and_dropped(cuda_device):
         ref = go.weighted_em(xy, cnt, w0, mu0, cov0, max_iter=8)
         assert r["status"][g] == 0 and r["n_iter"][g] == ref["n_iter"]
         assert_gmm_close(r, g, ref, what="remove_low cluster gene %d" % g)
+
+
+def test_ill_conditioned_covariance_reports_status_2(cuda_device):
+    """A covariance that loses positive-definiteness (collinear spots, reg_covar = 0): sklearn raises ValueError
+    ("ill-defined empirical covariance", _gaussian_mixture.py:361-367 -> distribution.py:200-202); the kernel reports
+    STM_GENE_ILL_CONDITIONED with zero-filled outputs, the host mirror raises for that gene, healthy genes are unaffected."""
+    from sklearn.mixture import GaussianMixture
+    from oracle import gmm_oracle as go
+    from stminer_b200.Algorithm.distribution import result_to_gmm_dict
+    from stminer_b200.staging import SpotMatrix
+    rng = np.random.default_rng(0)
+    n = 60
+    x_line, y_line = np.arange(n, dtype=np.int32), np.full(n, 7, dtype=np.int32)          # all spots on one grid line
+    x_ok, y_ok = rng.integers(0, 30, n).astype(np.int32), rng.integers(0, 30, n).astype(np.int32)
+    sx, sy = np.concatenate([x_line, x_ok]), np.concatenate([y_line, y_ok])
+    val = (1 + rng.poisson(2.0, 2 * n)).astype(np.float32)
+    sm = SpotMatrix(np.array([0, n, 2 * n], dtype=np.int64), np.arange(2 * n, dtype=np.int32), val, sx, sy, ["line", "ok"])
+    K = 2
+    w0 = np.full(K, 0.5)
+    mu0 = np.array([[15.0, 7.0], [45.0, 7.0]])
+    cov0 = np.tile(np.array([[50.0, 0.0], [0.0, 1.0]]), (K, 1, 1))
+    init = (np.tile(w0, (2, 1)), np.stack([mu0, np.array([[8.0, 8.0], [22.0, 22.0]])]), np.tile(cov0, (2, 1, 1, 1)))
+    res = _fit(sm, K, init, reg_covar=0.0)
+    assert res["status"].tolist() == [2, 0]
+    assert not res["weights"][0].any() and not res["covariances"][0].any() and res["converged"][0] == 0
+    assert abs(res["weights"][1].sum() - 1.0) < 1e-9
+    xy, c = sm.gene_spots(0)
+    with pytest.raises(ValueError):            # the reference's own solver on the same gene
+        GaussianMixture(K, reg_covar=0.0, weights_init=w0, means_init=mu0,
+                        precisions_init=np.linalg.inv(cov0)).fit(go.array_to_list(xy, c).astype(float))
+    with pytest.raises(ValueError, match="Gene id: line"):
+        result_to_gmm_dict(sm.genes, res)
