@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
   unsigned short* s_S = s_P + EMD_MAXPATH;
   __shared__ double s_scr[EMD_WARPS];
   __shared__ long long s_ll[3 * EMD_WARPS];
-  __shared__ unsigned long long s_slot[3];
+  __shared__ int2 s_wkey[2 * EMD_WARPS];   // per-warp (reduced cost, position) of the pricing arg-min, double-buffered
   __shared__ int s_i[16];
   __shared__ long long s_delta;
 
@@ -208,7 +208,6 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     long long it = 0;
     int status = 0;
     unsigned round = 0;
-    if (tid == 0) { s_slot[0] = ~0ULL; s_slot[1] = ~0ULL; s_slot[2] = ~0ULL; }
     __syncthreads();
 
 #ifdef STM_EMD_PROFILE
@@ -228,7 +227,8 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
         // The block is arcs [next_arc, next_arc + cnt) of the j-major arc order (wrapping): a few target rows,
         // each a contiguous range of sources.  Per row the target's terms stay in registers and the inner loop is
         // two shared loads, two IMADs and a compare per arc.
-        long long key = LLONG_MAX;
+        int g_rc = INT_MAX;          // most negative reduced cost of the block (INT_MAX: none below zero)
+        unsigned g_k = 0xffffffffu;  // its position in block order (ties: first in the serial scan order)
         {
           int brc = 0, bi = -1, bj_best = 0;
           if (whole_rows) {
@@ -271,32 +271,31 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
               if (++j >= m) j = 0;
             }
           }
+          int k = 0;
           if (bi >= 0) {
-            int k = bj_best * n + bi - next_arc;   // position in block order decides ties, as in the serial scan
+            k = bj_best * n + bi - next_arc;   // position in block order decides ties, as in the serial scan
             if (k < 0) k += n_arcs;
-            key = ((long long)brc << 32) | (unsigned)k;
           }
-        }
-        for (int o = 16; o > 0; o >>= 1) key = min(key, shfl_xor_ll(key, o));
-        // cross-warp minimum: one shared atomicMin per warp on a rotating slot.  Thread 0 re-arms the NEXT round's slot
-        // before this round's barrier; with three slots that one was last read two rounds ago, i.e. before the
-        // barrier every thread has already passed (two slots would race with a slow reader of the previous round)
-        {
-          unsigned long long* slot = s_slot + round % 3;
-          if (tid == 0) s_slot[(round + 1) % 3] = ~0ULL;
-          if (lane == 0) atomicMin(slot, (unsigned long long)key ^ 0x8000000000000000ULL);
+          // lexicographic (reduced cost, position) minimum in two 32-bit REDUX steps per level: over the warp, then —
+          // through one shared entry per warp, double-buffered, one barrier — over the CTA.  (A 64-bit shared
+          // atomicMin is a CAS loop: 32 warps contending on one slot cost several thousand cycles per block.)
+          const int w_rc = __reduce_min_sync(FULL_MASK, bi >= 0 ? brc : INT_MAX);
+          const unsigned w_k = __reduce_min_sync(FULL_MASK, (bi >= 0 && brc == w_rc) ? (unsigned)k : 0xffffffffu);
+          int2* wkey = s_wkey + (round & 1) * EMD_WARPS;
+          if (lane == 0) wkey[warp] = make_int2(w_rc, (int)w_k);
           __syncthreads();
-          key = (long long)(*slot ^ 0x8000000000000000ULL);
+          const int2 e = lane < EMD_WARPS ? wkey[lane] : make_int2(INT_MAX, -1);
+          g_rc = __reduce_min_sync(FULL_MASK, e.x);
+          g_k = __reduce_min_sync(FULL_MASK, e.x == g_rc ? (unsigned)e.y : 0xffffffffu);
           ++round;
         }
-        const int rc = (int)(key >> 32);
         const int start = next_arc;
         scanned += cnt;
         next_arc += cnt;
         if (next_arc >= n_arcs) next_arc -= n_arcs;
-        if (key != LLONG_MAX && rc < 0) {
-          best_rc = rc;
-          best_e = start + (int)(unsigned)key;
+        if (g_rc < 0) {
+          best_rc = g_rc;
+          best_e = start + (int)g_k;
           if (best_e >= n_arcs) best_e -= n_arcs;
           break;
         }

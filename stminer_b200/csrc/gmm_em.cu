@@ -952,12 +952,12 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     float ccx = 0.f, ccy = 0.f;
     constexpr int SEED_R = 8;   // seeds per thread that can stay in registers over the K rounds
     if (ns <= SEED_R * T) {
-      // Register-resident rounds: a thread keeps ITS seeds (x, y, w, running D^2) in registers, the warp arg-min is two
-      // REDUX instructions, the CTA arg-min one shared atomicMin per warp on a double-buffered slot — one barrier and no
-      // seed traffic per round (the rounds are latency-bound: 2.7k -> ~1k cycles each).  Same keys, same (key, index)
-      // order, hence the same picks as the generic loop below.
-      __shared__ unsigned long long s_slot3[3];   // three rotating slots: the one re-armed in round c was last read in
-                                                  // round c - 2, i.e. before the barrier every thread passed to get here
+      // Register-resident rounds: a thread keeps ITS seeds (x, y, w, running D^2) in registers; the arg-min over the
+      // warp is two REDUX instructions, the arg-min over the CTA goes through one shared entry per warp (double-
+      // buffered) and two more REDUX — one barrier, no atomics and no seed traffic per round (the rounds are
+      // latency-bound).  Same keys, same (key, index) order, hence the same picks as the generic loop below.
+      uint2* s_wkey = reinterpret_cast<uint2*>(s_red);   // [2 * WARPS]; s_red is idle until the first flush_stats
+      static_assert(4 * WARPS <= WARPS * NSTAT, "s_wkey aliases s_red");
       float px[SEED_R], py[SEED_R], pw[SEED_R], pd[SEED_R];
 #pragma unroll
       for (int r = 0; r < SEED_R; ++r) {
@@ -965,8 +965,6 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
         const float4 v = i < ns ? s_seed[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         px[r] = v.x; py[r] = v.y; pw[r] = v.z; pd[r] = 0.f;
       }
-      if (tid == 0) { s_slot3[0] = ~0ULL; s_slot3[1] = ~0ULL; s_slot3[2] = ~0ULL; }
-      __syncthreads();
       for (int c = 0; c < K; ++c) {
         unsigned bk = 0xffffffffu;
         int bi = 0x7fffffff;
@@ -990,12 +988,13 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
         }
         const unsigned wk = __reduce_min_sync(FULL_MASK, bk);
         const int wi = __reduce_min_sync(FULL_MASK, bk == wk ? bi : 0x7fffffff);
-        unsigned long long* slot = s_slot3 + c % 3;
-        if (tid == 0) s_slot3[(c + 1) % 3] = ~0ULL;            // re-arm the next round's slot
-        if (lane == 0 && wk != 0xffffffffu) atomicMin(slot, ((unsigned long long)wk << 32) | (unsigned)wi);
+        uint2* wkey = s_wkey + (c & 1) * WARPS;
+        if (lane == 0) wkey[warp] = make_uint2(wk, (unsigned)wi);
         __syncthreads();
-        const unsigned long long best = *slot;
-        const int pick = best == ~0ULL ? 0 : (int)(unsigned)best;   // all remaining mass on chosen centres: reuse seed 0
+        const uint2 e = lane < WARPS ? wkey[lane] : make_uint2(0xffffffffu, 0x7fffffffu);
+        const unsigned gk = __reduce_min_sync(FULL_MASK, e.x);
+        const unsigned gi = __reduce_min_sync(FULL_MASK, e.x == gk ? e.y : 0x7fffffffu);
+        const int pick = gk == 0xffffffffu ? 0 : (int)gi;   // all remaining mass on chosen centres: reuse seed 0
         const float4 pv = s_seed[pick];
         ccx = pv.x; ccy = pv.y;
         if (tid == 0) { s_par[8 * c + 6] = ccx; s_par[8 * c + 7] = ccy; }
