@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
 
 #ifdef STM_EMD_PROFILE
     long long c_price = 0, c_walk = 0, c_leave = 0, c_update = 0, n_scanned = 0, c_t0 = 0, sum_len = 0, sum_s = 0, sum_range = 0;
+    long long c_scan = 0, c_red = 0, n_blocks = 0, c_t1 = 0;
 #define PROF_T(x) { const long long _c = clock64(); x += _c - c_t0; c_t0 = _c; }
 #else
 #define PROF_T(x)
@@ -227,6 +228,9 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
         // The block is arcs [next_arc, next_arc + cnt) of the j-major arc order (wrapping): a few target rows,
         // each a contiguous range of sources.  Per row the target's terms stay in registers and the inner loop is
         // two shared loads, two IMADs and a compare per arc.
+#ifdef STM_EMD_PROFILE
+        c_t1 = clock64(); ++n_blocks;
+#endif
         int g_rc = INT_MAX;          // most negative reduced cost of the block (INT_MAX: none below zero)
         unsigned g_k = 0xffffffffu;  // its position in block order (ties: first in the serial scan order)
         {
@@ -243,15 +247,52 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
               sx[r] = (xy << 16) >> 16; sy[r] = xy >> 16;
               sp[r] = i < n ? s_pi[i] : INT_MAX / 2;     // never the minimum
             }
-            int j = next_arc / n;
+            // The scan only tracks the thread's minimum (an add, two IMADs and a share of a 3-input min per arc); the
+            // arc that attains the block minimum is located afterwards by the few threads whose minimum equals it.
+            const int j0 = next_arc / n;
+            int j = j0;
             for (int rr = cnt / n; rr > 0; --rr) {
               const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
 #pragma unroll
-              for (int r = 0; r < EMD_RMAX; ++r) {
-                const int rc = sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj));
-                if (rc < brc) { brc = rc; bi = tid + r * EMD_THREADS; bj_best = j; }
-              }
+              for (int r = 0; r < EMD_RMAX; ++r) brc = min(brc, sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj)));
               if (++j >= m) j = 0;
+            }
+            // ---- level 1: the block's most negative reduced cost --------------------------------------------
+            {
+              const int w_rc = __reduce_min_sync(FULL_MASK, brc);
+              int* wrc = reinterpret_cast<int*>(s_wkey + (round & 1) * EMD_WARPS);
+              if (lane == 0) wrc[warp] = w_rc;
+              __syncthreads();
+              g_rc = __reduce_min_sync(FULL_MASK, lane < EMD_WARPS ? wrc[lane] : 0);
+              ++round;
+            }
+            if (g_rc < 0) {
+              // ---- level 2: its first position in block order (rows from the block start, sources ascending) ----
+              unsigned myk = 0xffffffffu;
+              if (brc == g_rc) {
+                j = j0;
+                for (int rr = cnt / n; rr > 0 && myk == 0xffffffffu; --rr) {
+                  const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
+#pragma unroll
+                  for (int r = 0; r < EMD_RMAX; ++r) {
+                    const int rc = sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj));
+                    if (rc == g_rc && myk == 0xffffffffu) {
+                      int k = j * n + tid + r * EMD_THREADS - next_arc;
+                      if (k < 0) k += n_arcs;
+                      myk = (unsigned)k;
+                    }
+                  }
+                  if (++j >= m) j = 0;
+                }
+              }
+              const unsigned w_k = __reduce_min_sync(FULL_MASK, myk);
+              unsigned* wk = reinterpret_cast<unsigned*>(s_wkey + (round & 1) * EMD_WARPS);
+              if (lane == 0) wk[warp] = w_k;
+              __syncthreads();
+              g_k = __reduce_min_sync(FULL_MASK, lane < EMD_WARPS ? wk[lane] : 0xffffffffu);
+              ++round;
+            } else {
+              g_rc = INT_MAX;
             }
           } else {
             // general block: arcs [next_arc, next_arc + cnt) of the j-major order (wrapping) = a few target rows,
@@ -271,6 +312,10 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
               if (++j >= m) j = 0;
             }
           }
+#ifdef STM_EMD_PROFILE
+          { const long long _c = clock64(); c_scan += _c - c_t1; c_t1 = _c; }
+#endif
+          if (!whole_rows) {
           int k = 0;
           if (bi >= 0) {
             k = bj_best * n + bi - next_arc;   // position in block order decides ties, as in the serial scan
@@ -288,7 +333,11 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
           g_rc = __reduce_min_sync(FULL_MASK, e.x);
           g_k = __reduce_min_sync(FULL_MASK, e.x == g_rc ? (unsigned)e.y : 0xffffffffu);
           ++round;
+          }
         }
+#ifdef STM_EMD_PROFILE
+        { const long long _c = clock64(); c_red += _c - c_t1; c_t1 = _c; }
+#endif
         const int start = next_arc;
         scanned += cnt;
         next_arc += cnt;
@@ -426,9 +475,10 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     }
 #ifdef STM_EMD_PROFILE
     if (tid == 0 && g < 2)
-      printf("[emd prof] g=%d n=%d m=%d pivots=%lld cycles/pivot: price %.0f walk %.0f leave %.0f update %.0f | arcs scanned/pivot %.0f cycle len %.1f subtree %.1f range %.1f\n",
+      printf("[emd prof] g=%d n=%d m=%d pivots=%lld cycles/pivot: price %.0f walk %.0f leave %.0f update %.0f | arcs scanned/pivot %.0f cycle len %.1f subtree %.1f range %.1f | blocks/pivot %.2f, per block: scan %.0f reduce %.0f cycles\n",
              g, n, m, it, (double)c_price / it, (double)c_walk / it, (double)c_leave / it, (double)c_update / it,
-             (double)n_scanned / it, (double)sum_len / it, (double)sum_s / it, (double)sum_range / it);
+             (double)n_scanned / it, (double)sum_len / it, (double)sum_s / it, (double)sum_range / it,
+             (double)n_blocks / it, (double)c_scan / n_blocks, (double)c_red / n_blocks);
 #endif
     // ---- objective: real tree arcs only ------------------------------------------------------------
     double part = 0.0;
