@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
   __shared__ long long s_ll[3 * EMD_WARPS];
   __shared__ int2 s_wkey[2 * EMD_WARPS];   // per-warp (reduced cost, position) of the pricing arg-min, double-buffered
   __shared__ int s_i[16];
+  __shared__ int s_wsum[EMD_WARPS];
   __shared__ long long s_delta;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -358,20 +359,41 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
       ++it;
       const int ej = best_e / n, ei = best_e - ej * n;
       const int u_i = ei, u_j = n + ej;
-      // ---- cycle: two lanes walk the endpoints up to the join node --------------------------------
-      if (tid == 0 || tid == 32) {   // lanes of two different warps, so the two walks overlap
-        const int from = tid == 0 ? u_i : u_j, other = tid == 0 ? u_j : u_i;
-        unsigned short* path = tid == 0 ? s_pathA : s_pathB;
-        const int po = s_pos[other];
-        int len = 0, v = from;
-        while (true) {
-          const int pv = s_pos[v], sv = s_size[v], nv = s_parent[v];   // three independent loads per step
-          if (pv <= po && po < pv + sv) break;
-          if (len < EMD_MAXPATH) path[len] = (unsigned short)v;
-          ++len;
-          v = nv;
+      // ---- cycle: the two tree paths from the entering arc's endpoints up to their join node -----------------
+      // A node v is an ancestor of u iff pos[v] <= pos[u] < pos[v] + size[v].  Instead of chasing parent pointers from
+      // both endpoints (two lanes, ~180 cycles per step, everyone else waiting), every thread tests a run of consecutive
+      // PREORDER POSITIONS: path A = ancestors-or-self of u_i that are not ancestors of u_j, path B the converse; along
+      // a path the position decreases, so an ordered compaction (one block scan) yields both paths in walking order.
+      {
+        const int pu = s_pos[u_i], pw = s_pos[u_j];
+        const int per = (N + EMD_THREADS - 1) / EMD_THREADS;       // <= 32 for every problem that fits a CTA
+        const int x0 = tid * per, x1 = min(N, x0 + per);
+        unsigned mA = 0u, mB = 0u;
+        for (int x = x0; x < x1; ++x) {
+          if (x > pu && x > pw) break;                             // ancestors precede their descendants
+          const int sz = s_size[s_order[x]];
+          const bool inU = x <= pu && pu < x + sz, inW = x <= pw && pw < x + sz;
+          if (inU != inW) { if (inU) mA |= 1u << (x - x0); else mB |= 1u << (x - x0); }
         }
-        s_i[tid == 0 ? 1 : 2] = len;
+        // exclusive block scan of the two counts, packed in one word
+        const int cnt = __popc(mA) | (__popc(mB) << 16);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int wtot = lane < EMD_WARPS ? s_wsum[lane] : 0, wincl = wtot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, wincl, o); if (lane >= o) wincl += t; }
+        const int total = __shfl_sync(FULL_MASK, wincl, 31);
+        const int before = __shfl_sync(FULL_MASK, wincl - wtot, warp) + incl - cnt;
+        const int nA = total & 0xffff, nB = total >> 16;
+        if (tid == 0) { s_i[1] = nA; s_i[2] = nB; }
+        if (nA <= EMD_MAXPATH && nB <= EMD_MAXPATH) {
+          int ra = before & 0xffff, rb = before >> 16;             // rank in ascending position = distance from the join
+          for (unsigned m = mA; m; m &= m - 1) s_pathA[nA - 1 - ra++] = s_order[x0 + __ffs(m) - 1];
+          for (unsigned m = mB; m; m &= m - 1) s_pathB[nB - 1 - rb++] = s_order[x0 + __ffs(m) - 1];
+        }
       }
       __syncthreads();
       const int lenA = s_i[1], lenB = s_i[2];
