@@ -369,11 +369,21 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
         const int per = (N + EMD_THREADS - 1) / EMD_THREADS;       // <= 32 for every problem that fits a CTA
         const int x0 = tid * per, x1 = min(N, x0 + per);
         unsigned mA = 0u, mB = 0u;
-        for (int x = x0; x < x1; ++x) {
-          if (x > pu && x > pw) break;                             // ancestors precede their descendants
-          const int sz = s_size[s_order[x]];
-          const bool inU = x <= pu && pu < x + sz, inW = x <= pw && pw < x + sz;
-          if (inU != inW) { if (inU) mA |= 1u << (x - x0); else mB |= 1u << (x - x0); }
+        constexpr int PER_UNROLL = 4;                              // independent load pairs in flight
+        const int xlim = min(x1, max(pu, pw) + 1);                 // ancestors precede their descendants
+        for (int xb = x0; xb < xlim; xb += PER_UNROLL) {
+          int vv[PER_UNROLL], sz[PER_UNROLL];
+#pragma unroll
+          for (int q = 0; q < PER_UNROLL; ++q) vv[q] = xb + q < xlim ? s_order[xb + q] : root;
+#pragma unroll
+          for (int q = 0; q < PER_UNROLL; ++q) sz[q] = xb + q < xlim ? (int)s_size[vv[q]] : 0;   // 0: never an ancestor
+#pragma unroll
+          for (int q = 0; q < PER_UNROLL; ++q) {
+            const int x = xb + q;
+            const unsigned inU = (unsigned)(pu - x) < (unsigned)sz[q], inW = (unsigned)(pw - x) < (unsigned)sz[q];
+            mA |= (inU & ~inW & 1u) << ((x - x0) & 31);
+            mB |= (inW & ~inU & 1u) << ((x - x0) & 31);
+          }
         }
         // exclusive block scan of the two counts, packed in one word
         const int cnt = __popc(mA) | (__popc(mB) << 16);
