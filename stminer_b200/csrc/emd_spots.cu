@@ -366,7 +366,9 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
       // a path the position decreases, so an ordered compaction (one block scan) yields both paths in walking order.
       {
         const int pu = s_pos[u_i], pw = s_pos[u_j];
-        const int per = (N + EMD_THREADS - 1) / EMD_THREADS;       // <= 32 for every problem that fits a CTA
+        int per = (N + EMD_THREADS - 1) / EMD_THREADS;             // <= 30 for every problem that fits a CTA
+        per += (2 - per) & 3;   // per = 2 (mod 4): a lane stride of per uint16 is an odd number of 4-byte words, so the
+                                // loads of s_order[x0 + q] across a warp hit 32 different banks
         const int x0 = tid * per, x1 = min(N, x0 + per);
         unsigned mA = 0u, mB = 0u;
         constexpr int PER_UNROLL = 4;                              // independent load pairs in flight
