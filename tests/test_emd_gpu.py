@@ -88,3 +88,34 @@ def test_host_api_csr_images(cuda_device):
     assert abs(df.loc["g0", "g1"] - d01) < 1e-12
     ref34 = eo.calculate_ot_distance(imgs["g3"], imgs["g4"])
     assert abs(df.loc["g3", "g4"] - ref34) < 1e-10 * ref34
+
+
+@pytest.mark.parametrize("n,m", [(250, 200), (600, 450), (640, 640)])
+def test_emd_one_dimensional_images_deep_trees(cuda_device, n, m):
+    """Spots on a single grid line: the optimal plan is monotone and the basis trees are long chains, i.e. long cycle
+    paths — the stress case for the parallel path extraction (ordered compaction over many threads).  Same pivot count
+    and cost as the oracle; the 1-D optimum also has a closed form (monotone coupling).  (Longer lines do not fit the
+    kernel's int32 potentials: (span^2 + 1) * nodes must stay below 2^30 — status 3.)"""
+    from stminer_b200.Algorithm.distance import emd_batched
+    rng = np.random.default_rng(n)
+    span = n + n // 3
+    sx = np.sort(rng.choice(span, size=n, replace=False)).astype(np.int32)
+    tx = np.sort(rng.choice(span, size=m, replace=False)).astype(np.int32)
+    src = (sx, np.zeros(n, dtype=np.int32), rng.gamma(2.0, 1.0, n) + 0.05)
+    tgt = (tx, np.full(m, 3, dtype=np.int32), rng.gamma(2.0, 1.0, m) + 0.05)
+    cost, status, iters = emd_batched(src, [tgt], return_iters=True, block_size=4 * n)
+    c, st, it = eo.emd_network_simplex(*src, *tgt, block_size=4 * n)
+    assert status[0] == st == 0 and iters[0] == it
+    assert abs(cost[0] - c) <= 1e-12 * max(1.0, c)
+    if True:           # monotone (north-west corner) coupling of the sorted supports is optimal for a convex cost on a line
+        a, b = src[2] / src[2].sum(), tgt[2] / tgt[2].sum()
+        i = j = 0
+        ra, rb, tot = a[0], b[0], 0.0
+        while i < n and j < m:
+            f = min(ra, rb)
+            tot += f * ((int(sx[i]) - int(tx[j])) ** 2 + 9)
+            ra -= f; rb -= f
+            if ra <= 1e-18 and i < n - 1: i += 1; ra = a[i]
+            elif rb <= 1e-18 and j < m - 1: j += 1; rb = b[j]
+            else: break
+        assert abs(cost[0] - tot) <= 1e-6 * tot
