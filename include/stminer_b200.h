@@ -162,8 +162,13 @@ int stm_gmm_dist_one_vs_all(const double* qw, const double* qmu, const double* q
  *                (one problem at a time each) pull problems from a queue
  *   out_cost[G] float64 = sum_ij G_ij * M_ij;  out_iters[G] (nullable) pivots;  out_status[G]:
  *     0 optimal, 1 iteration limit reached (POT returns the current, sub-optimal value with a warning),
- *     2 empty image, 3 problem does not fit one CTA's shared memory / int16 coordinate span / int32 potentials
- *     (out_cost = NaN), 4-5 internal limits (cycle longer than 2048 arcs, unbounded ray).
+ *     2 empty image, 3 problem does not fit one CTA's shared memory / int16 coordinate span / the range of the
+ *     potentials (out_cost = NaN), 4-5 internal limits (cycle longer than 2048 arcs, unbounded ray).
+ *
+ * stm_emd_spots_batched keeps int32 potentials (18 B of shared memory per node, problems up to ~11.9k nodes); it needs
+ * 2 * (span_x^2 + span_y^2 + 1) * (n + m + 1) < 2^31 and reports status 3 otherwise.  stm_emd_spots_batched_wide is the
+ * same solver (same pivot sequence) with 64-bit potentials for problems beyond that bound — scattered integer
+ * coordinates, long thin tissues — at 22 B per node (~9.8k nodes) and a slower pricing loop.
  */
 int64_t stm_emd_workspace_bytes(int32_t n_src, int64_t max_tgt, int32_t n_ctas);
 int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
@@ -172,6 +177,12 @@ int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y, const doub
                           int64_t max_iter, int32_t block_size,
                           void* workspace, int64_t workspace_bytes, int32_t n_ctas,
                           double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream);
+int stm_emd_spots_batched_wide(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
+                               const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
+                               const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
+                               int64_t max_iter, int32_t block_size,
+                               void* workspace, int64_t workspace_bytes, int32_t n_ctas,
+                               double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream);
 
 /*
  * Metric MDS by SMACOF on a precomputed dissimilarity matrix, float64, whole iteration loop on the device.

@@ -145,25 +145,44 @@ def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, devic
         out = (np.zeros(G), np.full(G, 2, dtype=np.int32))
         return out + (np.zeros(G, dtype=np.int64),) if return_iters else out
     max_tgt = int(sizes.max())
-    order = np.argsort(-sizes, kind="stable").astype(np.int32)      # largest problems first
+    # the default kernel keeps int32 potentials: it needs 2 * (span^2 + 1) * nodes < 2^31 for the bounding box of source
+    # and target together; problems beyond that (scattered coordinates, long thin tissues) go to the 64-bit variant
+    nz = sizes > 0
+    first = ptr[:-1][nz]
+    ext = {}
+    for name, a, s0 in (("x", tx, sx), ("y", ty, sy)):
+        lo = np.full(G, int(s0.min()), dtype=np.int64); hi = np.full(G, int(s0.max()), dtype=np.int64)
+        if nz.any():
+            lo[nz] = np.minimum(lo[nz], np.minimum.reduceat(a, first)); hi[nz] = np.maximum(hi[nz], np.maximum.reduceat(a, first))
+        ext[name] = hi - lo
+    maxc = ext["x"] ** 2 + ext["y"] ** 2
+    narrow = 2 * (maxc + 1) * (len(sx) + sizes + 1) + maxc < 2 ** 31 - 1
     up = lambda a: torch.from_numpy(a).to(device)
-    d = [up(a) for a in (sx, sy, sm, ptr, tx, ty, tm, order)]
+    d = [up(a) for a in (sx, sy, sm, ptr, tx, ty, tm)]
     with torch.cuda.device(device):
         props = torch.cuda.get_device_properties(device)
-        nodes = len(sx) + max_tgt + 1
-        smem = nodes * 18 + 4 * 2048 * 2 + 64 + 1024
-        per_sm = max(1, min(8, (227 * 1024) // smem))
-        n_ctas = int(min(G, props.multi_processor_count * per_sm))
-        ws_bytes = int(lib.stm_emd_workspace_bytes(len(sx), max_tgt, n_ctas))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
         cost = torch.empty(G, dtype=torch.float64, device=device)
         status = torch.empty(G, dtype=torch.int32, device=device)
         iters = torch.empty(G, dtype=torch.int64, device=device)
-        st = lib.stm_emd_spots_batched(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), len(sx), _lib.ptr(d[3]),
-                                       _lib.ptr(d[4]), _lib.ptr(d[5]), _lib.ptr(d[6]), G, max_tgt, _lib.ptr(d[7]),
-                                       int(max_iter), int(block_size), _lib.ptr(ws), ws_bytes, n_ctas,
-                                       _lib.ptr(cost), _lib.ptr(status), _lib.ptr(iters), _lib.current_stream_ptr())
-    _lib.check(st, "stm_emd_spots_batched")
+        keep = []
+        for wide, sel in ((False, np.flatnonzero(narrow)), (True, np.flatnonzero(~narrow))):
+            if len(sel) == 0:
+                continue
+            order = sel[np.argsort(-sizes[sel], kind="stable")].astype(np.int32)      # largest problems first
+            d_order = up(order)
+            nodes = len(sx) + int(sizes[sel].max()) + 1
+            smem = nodes * (22 if wide else 18) + 4 * 2048 * 2 + 64 + 1024
+            per_sm = max(1, min(8, (227 * 1024) // smem))
+            n_ctas = int(min(len(sel), props.multi_processor_count * per_sm))
+            ws_bytes = int(lib.stm_emd_workspace_bytes(len(sx), max_tgt, n_ctas))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            fn = lib.stm_emd_spots_batched_wide if wide else lib.stm_emd_spots_batched
+            st = fn(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), len(sx), _lib.ptr(d[3]),
+                    _lib.ptr(d[4]), _lib.ptr(d[5]), _lib.ptr(d[6]), len(sel), int(sizes[sel].max()), _lib.ptr(d_order),
+                    int(max_iter), int(block_size), _lib.ptr(ws), ws_bytes, n_ctas,
+                    _lib.ptr(cost), _lib.ptr(status), _lib.ptr(iters), _lib.current_stream_ptr())
+            _lib.check(st, "stm_emd_spots_batched_wide" if wide else "stm_emd_spots_batched")
+            keep.append((d_order, ws))
     out = (cost.cpu().numpy(), status.cpu().numpy())
     return out + (iters.cpu().numpy(),) if return_iters else out
 

@@ -19,6 +19,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "stm_common.cuh"
 
@@ -106,9 +107,14 @@ __global__ void __launch_bounds__(EMD_PREP_THREADS) emd_prep_kernel(const double
   integerize<EMD_PREP_THREADS>(src_mass, n, src_int, s_scr, s_ll);
 }
 
-template <int EMD_THREADS>
+// WIDE = 64-bit potentials and reduced costs for problems whose coordinate span makes (span^2 + 1) * nodes exceed the
+// int32 range of the default kernel (scattered integer coordinates, long thin tissues): 22 instead of 18 bytes of shared
+// memory per node and the general (non register-resident) pricing path, same pivot sequence.
+template <int EMD_THREADS, bool WIDE>
 __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
   constexpr int EMD_WARPS = EMD_THREADS / 32;
+  using pi_t = typename std::conditional<WIDE, long long, int>::type;
+  constexpr pi_t PI_NONE = WIDE ? (pi_t)LLONG_MAX : (pi_t)INT_MAX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap = p.cap_nodes;
   // s_pi holds ADJUSTED potentials: pi_i + |x_i|^2 for sources, pi_j - |x_j|^2 for sinks, so that the reduced
@@ -119,8 +125,8 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
   // shared-memory instead of L2 latency
   const int fcap = p.flow_smem_nodes;
   long long* s_flow = reinterpret_cast<long long*>(smem_raw);           // [fcap]
-  int* s_pi = reinterpret_cast<int*>(s_flow + fcap);                     // [cap]
-  int* s_xy = s_pi + cap;                                                // [cap] {int16 x | int16 y}
+  pi_t* s_pi = reinterpret_cast<pi_t*>(s_flow + fcap);                   // [cap]
+  int* s_xy = reinterpret_cast<int*>(s_pi + cap);                        // [cap] {int16 x | int16 y}
   unsigned short* s_parent = reinterpret_cast<unsigned short*>(s_xy + cap);
   unsigned short* s_pos = s_parent + cap;
   unsigned short* s_size = s_pos + cap;
@@ -135,6 +141,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
   __shared__ int2 s_wkey[2 * EMD_WARPS];   // per-warp (reduced cost, position) of the pricing arg-min, double-buffered
   __shared__ int s_i[16];
   __shared__ int s_wsum[EMD_WARPS];
+  __shared__ long long s_wrc64[WIDE ? 2 * EMD_WARPS : 1];   // per-warp reduced costs of the WIDE pricing arg-min
   __shared__ long long s_delta;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -177,7 +184,8 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     const long long maxc = (long long)(xmax - xmin) * (xmax - xmin) + (long long)(ymax - ymin) * (ymax - ymin);
     const long long BIG = (maxc + 1) * (long long)N;
     const bool coords_ok = (xmax - ox) < 32768 && (ox - xmin) < 32768 && (ymax - oy) < 32768 && (oy - ymin) < 32768;
-    if (!fits || !coords_ok || 2 * BIG + maxc >= 2147483647LL) {   // int32 potentials / int16 coordinates / capacity
+    const long long pi_limit = WIDE ? (1LL << 61) : 2147483647LL;
+    if (!fits || !coords_ok || 2 * BIG + maxc >= pi_limit) {   // range of the potentials / int16 coordinates / capacity
       if (tid == 0) { p.out_cost[g] = nan(""); p.out_status[g] = 3; if (p.out_iters) p.out_iters[g] = 0; }
       continue;
     }
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     for (int v = tid; v < n + m; v += EMD_THREADS) {
       s_parent[v] = (unsigned short)root; s_order[v + 1] = (unsigned short)v; s_pos[v] = (unsigned short)(v + 1);
       const int xy = s_xy[v], xr = (xy << 16) >> 16, yr = xy >> 16, r2 = xr * xr + yr * yr;
-      s_size[v] = 1; s_pi[v] = v < n ? (int)-BIG + r2 : (int)BIG - r2;
+      s_size[v] = 1; s_pi[v] = v < n ? (pi_t)(-BIG + r2) : (pi_t)(BIG - r2);
     }
     if (tid == 0) {
       s_order[0] = (unsigned short)root; s_pos[root] = 0; s_size[root] = (unsigned short)N; s_parent[root] = NONE16;
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     if (p.block_size <= 0 && n <= EMD_RMAX * EMD_THREADS) B = max(1, (B + n / 2) / n) * n;   // whole target rows
     if (B < 10) B = 10;
     if (B > n_arcs) B = n_arcs;
-    const bool whole_rows = B % n == 0 && n <= EMD_RMAX * EMD_THREADS;   // n_arcs and every block start are multiples of n
+    const bool whole_rows = !WIDE && B % n == 0 && n <= EMD_RMAX * EMD_THREADS;   // n_arcs and every block start are multiples of n
     int next_arc = 0;
     long long it = 0;
     int status = 0;
@@ -223,7 +231,8 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
       c_t0 = clock64();
 #endif
       // ---- entering arc: block search over arcs e = j*n + i ----------------------------------------
-      int scanned = 0, best_e = -1, best_rc = 0;
+      int scanned = 0, best_e = -1;
+      pi_t best_rc = 0;
       while (scanned < n_arcs) {
         const int cnt = min(B, n_arcs - scanned);
         // The block is arcs [next_arc, next_arc + cnt) of the j-major arc order (wrapping): a few target rows,
@@ -232,11 +241,15 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
 #ifdef STM_EMD_PROFILE
         c_t1 = clock64(); ++n_blocks;
 #endif
-        int g_rc = INT_MAX;          // most negative reduced cost of the block (INT_MAX: none below zero)
+        pi_t g_rc = PI_NONE;         // most negative reduced cost of the block (PI_NONE: none below zero)
         unsigned g_k = 0xffffffffu;  // its position in block order (ties: first in the serial scan order)
         {
-          int brc = 0, bi = -1, bj_best = 0;
+          pi_t brc = 0;
+          int bi = -1, bj_best = 0;
+          bool fast_done = false;
+          if constexpr (!WIDE) {
           if (whole_rows) {
+            fast_done = true;
             // Fast path (the default block size is a whole number of target rows): every thread keeps ITS sources'
             // terms in registers for the whole block and meets each target row with no shared-memory traffic
             // beyond the row's three broadcast words — six integer instructions per arc.
@@ -293,19 +306,22 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
               g_k = __reduce_min_sync(FULL_MASK, lane < EMD_WARPS ? wk[lane] : 0xffffffffu);
               ++round;
             } else {
-              g_rc = INT_MAX;
+              g_rc = PI_NONE;
             }
-          } else {
+          }
+          }
+          if (!fast_done) {
             // general block: arcs [next_arc, next_arc + cnt) of the j-major order (wrapping) = a few target rows,
             // each a contiguous range of sources
             int left = cnt;
             int j = next_arc / n, lo = next_arc - j * n;
             while (left > 0) {
               const int hi = min(n, lo + left);
-              const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
+              const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16);
+              const pi_t bj = s_pi[n + j];
               for (int i = lo + tid; i < hi; i += EMD_THREADS) {
                 const int xy = s_xy[i];
-                const int rc = ((xy << 16) >> 16) * nx2 + ((xy >> 16) * ny2 + (s_pi[i] - bj));
+                const pi_t rc = (pi_t)((xy << 16) >> 16) * nx2 + ((pi_t)(xy >> 16) * ny2 + (s_pi[i] - bj));
                 if (rc < brc) { brc = rc; bi = i; bj_best = j; }
               }
               left -= hi - lo;
@@ -316,7 +332,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
 #ifdef STM_EMD_PROFILE
           { const long long _c = clock64(); c_scan += _c - c_t1; c_t1 = _c; }
 #endif
-          if (!whole_rows) {
+          if (!fast_done) {
           int k = 0;
           if (bi >= 0) {
             k = bj_best * n + bi - next_arc;   // position in block order decides ties, as in the serial scan
@@ -325,14 +341,38 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
           // lexicographic (reduced cost, position) minimum in two 32-bit REDUX steps per level: over the warp, then —
           // through one shared entry per warp, double-buffered, one barrier — over the CTA.  (A 64-bit shared
           // atomicMin is a CAS loop: 32 warps contending on one slot cost several thousand cycles per block.)
-          const int w_rc = __reduce_min_sync(FULL_MASK, bi >= 0 ? brc : INT_MAX);
-          const unsigned w_k = __reduce_min_sync(FULL_MASK, (bi >= 0 && brc == w_rc) ? (unsigned)k : 0xffffffffu);
-          int2* wkey = s_wkey + (round & 1) * EMD_WARPS;
-          if (lane == 0) wkey[warp] = make_int2(w_rc, (int)w_k);
-          __syncthreads();
-          const int2 e = lane < EMD_WARPS ? wkey[lane] : make_int2(INT_MAX, -1);
-          g_rc = __reduce_min_sync(FULL_MASK, e.x);
-          g_k = __reduce_min_sync(FULL_MASK, e.x == g_rc ? (unsigned)e.y : 0xffffffffu);
+          if constexpr (!WIDE) {
+            const int w_rc = __reduce_min_sync(FULL_MASK, bi >= 0 ? brc : INT_MAX);
+            const unsigned w_k = __reduce_min_sync(FULL_MASK, (bi >= 0 && brc == w_rc) ? (unsigned)k : 0xffffffffu);
+            int2* wkey = s_wkey + (round & 1) * EMD_WARPS;
+            if (lane == 0) wkey[warp] = make_int2(w_rc, (int)w_k);
+            __syncthreads();
+            const int2 e = lane < EMD_WARPS ? wkey[lane] : make_int2(INT_MAX, -1);
+            g_rc = __reduce_min_sync(FULL_MASK, e.x);
+            g_k = __reduce_min_sync(FULL_MASK, e.x == g_rc ? (unsigned)e.y : 0xffffffffu);
+          } else {
+            // 64-bit reduced costs: lexicographic (rc, position) minimum by shuffles, over the warp and then over the
+            // per-warp entries
+            long long r64 = bi >= 0 ? (long long)brc : LLONG_MAX;
+            unsigned k32 = bi >= 0 ? (unsigned)k : 0xffffffffu;
+            for (int o = 16; o > 0; o >>= 1) {
+              const long long orc = shfl_xor_ll(r64, o);
+              const unsigned ok = __shfl_xor_sync(FULL_MASK, k32, o);
+              if (orc < r64 || (orc == r64 && ok < k32)) { r64 = orc; k32 = ok; }
+            }
+            long long* wr = s_wrc64 + (round & 1) * EMD_WARPS;
+            unsigned* wk = reinterpret_cast<unsigned*>(s_wkey + (round & 1) * EMD_WARPS);
+            if (lane == 0) { wr[warp] = r64; wk[warp] = k32; }
+            __syncthreads();
+            r64 = lane < EMD_WARPS ? wr[lane] : LLONG_MAX;
+            k32 = lane < EMD_WARPS ? wk[lane] : 0xffffffffu;
+            for (int o = 16; o > 0; o >>= 1) {
+              const long long orc = shfl_xor_ll(r64, o);
+              const unsigned ok = __shfl_xor_sync(FULL_MASK, k32, o);
+              if (orc < r64 || (orc == r64 && ok < k32)) { r64 = orc; k32 = ok; }
+            }
+            g_rc = (pi_t)r64; g_k = k32;
+          }
           ++round;
           }
         }
@@ -446,7 +486,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
       const int s = s_size[q], a0 = s_pos[q];
       const int pt = s_pos[t_in];
       const int ptr = pt < a0 ? pt : pt - s;
-      const int shift = side == 0 ? -best_rc : best_rc;
+      const pi_t shift = side == 0 ? -best_rc : best_rc;
       // ---- flow update along the cycle + old flows / positions / sizes of the reversed path --------
       for (int a = tid; a < lenA; a += EMD_THREADS) { const int v = s_pathA[a]; FL(v) += (v < n) ? -delta : delta; }
       for (int b = tid; b < lenB; b += EMD_THREADS) { const int v = s_pathB[b]; FL(v) += (v >= n) ? -delta : delta; }
@@ -535,8 +575,9 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
   }
 }
 
-inline size_t emd_smem_bytes(int64_t cap_nodes, int64_t flow_nodes = 0) {
-  return (size_t)flow_nodes * 8 + (size_t)cap_nodes * (4 + 2 + 2 + 5 * 2) + 4 * (size_t)EMD_MAXPATH * 2 + 64;
+inline size_t emd_node_bytes(bool wide) { return (wide ? 8 : 4) + 4 + 5 * 2; }   // potential, packed xy, five uint16 tree arrays
+inline size_t emd_smem_bytes(int64_t cap_nodes, int64_t flow_nodes = 0, bool wide = false) {
+  return (size_t)flow_nodes * 8 + (size_t)cap_nodes * emd_node_bytes(wide) + 4 * (size_t)EMD_MAXPATH * 2 + 64;
 }
 inline int64_t emd_ws_cap(int64_t n_src, int64_t max_tgt) { return (n_src + max_tgt + 1 + 7) & ~7LL; }
 
@@ -548,13 +589,14 @@ extern "C" int64_t stm_emd_workspace_bytes(int32_t n_src, int64_t max_tgt, int32
   return 256 + (int64_t)n_src * 8 + (int64_t)n_ctas * stm::emd_ws_cap(n_src, max_tgt) * 8 + 256;
 }
 
-extern "C" int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
-                                     const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
-                                     const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
-                                     int64_t max_iter, int32_t block_size,
-                                     void* workspace, int64_t workspace_bytes, int32_t n_ctas,
-                                     double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream) {
-  using namespace stm;
+namespace stm {
+namespace {
+int emd_launch(bool wide, const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
+               const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
+               const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
+               int64_t max_iter, int32_t block_size,
+               void* workspace, int64_t workspace_bytes, int32_t n_ctas,
+               double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream) {
   STM_CHECK_ARG(G >= 0, "G < 0");
   if (G == 0) return STM_OK;
   STM_CHECK_ARG(n_src > 0 && src_x && src_y && src_mass, "empty or null source image");
@@ -567,7 +609,7 @@ extern "C" int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y,
   STM_CHECK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   // node capacity of one CTA: the whole tree lives in shared memory; larger problems get status 3
   int64_t cap = emd_ws_cap(n_src, max_tgt);
-  const int64_t max_cap = (((int64_t)max_optin - 4096 - (int64_t)emd_smem_bytes(0)) / 18) & ~7LL;   // static smem + 1 KB reserve
+  const int64_t max_cap = (((int64_t)max_optin - 4096 - (int64_t)emd_smem_bytes(0)) / (int64_t)emd_node_bytes(wide)) & ~7LL;   // static smem + reserve
   if (cap > max_cap) cap = max_cap;
   char* ws = static_cast<char*>(workspace);
   EmdArgs a{};
@@ -582,7 +624,7 @@ extern "C" int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y,
   STM_CHECK_CUDA(cudaMemsetAsync(a.counter, 0, 256, st));
   emd_prep_kernel<<<1, EMD_PREP_THREADS, 0, st>>>(src_mass, n_src, a.src_int);
   STM_CHECK_CUDA(cudaGetLastError());
-  const size_t tree_smem = emd_smem_bytes((int)cap);
+  const size_t tree_smem = emd_smem_bytes((int)cap, 0, wide);
   const int grid = n_ctas < G ? n_ctas : G;
   // Problems that leave room for only one CTA per SM get 1,024 threads (pricing is the dominant phase and
   // scales with the thread count); small problems run several 256-thread CTAs per SM.
@@ -593,14 +635,35 @@ extern "C" int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y,
   int64_t fcap = (share - (int64_t)tree_smem) / 8;
   fcap = std::max<int64_t>(0, std::min<int64_t>(fcap, cap)) & ~1LL;
   a.flow_smem_nodes = (int32_t)fcap;
-  const size_t smem = emd_smem_bytes((int)cap, fcap);
-  if (one_per_sm) {
-    STM_CHECK_CUDA(cudaFuncSetAttribute(emd_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    emd_kernel<1024><<<grid, 1024, smem, st>>>(a);
-  } else {
-    STM_CHECK_CUDA(cudaFuncSetAttribute(emd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    emd_kernel<256><<<grid, 256, smem, st>>>(a);
-  }
-  STM_CHECK_CUDA(cudaGetLastError());
-  return STM_OK;
+  const size_t smem = emd_smem_bytes((int)cap, fcap, wide);
+  auto launch = [&](auto kern, int threads) -> int {
+    STM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, st>>>(a);
+    STM_CHECK_CUDA(cudaGetLastError());
+    return STM_OK;
+  };
+  if (one_per_sm) return wide ? launch(emd_kernel<1024, true>, 1024) : launch(emd_kernel<1024, false>, 1024);
+  return wide ? launch(emd_kernel<256, true>, 256) : launch(emd_kernel<256, false>, 256);
+}
+}  // namespace
+}  // namespace stm
+
+extern "C" int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
+                                     const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
+                                     const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
+                                     int64_t max_iter, int32_t block_size,
+                                     void* workspace, int64_t workspace_bytes, int32_t n_ctas,
+                                     double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream) {
+  return stm::emd_launch(false, src_x, src_y, src_mass, n_src, tgt_ptr, tgt_x, tgt_y, tgt_mass, G, max_tgt, order, max_iter,
+                         block_size, workspace, workspace_bytes, n_ctas, out_cost, out_status, out_iters, stream);
+}
+
+extern "C" int stm_emd_spots_batched_wide(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
+                                          const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
+                                          const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
+                                          int64_t max_iter, int32_t block_size,
+                                          void* workspace, int64_t workspace_bytes, int32_t n_ctas,
+                                          double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream) {
+  return stm::emd_launch(true, src_x, src_y, src_mass, n_src, tgt_ptr, tgt_x, tgt_y, tgt_mass, G, max_tgt, order, max_iter,
+                         block_size, workspace, workspace_bytes, n_ctas, out_cost, out_status, out_iters, stream);
 }

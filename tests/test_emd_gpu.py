@@ -90,12 +90,12 @@ def test_host_api_csr_images(cuda_device):
     assert abs(df.loc["g3", "g4"] - ref34) < 1e-10 * ref34
 
 
-@pytest.mark.parametrize("n,m", [(250, 200), (600, 450), (640, 640)])
+@pytest.mark.parametrize("n,m", [(250, 200), (600, 450), (640, 640), (2500, 1900), (5000, 3000)])
 def test_emd_one_dimensional_images_deep_trees(cuda_device, n, m):
     """Spots on a single grid line: the optimal plan is monotone and the basis trees are long chains, i.e. long cycle
     paths — the stress case for the parallel path extraction (ordered compaction over many threads).  Same pivot count
-    and cost as the oracle; the 1-D optimum also has a closed form (monotone coupling).  (Longer lines do not fit the
-    kernel's int32 potentials: (span^2 + 1) * nodes must stay below 2^30 — status 3.)"""
+    and cost as the oracle; the 1-D optimum also has a closed form (monotone coupling).  The two longest lines exceed
+    the int32 potentials of the default kernel ((span^2 + 1) * nodes >= 2^30) and run on the 64-bit variant."""
     from stminer_b200.Algorithm.distance import emd_batched
     rng = np.random.default_rng(n)
     span = n + n // 3
@@ -119,3 +119,20 @@ def test_emd_one_dimensional_images_deep_trees(cuda_device, n, m):
             elif rb <= 1e-18 and j < m - 1: j += 1; rb = b[j]
             else: break
         assert abs(cost[0] - tot) <= 1e-6 * tot
+
+
+def test_emd_batch_mixes_int32_and_64bit_problems(cuda_device):
+    """One launch request whose targets need different potential widths: a target far away from the source makes
+    (span^2 + 1) * nodes overflow int32, so the host routes it to stm_emd_spots_batched_wide; results stay in target
+    order and both match the oracle (cost and pivot count)."""
+    from stminer_b200.Algorithm.distance import emd_batched
+    rng = np.random.default_rng(9)
+    src, tg = _random_problem(rng, 300, [200, 150, 260], 40)
+    far = (tg[1][0] + 3000, tg[1][1] + 1700, tg[1][2])
+    targets = [tg[0], far, tg[2]]
+    cost, status, iters = emd_batched(src, targets, block_size=500, return_iters=True)
+    for g, t in enumerate(targets):
+        c, st, it = eo.emd_network_simplex(*src, *t, block_size=500)
+        assert status[g] == st == 0 and iters[g] == it, g
+        assert abs(cost[g] - c) <= 1e-12 * max(1.0, c)
+    assert cost[1] > 1e6 > cost[0]
