@@ -19,7 +19,8 @@
  *   - the tree is kept as parent / preorder-position / subtree-size arrays (a subtree is a contiguous
  *     segment of the preorder array), which is what makes the tree update data-parallel on the GPU.
  *
- * Pinning: the reference holds no golden value for this path that is usable here (its only pin is the top-2
+ * Pinning — PARITY UNPINNED against the reference itself: POT cannot be imported here and the reference holds no golden
+ * value for this path that is usable here (its only pin is the top-2
  * gene ranking on the missing tests/data/test.h5ad, tests/test_STMiner.py:48-49).  The oracle is pinned
  * against an independent exact LP solve (scipy.optimize.linprog, HiGHS) on small problems in
  * tests/test_oracle_emd.py, and against committed golden values tests/golden/emd_small.npz made the same way.

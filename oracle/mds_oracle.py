@@ -15,6 +15,10 @@ rule and different ``MDS`` defaults.  So the published 1.3.0 algorithm is restat
         start ``random_state.uniform(size=n*d)`` from the SAME RandomState (global numpy state for random_state=None,
         smacof() serial branch), best final stress wins; max_iter=300, eps=1e-3.
 
+Pinning: rule 1 is checked against the real scikit-learn of this image (tests/test_oracle_mds.py) — the same Guttman
+update the pinned version runs; the stopping rule and restart scheme of 1.3.0 (rule 0, ``mds_fit``) are restated from the
+published source and cannot be run here: PARITY UNPINNED for the iteration at which rule 0 stops.
+
 Only ``tests/`` and the CPU legs of ``bench.py`` may import this module.
 """
 from __future__ import annotations
