@@ -136,3 +136,19 @@ def test_emd_batch_mixes_int32_and_64bit_problems(cuda_device):
         assert status[g] == st == 0 and iters[g] == it, g
         assert abs(cost[g] - c) <= 1e-12 * max(1.0, c)
     assert cost[1] > 1e6 > cost[0]
+
+
+def test_emd_one_cta_per_sm_kernel_matches_oracle(cuda_device):
+    """A problem large enough for the 1,024-thread kernel (one CTA per SM) with int32 potentials and the register-
+    resident whole-row pricing path: cost AND pivot count of the oracle at the same block size (9 target rows)."""
+    from stminer_b200.Algorithm.distance import emd_batched
+    rng = np.random.default_rng(11)
+    n, m, R = 3600, 2200, 60
+    src, tg = _random_problem(rng, n, [m], R)
+    B = 9 * n
+    cost, status, iters = emd_batched(src, tg, block_size=B, return_iters=True)
+    c, st, it = eo.emd_network_simplex(*src, *tg[0], block_size=B)
+    assert status[0] == st == 0 and iters[0] == it
+    assert abs(cost[0] - c) <= 1e-12 * max(1.0, c)
+    cost_d, status_d = emd_batched(src, tg)                       # the kernel's own default block size: same optimum
+    assert status_d[0] == 0 and abs(cost_d[0] - c) <= 1e-12 * max(1.0, c)
