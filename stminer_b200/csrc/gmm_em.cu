@@ -57,6 +57,9 @@ constexpr int KM_LMAX = 6;                // greedy k-means++ candidates: 2 + fl
 #ifndef STM_EM_MAGIC_I2F
 #define STM_EM_MAGIC_I2F 0    // int16 -> float by magic-number add instead of I2F (XU pipe)
 #endif
+#ifndef STM_EM_L2_PREFETCH
+#define STM_EM_L2_PREFETCH 0  // prefetch a later gene's column into L2 during the EM loop
+#endif
 #ifndef STM_EM_T_LARGE
 #define STM_EM_T_LARGE 512    // CTA size of the one-CTA large bucket (1 CTA per SM)
 #endif
@@ -1149,6 +1152,26 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
   __syncthreads();
 
   EM_PROF(pf_assign)
+#if STM_EM_L2_PREFETCH
+  // While this gene iterates, pull the column of a gene that will start about one wave of CTAs later into L2, so its
+  // prologue (bound by the latency of its first loads) finds the data on chip.
+  if constexpr (!CL) {
+    const int ahead = slot + (int)gridDim.x / 8 + 148;
+    if (ahead < p.order_begin + (int)gridDim.x) {
+      const int ga = p.gene_order ? p.gene_order[ahead] : ahead;
+      const int64_t q0 = p.col_ptr[ga], q1 = p.col_ptr[ga + 1];
+      const char* r0 = compact ? reinterpret_cast<const char*>(reinterpret_cast<const unsigned short*>(p.row_idx) + q0)
+                               : reinterpret_cast<const char*>(p.row_idx + q0);
+      const char* v0 = compact ? reinterpret_cast<const char*>(reinterpret_cast<const short*>(p.val) + q0)
+                               : reinterpret_cast<const char*>(p.val + q0);
+      const int64_t bytes = (q1 - q0) * (compact ? 2 : 4);
+      for (int64_t o = (int64_t)tid * 128; o < bytes; o += (int64_t)T * 128) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(v0 + o));
+      }
+    }
+  }
+#endif
   // ---- EM loop (sklearn mixture/_base.py:265-278) ---------------------------------------------
   double lb_prev = -INFINITY, lb = 0.0;
   int n_iter = 0, converged = 0;
