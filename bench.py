@@ -439,6 +439,34 @@ def run_ours(args, rank, world, local_rank):
         cpu = CpuReference(cores)
         rate, wall, mean_fit, n = cpu.rate(sm, n_sample)
         cpu.close()
+        # the other two stages of the path, on bounded samples, one core each (the reference runs them serially)
+        try:
+            from oracle import dist_oracle as do
+            Wh, MUh, COVh = host["weights"][sel], host["means"][sel], host["covariances"][sel]
+            do.distribution_distance(Wh[0], MUh[0], COVh[0], Wh[1], MUh[1], COVh[1])          # numba compile
+            n_p = 24
+            t_c = time.perf_counter()
+            for q in range(n_p):
+                do.distribution_distance(Wh[q], MUh[q], COVh[q], Wh[q + 1], MUh[q + 1], COVh[q + 1])
+            t_c = time.perf_counter() - t_c
+            line["pairs"]["cpu_pairs_per_sec_1_core"] = n_p / t_c
+            line["pairs"]["cpu_note"] = ("reference arithmetic (K^2 njit Hellinger calls + scipy LSAP per pair, "
+                                         "distance.py:13-36) on %d pairs, one core" % n_p)
+        except Exception as e:        # pragma: no cover
+            line["pairs"]["cpu_note"] = "cpu sample failed: %r" % (e,)
+        if emd is not None:
+            try:
+                from oracle import emd_oracle as eo
+                small = min(range(len(tg)), key=lambda i: len(tg[i][0]))
+                t_c = time.perf_counter()
+                c_cpu, st_cpu, it_cpu = eo.emd_network_simplex(*src, *tg[small])
+                t_c = time.perf_counter() - t_c
+                emd["cpu_seconds_per_problem_1_core"] = t_c
+                emd["cpu_note"] = ("C restatement of the network simplex (POT is not installable here) on the smallest "
+                                   "problem of the batch (%d target spots, %d pivots), one core; GPU cost agrees to %.1e"
+                                   % (len(tg[small][0]), it_cpu, abs(c_cpu - float(ecost[small])) / max(1.0, abs(c_cpu))))
+            except Exception as e:    # pragma: no cover
+                emd["cpu_note"] = "cpu sample failed: %r" % (e,)
         line["cpu_baseline"] = {"value": rate, "unit": "genes/s", "cores": cores, "kind": "port",
                                 "sample": "%d random genes of the same data set, reference path (array_to_list + "
                                           "sklearn GaussianMixture.fit, KMeans init included), process-per-gene "
