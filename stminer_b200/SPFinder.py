@@ -288,19 +288,17 @@ class SPFinder:
         cells where at least ``vote_rate`` of the genes are expressed are kept."""
         sm = spot_matrix_from_adata(self.adata, gene_list)
         shape = (int(np.asarray(self.adata.obs["x"]).max()) + 1, int(np.asarray(self.adata.obs["y"]).max()) + 1)
-        total_count = np.zeros(shape)
-        votes = np.zeros(shape)
-        for g in range(sm.n_genes):
-            a, b = int(sm.col_ptr[g]), int(sm.col_ptr[g + 1])
-            r = sm.row_idx[a:b]
-            w = np.trunc(sm.val[a:b])
-            # AlgUtils.py:8-36 keeps negative cells in the grid; nonzero cells vote (np.nonzero, SPFinder.py:471)
-            nz = w != 0
-            xs, ys, w = sm.spot_x[r][nz], sm.spot_y[r][nz], w[nz]
-            s = w.sum()
-            if s != 0:
-                np.add.at(total_count, (xs, ys), w * (100 / s))
-            votes[xs, ys] += 1
+        # all genes at once on the CSC staging (one bincount per quantity instead of a Python loop over genes)
+        w = np.trunc(np.asarray(sm.val, dtype=np.float64))
+        # AlgUtils.py:8-36 keeps negative cells in the grid; nonzero cells vote (np.nonzero, SPFinder.py:471)
+        nz = w != 0
+        gene_of = np.repeat(np.arange(sm.n_genes), np.diff(sm.col_ptr))
+        sums = np.bincount(gene_of, weights=w, minlength=sm.n_genes)               # scale_array: 100 / sum, 0 if sum == 0
+        scale = np.divide(100.0, sums, out=np.zeros_like(sums), where=sums != 0)
+        cell = sm.spot_x[sm.row_idx].astype(np.int64) * shape[1] + sm.spot_y[sm.row_idx]
+        n_cells = shape[0] * shape[1]
+        total_count = np.bincount(cell[nz], weights=(w * scale[gene_of])[nz], minlength=n_cells).reshape(shape)
+        votes = np.bincount(cell[nz], minlength=n_cells).reshape(shape).astype(np.float64)
         vote_array = (votes > 0) & (votes / len(gene_list) >= vote_rate)
         total_count *= vote_array
         binary_arr = np.where(total_count != 0, 1, total_count)
