@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import logging
 from collections import Counter
+from collections.abc import Mapping
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -38,6 +39,66 @@ def scale_array(exp_matrix: np.ndarray, total_count: np.ndarray) -> np.ndarray:
     if total_sum == 0:
         return np.zeros_like(total_count)
     return exp_matrix * (100 / total_sum)
+
+
+class GeneImageDict(Mapping):
+    """``csr_dict`` of the reference — gene -> sparse (x, y) image (SPFinder.py:178-249) — built lazily.
+
+    The staging keeps ONE CSC matrix of the selected genes (values already clipped at the ``vmax`` percentile) and
+    the spot coordinates; ``d[gene]`` materialises the same ``csr_matrix((column, (x, y)))`` the reference stores
+    (cached), while the SVG ranking reads every gene's support straight from the CSC columns (``supports``)
+    instead of creating and re-parsing thousands of scipy objects."""
+
+    def __init__(self, genes, columns_csc, x, y):
+        self._genes = list(genes)
+        self._index = {g: i for i, g in enumerate(self._genes)}
+        self._M = columns_csc            # (n_obs, n_genes) CSC, float64, clipped
+        self._x = np.asarray(x).astype(np.int64)
+        self._y = np.asarray(y).astype(np.int64)
+        self._cache = {}
+
+    def __len__(self):
+        return len(self._genes)
+
+    def __iter__(self):
+        return iter(self._genes)
+
+    def __contains__(self, gene):
+        return gene in self._index
+
+    def __getitem__(self, gene):
+        if gene not in self._cache:
+            j = self._index[gene]
+            data = np.asarray(self._M[:, j].todense()).ravel()
+            self._cache[gene] = csr_matrix((data, (self._x, self._y)))      # SPFinder.py:244 (explicit zeros kept)
+        return self._cache[gene]
+
+    def supports(self, genes=None):
+        """``[(x, y, mass)]`` of the positive cells of every gene image, as ``csr_to_support(d[gene])`` returns them
+        (duplicate (x, y) rows summed, row-major order)."""
+        genes = self._genes if genes is None else list(genes)
+        ymul = int(self._y.max()) + 1
+        cell = self._x * ymul + self._y
+        uniq, inv = np.unique(cell, return_inverse=True)
+        merge = len(uniq) != len(cell)
+        out = []
+        M = self._M
+        for g in genes:
+            j = self._index[g]
+            a, b = M.indptr[j], M.indptr[j + 1]
+            r, v = M.indices[a:b], M.data[a:b]
+            if merge:                                         # rows sharing a cell are summed by the csr constructor
+                c = inv[r]
+                s = np.bincount(c, weights=v, minlength=len(uniq))
+                keep = np.flatnonzero(s > 0)
+                cc, vv = uniq[keep], s[keep]
+            else:
+                keep = v > 0
+                cc, vv = cell[r[keep]], v[keep]
+                o = np.argsort(cc, kind="stable")
+                cc, vv = cc[o], vv[o]
+            out.append(((cc // ymul).astype(np.int32), (cc % ymul).astype(np.int32), vv.astype(np.float64)))
+        return out
 
 
 def _n_nonzero(X, axis):
@@ -172,26 +233,29 @@ class SPFinder:
             first.setdefault(n, i)
         x = np.asarray(self.adata.obs["x"].values).ravel()
         y = np.asarray(self.adata.obs["y"].values).ravel()
-        Xc = self.adata.X.tocsc() if sparse.issparse(self.adata.X) else None
-        warned = set()
+        Xc = (self.adata.X.tocsc() if sparse.issparse(self.adata.X) else sparse.csc_matrix(np.asarray(self.adata.X)))
+        Xc = Xc.astype(np.float64)
+        warned, seen, keep_genes, keep_cols = set(), set(), [], []
         for gene in arr_list:
             if counts.get(gene, 0) != 1:           # SPFinder.py:225-234 (duplicates) / KeyError on unknown genes
                 if gene not in warned:
                     warned.add(gene)
                     logger.warning("Gene [%s] has more than one index, skip.", gene)
                 continue
-            try:
-                j = first[gene]
-                if Xc is not None:
-                    data = np.asarray(Xc[:, j].todense()).ravel().astype(np.float64)
-                else:
-                    data = np.asarray(self.adata.X[:, j], dtype=np.float64).ravel().copy()
-                p = np.percentile(data, vmax)
+            if gene not in seen:
+                seen.add(gene); keep_genes.append(gene); keep_cols.append(first[gene])
+        M = Xc[:, keep_cols].tocsc(copy=True)
+        M.sort_indices()
+        if vmax < 100:                                # clip at the percentile over ALL spots, zeros included, if it is > 0
+            n_obs = M.shape[0]
+            for j in range(M.shape[1]):
+                a, b = M.indptr[j], M.indptr[j + 1]
+                col = np.zeros(n_obs); col[:b - a] = M.data[a:b]
+                p = np.percentile(col, vmax)
                 if p > 0:
-                    data[data > p] = p
-                self.csr_dict[gene] = csr_matrix((data, (x, y)))
-            except Exception:
-                logger.error("Error when parsing gene %s.", gene, exc_info=True)
+                    np.minimum(M.data[a:b], p, out=M.data[a:b])
+        # vmax = 100: the percentile is the column maximum and the clip is the identity
+        self.csr_dict = GeneImageDict(keep_genes, M, x, y)
 
     def spatial_high_variable_genes(self, vmax: float = 100.0, thread: int = 1) -> None:
         """SPFinder.py:251-326: exact EMD between the per-spot total image and every gene image, then
@@ -205,7 +269,12 @@ class SPFinder:
         column_indices = np.array(self.adata.obs["y"].values).flatten()
         global_matrix = csr_matrix((data, (row_indices, column_indices)))
         keys = list(self.csr_dict.keys())
-        dist, status = ot_distances_to_source(global_matrix, [self.csr_dict[k] for k in keys], device=self.device)
+        if isinstance(self.csr_dict, GeneImageDict):          # supports straight from the staged CSC columns
+            from .Algorithm.distance import csr_to_support
+            from .sharding import emd_sharded
+            dist, status = emd_sharded(csr_to_support(global_matrix), self.csr_dict.supports(keys), device=self.device)
+        else:
+            dist, status = ot_distances_to_source(global_matrix, [self.csr_dict[k] for k in keys], device=self.device)
         distance_dict = {}
         for k, d, s in zip(keys, dist, status):
             if s == 2:                                # empty image: POT raises, the reference logs and skips

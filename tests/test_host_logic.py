@@ -142,3 +142,22 @@ def test_genes_to_pattern_vote():
         sp.get_pattern_array(mode="nope")
     with pytest.raises(ValueError, match="Unknown method"):
         sp.build_distance_array(method="nope")
+
+
+@pytest.mark.parametrize("n_obs,vmax", [(120, 100.0), (4000, 100.0), (4000, 85.0)])
+def test_gene_image_dict_supports_equal_the_materialised_images(n_obs, vmax):
+    """The SVG ranking reads each gene's support straight from the staged CSC columns; it must equal what the
+    reference's per-gene ``csr_matrix((column, (x, y)))`` + ``nonzero`` staging yields (distance.py:192-199) — also when
+    several spots share a cell (n_obs = 4000 on a 64 x 40 grid: the csr constructor sums them)."""
+    from stminer_b200.Algorithm.distance import csr_to_support
+    adata, X, xy = _adata(seed=8, n_obs=n_obs, n_var=12)
+    sp = SPFinder(adata)
+    sp.get_genes_csr_array(min_cells=1, normalize=False, vmax=vmax)
+    keys = list(sp.csr_dict.keys())
+    assert keys == list(sp.adata.var_names) and len(sp.csr_dict) == len(keys) and keys[3] in sp.csr_dict
+    sup = sp.csr_dict.supports()
+    for k, s in zip(keys, sup):
+        ref = csr_to_support(sp.csr_dict[k])
+        assert all(np.array_equal(a, b) for a, b in zip(ref, s)), k
+    part = sp.csr_dict.supports(keys[2:5])
+    assert all(np.array_equal(a, b) for a, b in zip(part[0], sup[2]))
