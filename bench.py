@@ -301,7 +301,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- third kernel of the path: exact spot-level EMD (global image vs gene image), Visium-size problems ---
     emd = None
-    if args.emd_genes > 0 and rank == 0:
+    if args.emd_genes > 0 and rank == 0 and world == 1:      # single-GPU extras: keep the multi-rank runs short
         from scipy import sparse as _sp
         from stminer_b200.Algorithm.distance import emd_batched
         from stminer_b200.Simulate import simulate_spot_matrix
@@ -326,7 +326,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the step after the distance matrix: cluster() = SMACOF MDS (4 restarts, 20 components) on the G x G matrix ----
     mds = None
-    if rank == 0 and not args.no_mds and Gp >= 64:
+    if rank == 0 and world == 1 and not args.no_mds and Gp >= 64:
         from stminer_b200.Algorithm.algorithm import mds_fit_transform
         from stminer_b200.Algorithm.distance import pairs_to_square
         local_all = gmm_pair_distances(W, MU, COV, 0, total_pairs, device=dev)
@@ -351,7 +351,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- long genes (BASELINE configs[3], Stereo-seq bin10-shaped): one gene per thread-block cluster ----------------
     s10 = None
-    if rank == 0 and args.s10_genes > 0:
+    if rank == 0 and world == 1 and args.s10_genes > 0:
         from stminer_b200.Simulate import simulate_long_genes
         from stminer_b200.staging import SpotMatrix
         path = "/tmp/stm_bench_S10_%d.npz" % args.s10_genes
