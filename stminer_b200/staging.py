@@ -23,6 +23,13 @@ def _wrap_i16(a: np.ndarray) -> np.ndarray:
     return ((a.astype(np.int64) + 32768) % 65536 - 32768).astype(np.int32)
 
 
+def _wrap_i16_float(a: np.ndarray) -> np.ndarray:
+    """int16 wrap of integer-valued floats, as floats; one min/max pass when nothing is out of range (the usual case)."""
+    if len(a) == 0 or (a.min() >= -32768.0 and a.max() <= 32767.0):
+        return a
+    return _wrap_i16(a).astype(np.float64)
+
+
 @dataclass
 class SpotMatrix:
     """CSC expression matrix over distinct spots (host copy, numpy)."""
@@ -177,9 +184,13 @@ class SpotMatrix:
         if columns is not None:
             M = M[:, np.asarray(columns, dtype=np.int64)]
             genes = [genes[c] for c in columns]
-        M = M.astype(np.float64, copy=True)
         if truncate_int16:
-            M.data = _wrap_i16(np.trunc(M.data)).astype(np.float64)        # AlgUtils.py:35
+            # AlgUtils.py:35; trunc copies the data, the structure arrays are copied because eliminate_zeros below works in
+            # place and tocsc() hands back the caller's own arrays when X already is CSC
+            M = sparse.csc_matrix((_wrap_i16_float(np.trunc(M.data.astype(np.float64, copy=False))),
+                                   M.indices.copy(), M.indptr.copy()), shape=M.shape)
+        else:
+            M = M.astype(np.float64, copy=True)
         # distinct spots, row-major (x, y) order
         ymul = int(y.max()) + 1 if len(y) else 1
         key = x * ymul + y
@@ -189,7 +200,7 @@ class SpotMatrix:
             P = sparse.csr_matrix((np.ones(n_obs), (inverse, np.arange(n_obs))), shape=(n_spots, n_obs))
             M = (P @ M).tocsc()                                              # duplicates summed (todense, AlgUtils.py:15)
             if truncate_int16:
-                M.data = _wrap_i16(M.data).astype(np.float64)
+                M.data = _wrap_i16_float(M.data)
         M.eliminate_zeros()
         M.sort_indices()
         return cls(M.indptr.astype(np.int64), M.indices.astype(np.int32), M.data.astype(np.float32),
