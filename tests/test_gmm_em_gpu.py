@@ -15,7 +15,8 @@ def _fit(sm, K, init, **kw):
 
 
 @pytest.mark.parametrize("config,K,nt,rep", [("T", 10, 6, 4), ("V", 20, 6, 3), ("T", 5, 4, 2), ("V", 32, 3, 2),
-                                              ("V", 40, 2, 2), ("V", 64, 2, 1), ("T", 3, 3, 2)])
+                                              ("V", 40, 2, 2), ("V", 64, 2, 1), ("T", 3, 3, 2), ("T", 1, 2, 2), ("V", 2, 2, 2),
+                                              ("V", 6, 2, 2), ("V", 11, 2, 2), ("V", 21, 2, 1), ("V", 41, 1, 2)])
 def test_em_parity_fixed_init(cuda_device, config, K, nt, rep):
     from stminer_b200.Simulate import simulate_spot_matrix
     sm = simulate_spot_matrix(config, seed=7, n_templates=nt, replicas=rep)
