@@ -356,3 +356,19 @@ def test_ill_conditioned_covariance_reports_status_2(cuda_device):
                         precisions_init=np.linalg.inv(cov0)).fit(go.array_to_list(xy, c).astype(float))
     with pytest.raises(ValueError, match="Gene id: line"):
         result_to_gmm_dict(sm.genes, res)
+
+
+@pytest.mark.parametrize("K", [4, 8, 33])
+def test_cluster_device_init_other_component_classes(cuda_device, K):
+    """Cluster path + on-device init for the other kernel classes (K <= 5, <= 10, <= 40): valid, reproducible fits whose
+    lower bound matches the one-CTA path started from the same seeds."""
+    from stminer_b200.Simulate import simulate_long_genes
+    sm = simulate_long_genes(2, seed=40 + K, nnz=[60000, 33000])
+    a = _fit(sm, K, None, seed=5)
+    b = _fit(sm, K, None, seed=5)
+    c = _fit(sm, K, None, seed=5, no_clusters=True)
+    assert (a["status"] == 0).all() and (c["status"] == 0).all()
+    for k in ("weights", "means", "covariances", "n_iter", "lower_bound"):
+        assert np.array_equal(a[k], b[k]), k
+    np.testing.assert_allclose(a["weights"].sum(axis=1), 1.0, atol=1e-9)
+    assert np.abs(a["lower_bound"] - c["lower_bound"]).max() < 5e-3
