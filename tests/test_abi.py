@@ -70,3 +70,23 @@ def test_fit_plan_orders_by_nnz_and_buckets():
     # K > 40 has one kernel shape and no cluster buckets
     assert lib.stm_gmm_fit_plan(col.ctypes.data, len(nnz), 64, 0, order.ctypes.data, buckets.ctypes.data) == 0
     assert buckets[:4].sum() == 0 and buckets.sum() == len(nnz)
+
+
+def test_product_code_never_touches_the_oracle_or_the_reference_tree():
+    """The oracle is test infrastructure: nothing under stminer_b200/ (nor the library sources) may import, load or
+    read it, and nothing that runs on the GPU box may read /root/reference."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bad = []
+    for base, _, files in os.walk(os.path.join(root, "stminer_b200")):
+        if "build" in os.path.basename(base):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(base, f), encoding="utf-8").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "libstm_oracle" in src or "/root/reference" in src:
+                    bad.append(os.path.join(base, f))
+    assert not bad, bad
+    for f in ("bench.py", "__graft_entry__.py"):
+        assert "/root/reference" not in open(os.path.join(root, f), encoding="utf-8").read(), f
