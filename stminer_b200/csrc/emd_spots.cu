@@ -28,7 +28,15 @@ namespace {
 
 constexpr int EMD_PREP_THREADS = 256;
 constexpr int EMD_MAXPATH = 2048;
-constexpr int EMD_RMAX = 5;   // sources per thread kept in registers by the whole-row pricing path
+#ifndef STM_EMD_T_BIG
+#define STM_EMD_T_BIG 512    // CTA size of the one-CTA-per-SM kernel: the pricing scan is issue-bound (same time at 512 or 1,024
+                             // threads) while every barrier-delimited serial phase is cheaper with 16 warps: 116 vs 111 problems/s
+#endif
+// sources per thread kept in registers by the whole-row pricing path: 5,120 sources per CTA for the big kernel
+#ifndef STM_EMD_MINB_SMALL
+#define STM_EMD_MINB_SMALL 1   // CTAs per SM the 256-thread kernel is compiled for (register bound)
+#endif
+constexpr int emd_rmax(int threads, bool big) { return big ? 5120 / threads : 5; }
 constexpr double EMD_SCALE = 1125899906842624.0;  // 2^50
 constexpr unsigned short NONE16 = 0xffffu;
 
@@ -110,9 +118,10 @@ __global__ void __launch_bounds__(EMD_PREP_THREADS) emd_prep_kernel(const double
 // WIDE = 64-bit potentials and reduced costs for problems whose coordinate span makes (span^2 + 1) * nodes exceed the
 // int32 range of the default kernel (scattered integer coordinates, long thin tissues): 22 instead of 18 bytes of shared
 // memory per node and the general (non register-resident) pricing path, same pivot sequence.
-template <int EMD_THREADS, bool WIDE>
-__global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
+template <int EMD_THREADS, bool WIDE, bool ONE_PER_SM>
+__global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMALL) emd_kernel(const EmdArgs p) {
   constexpr int EMD_WARPS = EMD_THREADS / 32;
+  constexpr int EMD_RMAX_T = emd_rmax(EMD_THREADS, ONE_PER_SM);
   using pi_t = typename std::conditional<WIDE, long long, int>::type;
   constexpr pi_t PI_NONE = WIDE ? (pi_t)LLONG_MAX : (pi_t)INT_MAX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -208,11 +217,11 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
     const int n_arcs = n * m;
     // pricing block: LEMON uses sqrt(#arcs); a CTA prices in parallel, so larger blocks (fewer, better pivots and
     // fewer barriers per arc) win — 32 arcs per thread measured best on Visium-size problems
-    int B = p.block_size > 0 ? p.block_size : max((int)sqrt((double)n_arcs), 32 * EMD_THREADS);
-    if (p.block_size <= 0 && n <= EMD_RMAX * EMD_THREADS) B = max(1, (B + n / 2) / n) * n;   // whole target rows
+    int B = p.block_size > 0 ? p.block_size : max((int)sqrt((double)n_arcs), ONE_PER_SM ? 32768 : 32 * EMD_THREADS);
+    if (p.block_size <= 0 && n <= EMD_RMAX_T * EMD_THREADS) B = max(1, (B + n / 2) / n) * n;   // whole target rows
     if (B < 10) B = 10;
     if (B > n_arcs) B = n_arcs;
-    const bool whole_rows = !WIDE && B % n == 0 && n <= EMD_RMAX * EMD_THREADS;   // n_arcs and every block start are multiples of n
+    const bool whole_rows = !WIDE && B % n == 0 && n <= EMD_RMAX_T * EMD_THREADS;   // n_arcs and every block start are multiples of n
     int next_arc = 0;
     long long it = 0;
     int status = 0;
@@ -253,9 +262,9 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
             // Fast path (the default block size is a whole number of target rows): every thread keeps ITS sources'
             // terms in registers for the whole block and meets each target row with no shared-memory traffic
             // beyond the row's three broadcast words — six integer instructions per arc.
-            int sx[EMD_RMAX], sy[EMD_RMAX], sp[EMD_RMAX];
+            int sx[EMD_RMAX_T], sy[EMD_RMAX_T], sp[EMD_RMAX_T];
 #pragma unroll
-            for (int r = 0; r < EMD_RMAX; ++r) {
+            for (int r = 0; r < EMD_RMAX_T; ++r) {
               const int i = tid + r * EMD_THREADS;
               const int xy = i < n ? s_xy[i] : 0;
               sx[r] = (xy << 16) >> 16; sy[r] = xy >> 16;
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
             for (int rr = cnt / n; rr > 0; --rr) {
               const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
 #pragma unroll
-              for (int r = 0; r < EMD_RMAX; ++r) brc = min(brc, sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj)));
+              for (int r = 0; r < EMD_RMAX_T; ++r) brc = min(brc, sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj)));
               if (++j >= m) j = 0;
             }
             // ---- level 1: the block's most negative reduced cost --------------------------------------------
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1) emd_kernel(const EmdArgs p) {
                 for (int rr = cnt / n; rr > 0 && myk == 0xffffffffu; --rr) {
                   const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
 #pragma unroll
-                  for (int r = 0; r < EMD_RMAX; ++r) {
+                  for (int r = 0; r < EMD_RMAX_T; ++r) {
                     const int rc = sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj));
                     if (rc == g_rc && myk == 0xffffffffu) {
                       int k = j * n + tid + r * EMD_THREADS - next_arc;
@@ -642,8 +651,9 @@ int emd_launch(bool wide, const int32_t* src_x, const int32_t* src_y, const doub
     STM_CHECK_CUDA(cudaGetLastError());
     return STM_OK;
   };
-  if (one_per_sm) return wide ? launch(emd_kernel<1024, true>, 1024) : launch(emd_kernel<1024, false>, 1024);
-  return wide ? launch(emd_kernel<256, true>, 256) : launch(emd_kernel<256, false>, 256);
+  if (one_per_sm)
+    return wide ? launch(emd_kernel<STM_EMD_T_BIG, true, true>, STM_EMD_T_BIG) : launch(emd_kernel<STM_EMD_T_BIG, false, true>, STM_EMD_T_BIG);
+  return wide ? launch(emd_kernel<256, true, false>, 256) : launch(emd_kernel<256, false, false>, 256);
 }
 }  // namespace
 }  // namespace stm

@@ -139,7 +139,7 @@ def test_emd_batch_mixes_int32_and_64bit_problems(cuda_device):
 
 
 def test_emd_one_cta_per_sm_kernel_matches_oracle(cuda_device):
-    """A problem large enough for the 1,024-thread kernel (one CTA per SM) with int32 potentials and the register-
+    """A problem large enough for the one-CTA-per-SM kernel with int32 potentials and the register-
     resident whole-row pricing path: cost AND pivot count of the oracle at the same block size (9 target rows)."""
     from stminer_b200.Algorithm.distance import emd_batched
     rng = np.random.default_rng(11)
