@@ -36,7 +36,7 @@ constexpr int EMD_MAXPATH = 2048;
 #ifndef STM_EMD_MINB_SMALL
 #define STM_EMD_MINB_SMALL 1   // CTAs per SM the 256-thread kernel is compiled for (register bound)
 #endif
-constexpr int emd_rmax(int threads, bool big) { return big ? 5120 / threads : 5; }
+constexpr int emd_rmax(int threads, bool big) { return big ? (5120 + threads - 1) / threads : 5; }
 constexpr double EMD_SCALE = 1125899906842624.0;  // 2^50
 constexpr unsigned short NONE16 = 0xffffu;
 
