@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     // ---- stage coordinates (relative to the source's first spot), bounding box, capacity checks ----
     const int ox = p.src_x[0], oy = p.src_y[0];
     int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
-    const bool fits = N <= cap && N < 65535 && (int64_t)n * m < 2147483647LL;
+    // N <= 30 * threads: the cycle-path scan keeps one bit per preorder position of a thread's run in a 32-bit mask
+    const bool fits = N <= cap && N < 65535 && N <= 30 * EMD_THREADS && (int64_t)n * m < 2147483647LL;
     for (int v = tid; v < n + m; v += EMD_THREADS) {
       const int x = v < n ? p.src_x[v] : p.tgt_x[t0 + v - n], y = v < n ? p.src_y[v] : p.tgt_y[t0 + v - n];
       xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
