@@ -8,27 +8,30 @@ import pandas as pd
 from .. import _lib
 
 
-def linear_sum_batched(costs):
+def linear_sum_batched(costs, device=None):
     """Optimal assignment cost of every K x K matrix of ``costs`` [B, K, K] (numpy or CUDA tensor, float64)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     t = costs if isinstance(costs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(costs, dtype=np.float64))
-    t = t.to(device="cuda", dtype=torch.float64).contiguous()
+    if device is None:
+        device = t.device if t.is_cuda else "cuda"
+    t = t.to(device=device, dtype=torch.float64).contiguous()
     if t.dim() != 3 or t.shape[1] != t.shape[2]:
         raise ValueError("expected cost matrices of shape [B, K, K], got %s" % (tuple(t.shape),))
     out = torch.empty((t.shape[0],), dtype=torch.float64, device=t.device)
-    st = lib.stm_lsap_batched(_lib.ptr(t), int(t.shape[1]), int(t.shape[0]), _lib.ptr(out), _lib.current_stream_ptr())
+    with torch.cuda.device(t.device):
+        st = lib.stm_lsap_batched(_lib.ptr(t), int(t.shape[1]), int(t.shape[0]), _lib.ptr(out), _lib.current_stream_ptr())
     _lib.check(st, "stm_lsap_batched")
     return out
 
 
-def linear_sum(cost) -> float:
+def linear_sum(cost, device=None) -> float:
     """Drop-in for ``linear_sum`` (algorithm.py:10-26): minimal total cost of a complete assignment.
     Like scipy, non-finite entries are an error (scipy: 'matrix contains invalid numeric entries')."""
     cost = np.asarray(cost, dtype=np.float64)
     if cost.ndim != 2 or cost.shape[0] != cost.shape[1]:
         raise ValueError("the device LSAP takes square cost matrices (the hot path's K x K costs)")
-    v = float(linear_sum_batched(cost[None]).cpu().numpy()[0])
+    v = float(linear_sum_batched(cost[None], device=device).cpu().numpy()[0])
     if not np.isfinite(v):
         raise ValueError("matrix contains invalid numeric entries")
     return v
@@ -99,7 +102,8 @@ def mds_fit_transform(dissimilarities, n_components: int = 2, n_init: int = 4, m
     return best[0].cpu().numpy(), best[1], best[2]
 
 
-def cluster(distance_array: pd.DataFrame, mds_components: int = 20, n_clusters: int = 10, method: str = "kmeans"):
+def cluster(distance_array: pd.DataFrame, mds_components: int = 20, n_clusters: int = 10, method: str = "kmeans",
+            device=None):
     """Drop-in for ``cluster`` (algorithm.py:29-61): MDS on the precomputed distances, then KMeans
     (``random_state=0, max_iter=1000, n_init=20``) or spectral clustering; returns
     ``(DataFrame[gene_id, labels], fit_result, embedding)``.  The MDS (SMACOF, O(G^2 d) per iteration) runs on the
@@ -109,7 +113,8 @@ def cluster(distance_array: pd.DataFrame, mds_components: int = 20, n_clusters: 
     if method not in ("kmeans", "spectral"):
         raise ValueError("method should be kmeans or spectral")
     index = distance_array.index
-    embedding_position, _, _ = mds_fit_transform(np.asarray(distance_array, dtype=np.float64), mds_components)
+    embedding_position, _, _ = mds_fit_transform(np.asarray(distance_array, dtype=np.float64), mds_components,
+                                                 device=device)
     if method == "kmeans":
         fit_result = KMeans(n_clusters=n_clusters, random_state=0, max_iter=1000, n_init=20).fit(embedding_position)
     else:

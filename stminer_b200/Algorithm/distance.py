@@ -63,7 +63,8 @@ def pairs_to_square(pairs, G: int):
 
 def build_gmm_distance_array(gmm_dict, device=None):
     """Drop-in for ``build_gmm_distance_array`` (distance.py:83-99): symmetric float64 DataFrame with a zero
-    diagonal, index = columns = ``list(gmm_dict.keys())``."""
+    diagonal, index = columns = ``list(gmm_dict.keys())``.  The warp LSAP keeps one or two cost columns per
+    lane, so mixtures are limited to K <= 64 components (the reference default is 20)."""
     genes, W, MU, COV = stack_gmms(gmm_dict)
     G = len(genes)
     if G == 0:
@@ -73,7 +74,19 @@ def build_gmm_distance_array(gmm_dict, device=None):
     pairs = gmm_pairs_sharded(W, MU, COV, device=device)
     pairs = pairs.to(torch.device(device if device is not None else "cuda"))
     square = pairs_to_square(pairs, G).cpu().numpy()
+    _raise_on_invalid(square, genes)
     return pd.DataFrame(square, index=genes, columns=genes)
+
+
+def _raise_on_invalid(square, genes, query=None):
+    """scipy's ``linear_sum_assignment`` raises on a cost matrix with NaN/inf entries (degenerate covariances);
+    the device LSAP returns NaN for such a pair — surface it the same way instead of storing it (algorithm.py:24)."""
+    bad = ~np.isfinite(square)
+    if bad.any():
+        idx = np.argwhere(bad)[0]
+        a = genes[idx[0]] if query is None else query
+        b = genes[idx[-1]]
+        raise ValueError("matrix contains invalid numeric entries (GMM distance of genes %s and %s)" % (a, b))
 
 
 def gmm_one_vs_all(qw, qmu, qcov, W, MU, COV, device=None):
@@ -99,7 +112,9 @@ def compare_gmm_distance(gmm, gmm_dict, device=None):
     d = gmm_one_vs_all(np.asarray(gmm.weights_, dtype=np.float64).reshape(K),
                        np.asarray(gmm.means_, dtype=np.float64).reshape(K, 2),
                        np.asarray(gmm.covariances_, dtype=np.float64).reshape(K, 2, 2), W, MU, COV, device=device)
-    df = pd.DataFrame.from_dict(dict(zip(genes, d.cpu().numpy())), orient="index")
+    d = d.cpu().numpy()
+    _raise_on_invalid(d, genes, query="<query>")
+    df = pd.DataFrame.from_dict(dict(zip(genes, d)), orient="index")
     return df.sort_values(0)
 
 

@@ -237,7 +237,9 @@ class SPFinder:
         Xc = Xc.astype(np.float64)
         warned, seen, keep_genes, keep_cols = set(), set(), [], []
         for gene in arr_list:
-            if counts.get(gene, 0) != 1:           # SPFinder.py:225-234 (duplicates) / KeyError on unknown genes
+            if gene not in counts:                 # ``self.adata[:, gene]`` raises KeyError (SPFinder.py:224)
+                raise KeyError("Values [%r], from [%r], are not valid obs/ var names or indices." % (gene, gene))
+            if counts[gene] != 1:                  # SPFinder.py:225-234: duplicated var names are skipped with a warning
                 if gene not in warned:
                     warned.add(gene)
                     logger.warning("Gene [%s] has more than one index, skip.", gene)
@@ -277,8 +279,11 @@ class SPFinder:
             dist, status = ot_distances_to_source(global_matrix, [self.csr_dict[k] for k in keys], device=self.device)
         distance_dict = {}
         for k, d, s in zip(keys, dist, status):
-            if s == 2:                                # empty image: POT raises, the reference logs and skips
-                logger.error("Failed to compute OT distance for gene %s.", k)
+            # status 0 = optimal, 1 = stopped at numItermax with the current basis cost (what POT returns too).
+            # Anything else (2 = empty image, >= 3 = the solver could not run the problem) is what an exception is
+            # in the reference's loop: logged, gene skipped (SPFinder.py:294-299) — never a NaN in the table.
+            if s >= 2 or not np.isfinite(d):
+                logger.error("Failed to compute OT distance for gene %s (solver status %d).", k, int(s))
                 continue
             distance_dict[k] = d
         self.global_distance = pd.DataFrame(list(distance_dict.items()), columns=["Gene", "Distance"]) \
@@ -335,7 +340,7 @@ class SPFinder:
         else:
             target = self.genes_distance_array
         self.genes_labels, self.kmeans_fit_result, self.mds_features = cluster(
-            target, n_clusters=n_clusters, mds_components=mds_components)
+            target, n_clusters=n_clusters, mds_components=mds_components, device=self.device)
 
     # ------------------------------------------------------------------ pattern voting
     def get_pattern_array(self, vote_rate: float = 0.0, mode: str = "vote") -> None:
@@ -378,7 +383,9 @@ class SPFinder:
         """SPFinder.py:491-524: mixture of the voted pattern image, fitted on the device."""
         if mode == "vote":
             _, total_count = self._genes_to_pattern(gene_list, vote_rate)
-            self.custom_pattern = _fit_image(np.round(total_count).astype(np.int32), n_components, self.seed, self.device)
+            # SPFinder.py:516-517: GaussianMixture(n_components).fit -> sklearn's default max_iter = 100
+            self.custom_pattern = _fit_image(np.round(total_count).astype(np.int32), n_components, self.seed, self.device,
+                                             max_iter=100)
         elif mode == "test":
             pass
         else:
@@ -412,14 +419,14 @@ class SPFinder:
         self.all_labels = all_labels
 
 
-def _fit_image(image: np.ndarray, n_components: int, seed: int, device):
+def _fit_image(image: np.ndarray, n_components: int, seed: int, device, max_iter: int = 200):
     """``get_gmm`` (distribution.py:37-41, max_iter=200 there) for a dense count image, on the device."""
     from .Algorithm.distribution import fit_spot_matrix, result_to_gmm_dict
     from .staging import DeviceSpotMatrix, SpotMatrix
     xs, ys = np.nonzero(image > 0)
     sm = SpotMatrix(np.array([0, len(xs)], dtype=np.int64), np.arange(len(xs), dtype=np.int32),
                     image[xs, ys].astype(np.float32), xs.astype(np.int32), ys.astype(np.int32), ["pattern"])
-    res = fit_spot_matrix(DeviceSpotMatrix(sm, device=device), n_components, init=None, max_iter=200, seed=seed)
+    res = fit_spot_matrix(DeviceSpotMatrix(sm, device=device), n_components, init=None, max_iter=max_iter, seed=seed)
     d = result_to_gmm_dict(sm.genes, res.to_host())
     if "pattern" not in d:
         raise ValueError("pattern image has fewer distinct spots than components")

@@ -82,7 +82,8 @@ def load():
         if _lib is not None:
             return _lib
         path = lib_path()
-        if not os.path.exists(path) or os.environ.get("STM_REBUILD") == "1":
+        stale = path == _build.LIB_PATH and _build.needs_build() and _build.have_nvcc()
+        if not os.path.exists(path) or stale or os.environ.get("STM_REBUILD") == "1":
             _build.build(force=os.environ.get("STM_REBUILD") == "1")
         if not os.path.exists(path):
             raise RuntimeError(

@@ -29,17 +29,36 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; the stminer_b200 CUDA library cannot be built")
 
 
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+def _source_hash() -> str:
+    """Content hash of everything the library is compiled from (mtimes do not survive a snapshot copy)."""
+    import hashlib
+    deps = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     deps.append(os.path.join(HERE, "..", "include", "stminer_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in deps:
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def needs_build() -> bool:
+    """True when the library is missing or was built from other sources than the ones in the tree."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(LIB_PATH + ".srchash"):
+        return True
+    with open(LIB_PATH + ".srchash") as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False, defines=None, out: str = None) -> str:
@@ -72,6 +91,9 @@ def build(force: bool = False, verbose: bool = False, defines=None, out: str = N
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    if lib_path == LIB_PATH and not defines:
+        with open(LIB_PATH + ".srchash", "w") as f:
+            f.write(_source_hash())
     return lib_path
 
 
