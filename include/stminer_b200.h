@@ -156,10 +156,16 @@ int stm_gmm_dist_one_vs_all(const double* qw, const double* qmu, const double* q
  *   src_x, src_y [n] int32, src_mass[n] float64 (positive, any scale — normalised inside as a/sum(a))
  *   tgt_ptr[G+1] int64, tgt_x, tgt_y int32, tgt_mass float64 (positive; normalised per target)
  *   max_tgt      largest target support in the batch; order[G] optional processing order (largest first)
- *   max_iter     pivot limit (reference: numItermax=200000); block_size: arcs priced per block search step,
- *                0 = about 32 arcs per thread rounded to whole target rows (LEMON/POT use sqrt(n*m))
- *   workspace    device scratch of at least stm_emd_workspace_bytes(n_src, max_tgt, n_ctas) bytes; n_ctas CTAs
- *                (one problem at a time each) pull problems from a queue
+ *   max_iter     pivot limit on the problem itself (reference: numItermax=200000); block_size: arcs priced per block
+ *                search step, 0 = about 32 arcs per thread rounded to whole target rows (LEMON/POT use sqrt(n*m))
+ *   flags        0 = multiscale start basis: the grid is coarsened by 2 x 2 cells level by level, the coarsest problem
+ *                is solved from the artificial star and every finer level starts from the refinement of the coarser
+ *                optimum; the finest level is the problem itself, solved to optimality by the same simplex, with about
+ *                ten times fewer pivots (max_iter applies to that level; out_iters counts all levels).
+ *                STM_EMD_STAR_START = the artificial star POT/LEMON start from (one level).  The optimum — the value
+ *                the reference returns — does not depend on the start basis.
+ *   workspace    16-byte aligned device scratch of at least stm_emd_workspace_bytes(n_src, max_tgt, n_ctas) bytes;
+ *                n_ctas CTAs (one problem at a time each) pull problems from a queue
  *   out_cost[G] float64 = sum_ij G_ij * M_ij;  out_iters[G] (nullable) pivots;  out_status[G]:
  *     0 optimal, 1 iteration limit reached (POT returns the current, sub-optimal value with a warning),
  *     2 empty image, 3 problem does not fit one CTA's shared memory / int16 coordinate span / the range of the
@@ -170,17 +176,18 @@ int stm_gmm_dist_one_vs_all(const double* qw, const double* qmu, const double* q
  * same solver (same pivot sequence) with 64-bit potentials for problems beyond that bound — scattered integer
  * coordinates, long thin tissues — at 22 B per node (~9.8k nodes) and a slower pricing loop.
  */
+#define STM_EMD_STAR_START 1u
 int64_t stm_emd_workspace_bytes(int32_t n_src, int64_t max_tgt, int32_t n_ctas);
 int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
                           const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
                           const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
-                          int64_t max_iter, int32_t block_size,
+                          int64_t max_iter, int32_t block_size, uint32_t flags,
                           void* workspace, int64_t workspace_bytes, int32_t n_ctas,
                           double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream);
 int stm_emd_spots_batched_wide(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
                                const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
                                const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
-                               int64_t max_iter, int32_t block_size,
+                               int64_t max_iter, int32_t block_size, uint32_t flags,
                                void* workspace, int64_t workspace_bytes, int32_t n_ctas,
                                double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream);
 

@@ -30,6 +30,9 @@ def _lib():
         lib.stm_oracle_emd.restype = C.c_int
         lib.stm_oracle_emd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+        lib.stm_oracle_emd_ms.restype = C.c_int
+        lib.stm_oracle_emd_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_int64, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -56,6 +59,21 @@ def emd_network_simplex(sx, sy, smass, tx, ty, tmass, max_iter=200000, block_siz
                                tx.ctypes.data, ty.ctypes.data, tmass.ctypes.data, len(tx),
                                int(max_iter), int(block_size), int(cand_threads), C.byref(cost), C.byref(iters))
     return cost.value, st, iters.value
+
+
+def emd_multiscale(sx, sy, smass, tx, ty, tmass, max_iter=200000, block_size=0, star=False):
+    """(cost, status, total pivots, pivots per level [0] = finest) with the multiscale start basis the CUDA kernel uses
+    by default (see emd_oracle.c); ``max_iter`` bounds the pivots of the finest level, i.e. of the original problem."""
+    sx = np.ascontiguousarray(sx, dtype=np.int32); sy = np.ascontiguousarray(sy, dtype=np.int32)
+    tx = np.ascontiguousarray(tx, dtype=np.int32); ty = np.ascontiguousarray(ty, dtype=np.int32)
+    smass = np.ascontiguousarray(smass, dtype=np.float64); tmass = np.ascontiguousarray(tmass, dtype=np.float64)
+    cost = C.c_double(0.0); iters = C.c_int64(0)
+    lev = np.zeros(16, dtype=np.int64)
+    st = _lib().stm_oracle_emd_ms(sx.ctypes.data, sy.ctypes.data, smass.ctypes.data, len(sx),
+                                  tx.ctypes.data, ty.ctypes.data, tmass.ctypes.data, len(tx),
+                                  int(max_iter), int(block_size), 1 if star else 0, C.byref(cost), C.byref(iters),
+                                  lev.ctypes.data)
+    return cost.value, st, iters.value, lev
 
 
 def emd_linprog(sx, sy, smass, tx, ty, tmass):

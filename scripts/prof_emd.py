@@ -1,16 +1,34 @@
-import sys, numpy as np
-sys.path.insert(0, '.')
+"""Spot-EMD timing on Visium-size problems: multiscale start (default) vs the star start.
+   python scripts/prof_emd.py [n_problems] [--star]"""
+import sys
+import time
+
+import numpy as np
 import torch
+from scipy import sparse
+
+sys.path.insert(0, ".")
 from stminer_b200.Algorithm.distance import emd_batched
-rng = np.random.default_rng(0)
-R, n, G = 60, 1500, 296
-s = rng.permutation(R * R)[:n]
-src = (s // R, s % R, rng.gamma(1.0, 1.0, n) + 0.01)
+from stminer_b200.Simulate import simulate_spot_matrix
+
+G = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 148
+vsm = simulate_spot_matrix("V", seed=0, n_templates=max(1, (G + 3) // 4), replicas=4, truncate_int16=False)
+X = sparse.csc_matrix((vsm.val, vsm.row_idx, vsm.col_ptr), shape=(vsm.n_spots, vsm.n_genes))
+src = (vsm.spot_x, vsm.spot_y, np.asarray(X.sum(axis=1)).ravel())
 tg = []
-for g in range(G):
-    m = int(rng.integers(400, 900)); t = rng.permutation(R * R)[:m]
-    tg.append((t // R, t % R, rng.gamma(1.0, 1.0, m) + 0.01))
-for _ in range(2):
-    torch.cuda.synchronize(); a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-    a.record(); c, st, it = emd_batched(src, tg, return_iters=True); b.record(); torch.cuda.synchronize()
-    print('%d problems (1500 x ~650): %.1f ms, mean pivots %.0f, status %s' % (G, a.elapsed_time(b), it.mean(), np.bincount(st)))
+for gi in range(min(G, vsm.n_genes)):
+    a, b = vsm.col_ptr[gi], vsm.col_ptr[gi + 1]
+    tg.append((vsm.spot_x[vsm.row_idx[a:b]], vsm.spot_y[vsm.row_idx[a:b]], vsm.val[a:b].astype(np.float64)))
+emd_batched(src, tg[:4])
+torch.cuda.synchronize()
+res = {}
+for star in ([False, True] if "--star" in sys.argv else [False]):
+    t0 = time.perf_counter()
+    cost, status, iters = emd_batched(src, tg, return_iters=True, star_start=star)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    res[star] = cost
+    print("%s start: %d problems in %.3f s = %.1f problems/s; mean pivots %.0f; status counts %s"
+          % ("star" if star else "multiscale", len(tg), dt, len(tg) / dt, iters.mean(), np.bincount(status).tolist()))
+if len(res) == 2:
+    print("max rel diff between the two starts: %.3e" % np.max(np.abs(res[True] - res[False]) / res[True]))

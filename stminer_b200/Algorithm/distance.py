@@ -136,12 +136,14 @@ def csr_to_support(img):
     return (coo.row[keep].astype(np.int32), coo.col[keep].astype(np.int32), coo.data[keep].astype(np.float64))
 
 
-def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, device=None, return_iters: bool = False):
+def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, device=None, return_iters: bool = False,
+                star_start: bool = False):
     """Exact EMD between one source support ``(x, y, mass)`` and every target support of ``targets``.
 
     Returns ``(cost[G] float64, status[G] int32)`` as numpy arrays (+ pivots with ``return_iters``).
     ``max_iter`` mirrors ``numItermax=200000`` of the reference (distance.py:201): a problem that hits it
-    reports status 1 and the cost of its current basis, as POT does.
+    reports status 1 and the cost of its current basis, as POT does.  ``star_start`` selects the artificial star
+    POT starts from instead of the multiscale start basis (same optimum, about ten times the pivots).
     """
     torch = _lib.require_cuda()
     lib = _lib.load()
@@ -194,7 +196,8 @@ def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, devic
             fn = lib.stm_emd_spots_batched_wide if wide else lib.stm_emd_spots_batched
             st = fn(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), len(sx), _lib.ptr(d[3]),
                     _lib.ptr(d[4]), _lib.ptr(d[5]), _lib.ptr(d[6]), len(sel), int(sizes[sel].max()), _lib.ptr(d_order),
-                    int(max_iter), int(block_size), _lib.ptr(ws), ws_bytes, n_ctas,
+                    int(max_iter), int(block_size), _lib.STM_EMD_STAR_START if star_start else 0,
+                    _lib.ptr(ws), ws_bytes, n_ctas,
                     _lib.ptr(cost), _lib.ptr(status), _lib.ptr(iters), _lib.current_stream_ptr())
             _lib.check(st, "stm_emd_spots_batched_wide" if wide else "stm_emd_spots_batched")
             keep.append((d_order, ws))

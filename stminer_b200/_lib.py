@@ -24,6 +24,7 @@ STM_FIT_REMOVE_LOW_EXP_SPOTS = 1
 STM_FIT_DEVICE_INIT = 2
 STM_FIT_COMPACT_INPUT = 4
 STM_FIT_NO_CLUSTERS = 8
+STM_EMD_STAR_START = 1
 STM_FIT_N_BUCKETS = 7     # cluster x16 / x8 / x4 / x2, then one CTA per gene: large / medium / small
 
 
@@ -56,9 +57,9 @@ SIGNATURES = {
     "stm_gmm_dist_one_vs_all": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     "stm_emd_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32]),
     "stm_emd_spots_batched": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int64, _P,
-                                        C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
+                                        C.c_int64, C.c_int32, C.c_uint32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "stm_emd_spots_batched_wide": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int64, _P,
-                                             C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
+                                             C.c_int64, C.c_int32, C.c_uint32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "stm_mds_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "stm_mds_smacof": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_double, C.c_int32, _P, C.c_int64,
                                  _P, _P, _P, _P]),

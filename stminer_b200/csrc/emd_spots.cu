@@ -11,10 +11,20 @@
 //   * pricing is a block search: the CTA evaluates a block of arcs in parallel and enters the most negative
 //     reduced cost of the first block that has one (LEMON's rule);
 //   * the spanning tree is stored as parent / preorder position / subtree size (uint16) in shared memory, a
-//     subtree being a contiguous segment of the preorder array — the two cycle paths are chased by two
-//     lanes, everything else (leaving-arc search, flow update, potential shift of the re-hung subtree,
-//     preorder re-numbering) is data-parallel over the CTA;
-//   * arc flows (int64) live in a per-CTA slice of a global workspace (touched only along the cycle).
+//     subtree being a contiguous segment of the preorder array — cycle paths, leaving-arc search, flow update,
+//     potential shift of the re-hung subtree and preorder re-numbering are all data-parallel over the CTA;
+//   * arc flows (int64) live in shared memory as far as it reaches, the rest in a per-CTA global slice;
+//   * MULTISCALE START (default): the LP optimum does not depend on the start basis, the number of pivots does — by
+//     a factor of ten.  Sources and targets are sorted along the Morton curve, the grid is coarsened by 2 x 2 cells
+//     level by level (a level's nodes are runs of the finer level's nodes), the coarsest problem (<= 64 nodes) is
+//     solved from the artificial star, and every finer level starts from the REFINEMENT of the coarser optimum:
+//     two north-west-corner passes deal the flow of each coarse arc first to the children of its source cell, then
+//     to the children of its target cell — a feasible forest with positive flows, completed to a strongly
+//     feasible spanning tree by hanging each component's first source under the root with a zero-flow
+//     artificial arc.  The finest level is the original problem, solved to optimality by the same simplex.
+//     Visium-size problems (4,992 x 3,000): ~6.5k pivots on the original problem + ~9k cheaper ones on the coarse
+//     levels instead of ~90k from the star.  STM_EMD_STAR_START selects the star (POT's start; same pivot sequence
+//     as oracle/emd_oracle.c::stm_oracle_emd for the same block size).
 #include <limits.h>
 #include <math.h>
 
@@ -26,8 +36,11 @@
 namespace stm {
 namespace {
 
-constexpr int EMD_PREP_THREADS = 256;
+constexpr int EMD_PREP_THREADS = 1024;
 constexpr int EMD_MAXPATH = 2048;
+constexpr int EMD_LV = 12;            // hierarchy levels kept (level 0 = the problem itself)
+constexpr int EMD_COARSEST = 64;      // the coarsest level solved has at most this many nodes (or is level EMD_LV - 1)
+constexpr int EMD_BIAS = 16384;       // Morton keys take coordinates relative to the source's corner in [-16384, 32768)
 #ifndef STM_EMD_T_BIG
 #define STM_EMD_T_BIG 512    // CTA size of the one-CTA-per-SM kernel: the pricing scan is issue-bound (same time at 512 or 1,024
                              // threads) while every barrier-delimited serial phase is cheaper with 16 warps: 116 vs 111 problems/s
@@ -39,15 +52,78 @@ constexpr int EMD_MAXPATH = 2048;
 constexpr int emd_rmax(int threads, bool big) { return big ? (5120 + threads - 1) / threads : 5; }
 constexpr double EMD_SCALE = 1125899906842624.0;  // 2^50
 constexpr unsigned short NONE16 = 0xffffu;
+constexpr unsigned short UNVIS16 = 0xfffeu;
+
+// One side's hierarchy in global memory: level l occupies [l * stride, l * stride + cnt[l]) of xy / mass and
+// [l * (stride + 1), ...] of child; child[l][c] .. child[l][c + 1] are the children (nodes of level l - 1) of node c.
+struct EmdHier {
+  int32_t* xy;      // {int16 x | int16 y} cell coordinates of the level, relative to the source's corner >> l
+  int64_t* mass;    // integer masses (total 2^50 on every level)
+  int32_t* child;
+  int32_t stride;
+};
+
+// per-CTA global scratch (element counts in nodes: capN = node capacity, capT = target capacity)
+struct EmdScratch {
+  int64_t* flow;      // [capN]   arc flows beyond the shared-memory part
+  int64_t* tint;      // [capT]   integer target masses in input order
+  EmdHier ht;         // target hierarchy of the problem being solved
+  uint32_t* codeA;    // [capT] Morton codes (ping)
+  uint32_t* codeB;    // [capT] (pong)
+  int32_t* tcnt;      // [EMD_LV]
+  // refinement
+  int32_t* aI; int32_t* aJ; int64_t* aF;        // [capN] coarse optimum: real arcs with positive flow
+  int32_t* offS; int32_t* curS; int32_t* lstS;  // [capN + 1], [capN + 1], [capN] arcs of every coarse source, by target
+  int32_t* offT; int32_t* curT; int32_t* lstT;  // same per coarse target (arc ranks, ascending)
+  int32_t* pcFirst;                             // [capN + 1] first piece of the arc of rank r
+  int32_t* pI; int64_t* pF;                     // [2 capN] pieces (fine source, flow)
+  int32_t* aoff;                                // [capN + 1] first fine arc of every coarse target
+  int32_t* fI; int32_t* fJ; int64_t* fF;        // [capN] fine forest
+  int32_t* tfirst;                              // [capT + 1] first fine arc of every fine target
+  unsigned short* gadj;                         // [4 capN + 16] fallback home of the tree-build adjacency
+};
+
+__host__ __device__ inline size_t emd_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// Carves a CTA's scratch out of `base` (nullptr: only the size is computed).
+__host__ __device__ inline size_t emd_scratch_layout(char* base, int64_t capN, int64_t capT, EmdScratch* s) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += emd_align16(bytes); return p; };
+  EmdScratch t;
+  t.flow = (int64_t*)take(8 * capN);
+  t.tint = (int64_t*)take(8 * capT);
+  t.ht.mass = (int64_t*)take(8 * (size_t)EMD_LV * capT);
+  t.ht.xy = (int32_t*)take(4 * (size_t)EMD_LV * capT);
+  t.ht.child = (int32_t*)take(4 * (size_t)EMD_LV * (capT + 1));
+  t.ht.stride = (int32_t)capT;
+  t.codeA = (uint32_t*)take(4 * capT);
+  t.codeB = (uint32_t*)take(4 * capT);
+  t.tcnt = (int32_t*)take(4 * EMD_LV);
+  t.aI = (int32_t*)take(4 * capN); t.aJ = (int32_t*)take(4 * capN); t.aF = (int64_t*)take(8 * capN);
+  t.offS = (int32_t*)take(4 * (capN + 1)); t.curS = (int32_t*)take(4 * (capN + 1)); t.lstS = (int32_t*)take(4 * capN);
+  t.offT = (int32_t*)take(4 * (capN + 1)); t.curT = (int32_t*)take(4 * (capN + 1)); t.lstT = (int32_t*)take(4 * capN);
+  t.pcFirst = (int32_t*)take(4 * (capN + 1));
+  t.pI = (int32_t*)take(4 * 2 * capN); t.pF = (int64_t*)take(8 * 2 * capN);
+  t.aoff = (int32_t*)take(4 * (capN + 1));
+  t.fI = (int32_t*)take(4 * capN); t.fJ = (int32_t*)take(4 * capN); t.fF = (int64_t*)take(8 * capN);
+  t.tfirst = (int32_t*)take(4 * (capT + 1));
+  t.gadj = (unsigned short*)take(2 * (4 * capN + 16));
+  if (s) *s = t;
+  return off;
+}
 
 struct EmdArgs {
   const int32_t* src_x; const int32_t* src_y; const double* src_mass; int32_t n_src;
   const int64_t* tgt_ptr; const int32_t* tgt_x; const int32_t* tgt_y; const double* tgt_mass;
   int32_t G; int32_t cap_nodes;   // shared-memory capacity in nodes
-  int32_t flow_smem_nodes;        // arc flows of nodes below this index live in shared memory, the rest in flow_ws
-  int64_t max_iter; int32_t block_size;
-  int64_t* src_int;               // [n_src] integer source masses (prep kernel)
-  int64_t* flow_ws;               // [gridDim.x][cap_nodes]
+  int32_t cap_tgt;                // largest target support of the batch
+  int32_t flow_smem_nodes;        // arc flows of nodes below this index live in shared memory, the rest in the scratch
+  int64_t max_iter; int32_t block_size; uint32_t flags;
+  // source side, built once per batch by emd_prep_kernel
+  int64_t* src_int;               // [n_src] integer source masses in input order (star start)
+  int32_t* src_hdr;               // [0, EMD_LV) node counts per level, [16] x0, [17] y0, [18] 1 = coordinates in range
+  EmdHier hs;
+  char* cta_ws; int64_t cta_ws_bytes;   // per-CTA scratch slices
   unsigned int* counter;          // dynamic problem queue
   const int32_t* order;           // optional processing order
   double* out_cost; int32_t* out_status; int64_t* out_iters;
@@ -109,10 +185,139 @@ __device__ void integerize(const double* mass, int n, int64_t* out, double* s_sc
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(EMD_PREP_THREADS) emd_prep_kernel(const double* src_mass, int n, int64_t* src_int) {
-  __shared__ double s_scr[EMD_PREP_THREADS / 32];
-  __shared__ long long s_ll[3 * EMD_PREP_THREADS / 32];
-  integerize<EMD_PREP_THREADS>(src_mass, n, src_int, s_scr, s_ll);
+__device__ __forceinline__ uint32_t morton16(uint32_t x, uint32_t y) {   // x, y < 2^16: x in the odd bits, y in the even bits
+  uint32_t a = x, b = y;
+  a = (a | (a << 8)) & 0x00ff00ffu; a = (a | (a << 4)) & 0x0f0f0f0fu; a = (a | (a << 2)) & 0x33333333u; a = (a | (a << 1)) & 0x55555555u;
+  b = (b | (b << 8)) & 0x00ff00ffu; b = (b | (b << 4)) & 0x0f0f0f0fu; b = (b | (b << 2)) & 0x33333333u; b = (b | (b << 1)) & 0x55555555u;
+  return (a << 1) | b;
+}
+
+// Bitonic sort of P (a power of two) 64-bit keys by the whole CTA; `a` may be shared or global.
+template <int T>
+__device__ void cta_bitonic_sort(unsigned long long* a, int P) {
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += T) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const bool up = (i & k) == 0;
+        const unsigned long long x = a[i], y = a[l];
+        if ((x > y) == up) { a[i] = y; a[l] = x; }
+      }
+      __syncthreads();
+    }
+}
+
+// Exclusive block scan of one int per thread; every warp recomputes the cross-warp level.  s_ws: [T / 32].
+template <int T>
+__device__ __forceinline__ int cta_excl_scan(int v, int* s_ws, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
+  __syncthreads();                       // s_ws may still be read by the previous call
+  if (lane == 31) s_ws[warp] = incl;
+  __syncthreads();
+  const int w = lane < T / 32 ? s_ws[lane] : 0;
+  int wi = w;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, wi, o); if (lane >= o) wi += t; }
+  if (total) *total = __shfl_sync(FULL_MASK, wi, 31);
+  return __shfl_sync(FULL_MASK, wi - w, warp) + incl - v;
+}
+
+// a[0 .. len) -> inclusive prefix sums, in place (a[0] = 0 and the count of item k in a[k + 1] gives offsets).
+template <int T>
+__device__ void cta_prefix_inplace(int32_t* a, int len, int* s_ws) {
+  const int per = (len + T - 1) / T;
+  const int b = min(len, (int)threadIdx.x * per), e = min(len, b + per);
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += a[i];
+  int run = cta_excl_scan<T>(sum, s_ws, nullptr);
+  for (int i = b; i < e; ++i) { run += a[i]; a[i] = run; }
+  __syncthreads();
+}
+
+// Levels 1 .. EMD_LV - 1 of one side from its level 0 (cnt0 nodes in Morton order, codes in codeA).  cnt[] receives the
+// node counts.  Whole CTA.
+template <int T>
+__device__ void build_levels(const EmdHier h, int cnt0, uint32_t* codeA, uint32_t* codeB, int32_t* cnt, int* s_ws) {
+  if (threadIdx.x == 0) cnt[0] = cnt0;
+  int pn = cnt0;
+  uint32_t* cin = codeA;
+  uint32_t* cout = codeB;
+  for (int l = 1; l < EMD_LV; ++l) {
+    const int32_t* pxy = h.xy + (size_t)(l - 1) * h.stride;
+    const int64_t* pm = h.mass + (size_t)(l - 1) * h.stride;
+    int32_t* cxy = h.xy + (size_t)l * h.stride;
+    int64_t* cm = h.mass + (size_t)l * h.stride;
+    int32_t* cch = h.child + (size_t)l * (h.stride + 1);
+    const int per = (pn + T - 1) / T;
+    const int b = min(pn, (int)threadIdx.x * per), e = min(pn, b + per);
+    int heads = 0;
+    for (int i = b; i < e; ++i) heads += (i == 0 || (cin[i] >> 2) != (cin[i - 1] >> 2)) ? 1 : 0;
+    int total = 0;
+    int c = cta_excl_scan<T>(heads, s_ws, &total);
+    for (int i = b; i < e; ++i) {
+      if (i == 0 || (cin[i] >> 2) != (cin[i - 1] >> 2)) {
+        const int xy = pxy[i];
+        const int x = ((xy << 16) >> 16) >> 1, y = (xy >> 16) >> 1;          // arithmetic shifts: cell coordinates
+        cxy[c] = (x & 0xffff) | (y << 16);
+        cout[c] = cin[i] >> 2;
+        cch[c] = i;
+        ++c;
+      }
+    }
+    if (threadIdx.x == 0) { cch[total] = pn; cnt[l] = total; }
+    __syncthreads();
+    for (int k = threadIdx.x; k < total; k += T) {
+      long long s = 0;
+      for (int i = cch[k]; i < cch[k + 1]; ++i) s += pm[i];
+      cm[k] = s;
+    }
+    __syncthreads();
+    pn = total;
+    uint32_t* t = cin; cin = cout; cout = t;
+  }
+}
+
+// Source side of a batch: integer masses, Morton order, hierarchy.  One CTA.
+__global__ void __launch_bounds__(EMD_PREP_THREADS) emd_prep_kernel(const int32_t* src_x, const int32_t* src_y, const double* src_mass,
+                                                                     int n, int64_t* src_int, unsigned long long* sortbuf, int P,
+                                                                     uint32_t* codeA, uint32_t* codeB, EmdHier hs, int32_t* hdr) {
+  constexpr int T = EMD_PREP_THREADS;
+  __shared__ double s_scr[T / 32];
+  __shared__ long long s_ll[3 * T / 32];
+  __shared__ int s_ws[T / 32];
+  __shared__ int s_box[4];
+  const int tid = threadIdx.x;
+  integerize<T>(src_mass, n, src_int, s_scr, s_ll);
+  if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MIN; s_box[2] = INT_MAX; s_box[3] = INT_MIN; }
+  __syncthreads();
+  int x0 = INT_MAX, x1 = INT_MIN, y0 = INT_MAX, y1 = INT_MIN;
+  for (int i = tid; i < n; i += T) { const int x = src_x[i], y = src_y[i]; x0 = min(x0, x); x1 = max(x1, x); y0 = min(y0, y); y1 = max(y1, y); }
+  x0 = __reduce_min_sync(FULL_MASK, x0); x1 = __reduce_max_sync(FULL_MASK, x1);
+  y0 = __reduce_min_sync(FULL_MASK, y0); y1 = __reduce_max_sync(FULL_MASK, y1);
+  if ((tid & 31) == 0) { atomicMin(&s_box[0], x0); atomicMax(&s_box[1], x1); atomicMin(&s_box[2], y0); atomicMax(&s_box[3], y1); }
+  __syncthreads();
+  x0 = s_box[0]; x1 = s_box[1]; y0 = s_box[2]; y1 = s_box[3];
+  const bool ok = (long long)x1 - x0 < 32768 && (long long)y1 - y0 < 32768;
+  if (tid == 0) { hdr[16] = x0; hdr[17] = y0; hdr[18] = ok ? 1 : 0; }
+  if (!ok) { if (tid < EMD_LV) hdr[tid] = 0; return; }
+  for (int i = tid; i < P; i += T)
+    sortbuf[i] = i < n ? ((unsigned long long)morton16((uint32_t)(src_x[i] - x0 + EMD_BIAS), (uint32_t)(src_y[i] - y0 + EMD_BIAS)) << 32) | (unsigned)i
+                       : ~0ull;
+  __syncthreads();
+  cta_bitonic_sort<T>(sortbuf, P);
+  for (int i = tid; i < n; i += T) {
+    const unsigned long long k = sortbuf[i];
+    const int o = (int)(k & 0xffffffffu);
+    codeA[i] = (uint32_t)(k >> 32);
+    hs.xy[i] = ((src_x[o] - x0) & 0xffff) | ((src_y[o] - y0) << 16);
+    hs.mass[i] = src_int[o];
+  }
+  __syncthreads();
+  build_levels<T>(hs, n, codeA, codeB, hdr, s_ws);
 }
 
 // WIDE = 64-bit potentials and reduced costs for problems whose coordinate span makes (span^2 + 1) * nodes exceed the
@@ -150,13 +355,20 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
   __shared__ int2 s_wkey[2 * EMD_WARPS];   // per-warp (reduced cost, position) of the pricing arg-min, double-buffered
   __shared__ int s_i[16];
   __shared__ int s_wsum[EMD_WARPS];
+  __shared__ int s_ws[EMD_WARPS];          // block scans of the hierarchy / refinement code
+  __shared__ int s_lv[EMD_LV];             // node counts of the target hierarchy
   __shared__ long long s_wrc64[WIDE ? 2 * EMD_WARPS : 1];   // per-warp reduced costs of the WIDE pricing arg-min
   __shared__ long long s_delta;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = p.n_src;
-  int64_t* flow = p.flow_ws + (size_t)blockIdx.x * cap;
+  // the scratch pointers are recomputed where they are needed (hierarchy, tree build, refinement) so that they do not
+  // occupy registers across the pivot loop
+  char* const cta_ws = p.cta_ws + (size_t)blockIdx.x * p.cta_ws_bytes;
+#define EMD_SCRATCH(sc) EmdScratch sc; emd_scratch_layout(cta_ws, cap, p.cap_tgt, &sc)
+  int64_t* flow;
+  { EMD_SCRATCH(sc0); flow = sc0.flow; }
   auto FL = [&](int v) -> long long& { return v < fcap ? s_flow[v] : *reinterpret_cast<long long*>(flow + v); };
+  const bool hier_ok = p.src_hdr[18] != 0;
 
   for (;;) {
     __syncthreads();
@@ -166,54 +378,255 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     if (slot >= p.G) break;
     const int g = p.order ? p.order[slot] : slot;
     const int64_t t0 = p.tgt_ptr[g];
-    const int m = (int)(p.tgt_ptr[g + 1] - t0);
-    const int N = n + m + 1, root = n + m;
-    if (m <= 0 || n <= 0) {
+    const int m0 = (int)(p.tgt_ptr[g + 1] - t0);
+    const int n0 = p.n_src;
+    if (m0 <= 0 || n0 <= 0) {
       if (tid == 0) { p.out_cost[g] = 0.0; p.out_status[g] = 2; if (p.out_iters) p.out_iters[g] = 0; }
       continue;
     }
-    // ---- stage coordinates (relative to the source's first spot), bounding box, capacity checks ----
-    const int ox = p.src_x[0], oy = p.src_y[0];
+    // ---- bounding box (relative to the source's corner), capacity checks ------------------------------------
+    const int ox = hier_ok ? p.src_hdr[16] : p.src_x[0], oy = hier_ok ? p.src_hdr[17] : p.src_y[0];
     int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
-    // N <= 30 * threads: the cycle-path scan keeps one bit per preorder position of a thread's run in a 32-bit mask
-    const bool fits = N <= cap && N < 65535 && N <= 30 * EMD_THREADS && (int64_t)n * m < 2147483647LL;
-    for (int v = tid; v < n + m; v += EMD_THREADS) {
-      const int x = v < n ? p.src_x[v] : p.tgt_x[t0 + v - n], y = v < n ? p.src_y[v] : p.tgt_y[t0 + v - n];
+    int txmin = INT_MAX, tymin = INT_MAX, txmax = INT_MIN, tymax = INT_MIN;
+    for (int v = tid; v < n0 + m0; v += EMD_THREADS) {
+      const int x = v < n0 ? p.src_x[v] : p.tgt_x[t0 + v - n0], y = v < n0 ? p.src_y[v] : p.tgt_y[t0 + v - n0];
       xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
-      if (fits) s_xy[v] = ((x - ox) & 0xffff) | ((y - oy) << 16);
+      if (v >= n0) { txmin = min(txmin, x); tymin = min(tymin, y); txmax = max(txmax, x); tymax = max(tymax, y); }
     }
     xmin = __reduce_min_sync(FULL_MASK, xmin); xmax = __reduce_max_sync(FULL_MASK, xmax);
     ymin = __reduce_min_sync(FULL_MASK, ymin); ymax = __reduce_max_sync(FULL_MASK, ymax);
-    if (lane == 0) { s_ll[3 * warp] = ((long long)xmin << 32) | (unsigned)xmax; s_ll[3 * warp + 1] = ((long long)ymin << 32) | (unsigned)ymax; }
+    txmin = __reduce_min_sync(FULL_MASK, txmin); tymin = __reduce_min_sync(FULL_MASK, tymin);
+    txmax = __reduce_max_sync(FULL_MASK, txmax); tymax = __reduce_max_sync(FULL_MASK, tymax);
+    __syncthreads();
+    if (lane == 0) {
+      s_ll[3 * warp] = ((long long)xmin << 32) | (unsigned)xmax; s_ll[3 * warp + 1] = ((long long)ymin << 32) | (unsigned)ymax;
+      s_wkey[warp] = make_int2(txmin, tymin); s_wkey[EMD_WARPS + warp] = make_int2(txmax, tymax);
+    }
     __syncthreads();
     for (int w = 0; w < EMD_WARPS; ++w) {
       xmin = min(xmin, (int)(s_ll[3 * w] >> 32)); xmax = max(xmax, (int)(unsigned)s_ll[3 * w]);
       ymin = min(ymin, (int)(s_ll[3 * w + 1] >> 32)); ymax = max(ymax, (int)(unsigned)s_ll[3 * w + 1]);
+      txmin = min(txmin, s_wkey[w].x); tymin = min(tymin, s_wkey[w].y);
+      txmax = max(txmax, s_wkey[EMD_WARPS + w].x); tymax = max(tymax, s_wkey[EMD_WARPS + w].y);
     }
     __syncthreads();
-    const long long maxc = (long long)(xmax - xmin) * (xmax - xmin) + (long long)(ymax - ymin) * (ymax - ymin);
-    const long long BIG = (maxc + 1) * (long long)N;
+    const int N0 = n0 + m0 + 1;
+    // N + 1 <= cap: the tree build keeps N + 1 offsets in one node array; N <= 30 * threads: the cycle-path scan keeps one
+    // bit per preorder position of a thread's run in a 32-bit mask
+    const bool fits = N0 + 1 <= cap && N0 < 65534 && N0 <= 30 * EMD_THREADS && (int64_t)n0 * m0 < 2147483647LL;
+    const long long maxc0 = (long long)(xmax - xmin) * (xmax - xmin) + (long long)(ymax - ymin) * (ymax - ymin);
     const bool coords_ok = (xmax - ox) < 32768 && (ox - xmin) < 32768 && (ymax - oy) < 32768 && (oy - ymin) < 32768;
     const long long pi_limit = WIDE ? (1LL << 61) : 2147483647LL;
-    if (!fits || !coords_ok || 2 * BIG + maxc >= pi_limit) {   // range of the potentials / int16 coordinates / capacity
+    if (!fits || !coords_ok || 2 * (maxc0 + 1) * (long long)N0 + maxc0 >= pi_limit) {   // potentials / int16 coordinates / capacity
       if (tid == 0) { p.out_cost[g] = nan(""); p.out_status[g] = 3; if (p.out_iters) p.out_iters[g] = 0; }
       continue;
     }
-    // ---- integer masses and the initial star basis ----------------------------------------------
-    for (int i = tid; i < n; i += EMD_THREADS) flow[i] = p.src_int[i];
-    integerize<EMD_THREADS>(p.tgt_mass + t0, m, flow + n, s_scr, s_ll);
-    for (int v = tid; v < n + m; v += EMD_THREADS) {
-      s_parent[v] = (unsigned short)root; s_order[v + 1] = (unsigned short)v; s_pos[v] = (unsigned short)(v + 1);
-      const int xy = s_xy[v], xr = (xy << 16) >> 16, yr = xy >> 16, r2 = xr * xr + yr * yr;
-      s_size[v] = 1; s_pi[v] = v < n ? (pi_t)(-BIG + r2) : (pi_t)(BIG - r2);
+    // multiscale start unless asked otherwise (or the Morton keys cannot hold the coordinates)
+    bool star = (p.flags & STM_EMD_STAR_START) != 0 || !hier_ok || (ox - txmin) > EMD_BIAS || (oy - tymin) > EMD_BIAS;
+
+    long long it_total = 0;
+    int status = 0;
+    int n = n0, m = m0, N = N0, root = n0 + m0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+    it_total = 0; status = 0;
+    int L = 1;
+    if (!star) {
+      EMD_SCRATCH(sc);
+      // ---- target hierarchy: integer masses, Morton order (sorted in the still unused tree memory), levels ----
+      integerize<EMD_THREADS>(p.tgt_mass + t0, m0, sc.tint, s_scr, s_ll);
+      unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+      int P = 1;
+      while (P < m0) P <<= 1;
+      for (int i = tid; i < P; i += EMD_THREADS)
+        keys[i] = i < m0 ? ((unsigned long long)morton16((uint32_t)(p.tgt_x[t0 + i] - ox + EMD_BIAS), (uint32_t)(p.tgt_y[t0 + i] - oy + EMD_BIAS)) << 32) | (unsigned)i
+                         : ~0ull;
+      __syncthreads();
+      cta_bitonic_sort<EMD_THREADS>(keys, P);
+      for (int i = tid; i < m0; i += EMD_THREADS) {
+        const unsigned long long k = keys[i];
+        const int o = (int)(k & 0xffffffffu);
+        sc.codeA[i] = (uint32_t)(k >> 32);
+        sc.ht.xy[i] = ((p.tgt_x[t0 + o] - ox) & 0xffff) | ((p.tgt_y[t0 + o] - oy) << 16);
+        sc.ht.mass[i] = sc.tint[o];
+      }
+      __syncthreads();
+      build_levels<EMD_THREADS>(sc.ht, m0, sc.codeA, sc.codeB, sc.tcnt, s_ws);
+      if (tid < EMD_LV) s_lv[tid] = sc.tcnt[tid];
+      __syncthreads();
+      while (L < EMD_LV && p.src_hdr[L - 1] + s_lv[L - 1] > EMD_COARSEST) ++L;
     }
-    if (tid == 0) {
-      s_order[0] = (unsigned short)root; s_pos[root] = 0; s_size[root] = (unsigned short)N; s_parent[root] = NONE16;
-      s_pi[root] = 0; flow[root] = 0; s_i[4] = 0;
+
+    for (int lev = L - 1; lev >= 0; --lev) {
+    n = star ? n0 : p.src_hdr[lev];
+    m = star ? m0 : s_lv[lev];
+    N = n + m + 1; root = n + m;
+    const bool from_forest = !star && lev < L - 1;
+    const int Ef = from_forest ? s_i[8] : 0;
+    // ---- stage the level's coordinates, its bounding box -------------------------------------------------------
+    {
+      EMD_SCRATCH(sc);
+      int bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
+      const int32_t* hsx = p.hs.xy + (size_t)lev * p.hs.stride;
+      const int32_t* htx = sc.ht.xy + (size_t)lev * sc.ht.stride;
+      for (int v = tid; v < n + m; v += EMD_THREADS) {
+        int xy;
+        if (star) {
+          const int x = v < n ? p.src_x[v] : p.tgt_x[t0 + v - n], y = v < n ? p.src_y[v] : p.tgt_y[t0 + v - n];
+          xy = ((x - ox) & 0xffff) | ((y - oy) << 16);
+        } else {
+          xy = v < n ? hsx[v] : htx[v - n];
+        }
+        s_xy[v] = xy;
+        const int x = (xy << 16) >> 16, y = xy >> 16;
+        bx0 = min(bx0, x); bx1 = max(bx1, x); by0 = min(by0, y); by1 = max(by1, y);
+      }
+      bx0 = __reduce_min_sync(FULL_MASK, bx0); bx1 = __reduce_max_sync(FULL_MASK, bx1);
+      by0 = __reduce_min_sync(FULL_MASK, by0); by1 = __reduce_max_sync(FULL_MASK, by1);
+      __syncthreads();
+      if (lane == 0) { s_wkey[warp] = make_int2(bx0, by0); s_wkey[EMD_WARPS + warp] = make_int2(bx1, by1); }
+      __syncthreads();
+      for (int w = 0; w < EMD_WARPS; ++w) {
+        bx0 = min(bx0, s_wkey[w].x); by0 = min(by0, s_wkey[w].y);
+        bx1 = max(bx1, s_wkey[EMD_WARPS + w].x); by1 = max(by1, s_wkey[EMD_WARPS + w].y);
+      }
+      __syncthreads();
+      xmin = bx0; xmax = bx1; ymin = by0; ymax = by1;
     }
-    __syncthreads();
-    for (int v = tid; v < min(fcap, N); v += EMD_THREADS) s_flow[v] = flow[v];
-    __syncthreads();
+    const long long maxc = (long long)(xmax - xmin) * (xmax - xmin) + (long long)(ymax - ymin) * (ymax - ymin);
+    const long long BIG = (maxc + 1) * (long long)N;
+    bool forest_done = false;
+    if (from_forest) {
+      EMD_SCRATCH(sc);
+      // ---- start basis from the refined forest (sc.fI / fJ / fF, Ef arcs, grouped by target in sc.tfirst) ----------
+      // adjacency for the traversal: sources CSR (soff16 / sadj16), targets = their slice of the arc list (ai16)
+      unsigned short* soff16 = s_tmp;              // [n + 1]
+      unsigned short* tf16 = s_tmp + n + 1;        // [m + 1]
+      const bool adj_smem = (size_t)fcap * 8 >= (size_t)4 * (n + 1) + (size_t)4 * Ef + 16;
+      int* deg32 = adj_smem ? reinterpret_cast<int*>(s_flow) : sc.curS;
+      unsigned short* sadj16 = adj_smem ? reinterpret_cast<unsigned short*>(deg32 + n + 1) : sc.gadj;
+      unsigned short* ai16 = sadj16 + Ef;
+      for (int v = tid; v <= n; v += EMD_THREADS) deg32[v] = 0;
+      __syncthreads();
+      for (int e = tid; e < Ef; e += EMD_THREADS) { const int i = sc.fI[e]; atomicAdd(&deg32[i + 1], 1); ai16[e] = (unsigned short)i; }
+      __syncthreads();
+      cta_prefix_inplace<EMD_THREADS>(deg32, n + 1, s_ws);
+      for (int v = tid; v <= n; v += EMD_THREADS) soff16[v] = (unsigned short)deg32[v];
+      for (int j = tid; j <= m; j += EMD_THREADS) tf16[j] = (unsigned short)sc.tfirst[j];
+      __syncthreads();
+      for (int e = tid; e < Ef; e += EMD_THREADS) sadj16[atomicAdd(&deg32[sc.fI[e]], 1)] = (unsigned short)sc.fJ[e];
+      for (int v = tid; v < N; v += EMD_THREADS) s_parent[v] = UNVIS16;
+      __syncthreads();
+      for (int v = tid; v < n; v += EMD_THREADS) {      // lists in increasing target order (deterministic layout)
+        const int a = soff16[v], b = soff16[v + 1];
+        for (int x = a + 1; x < b; ++x) {
+          const unsigned short key = sadj16[x];
+          int y = x - 1;
+          while (y >= a && sadj16[y] > key) { sadj16[y + 1] = sadj16[y]; --y; }
+          sadj16[y + 1] = key;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        // depth-first traversal from every component's lowest source: parents, preorder, potentials
+        unsigned short* stk = s_size;
+        int cnt = 0, bad = 0;
+        s_order[0] = (unsigned short)root; s_pos[root] = 0; s_parent[root] = NONE16; s_pi[root] = 0; cnt = 1;
+        for (int s0 = 0; s0 < n; ++s0) {
+          if (s_parent[s0] != UNVIS16) continue;
+          s_parent[s0] = (unsigned short)root;
+          { const int xy = s_xy[s0], xr = (xy << 16) >> 16, yr = xy >> 16; s_pi[s0] = (pi_t)(-BIG + (xr * xr + yr * yr)); }
+          int sp = 0;
+          stk[sp++] = (unsigned short)s0;
+          while (sp > 0) {
+            const int v = stk[--sp];
+            s_order[cnt] = (unsigned short)v; s_pos[v] = (unsigned short)cnt; ++cnt;
+            const int pv = s_parent[v];
+            const int xy = s_xy[v], xv = (xy << 16) >> 16, yv = xy >> 16;
+            if (v < n) {
+              const pi_t piv = s_pi[v] - (pi_t)(xv * xv + yv * yv);
+              for (int k = (int)soff16[v + 1] - 1; k >= (int)soff16[v]; --k) {
+                const int w = n + sadj16[k];
+                if (w == pv) continue;
+                if (s_parent[w] != UNVIS16) { bad = 1; continue; }
+                s_parent[w] = (unsigned short)v;
+                const int wxy = s_xy[w], xw = (wxy << 16) >> 16, yw = wxy >> 16;
+                const int dx = xv - xw, dy = yv - yw;
+                s_pi[w] = piv + (pi_t)(dx * dx + dy * dy) - (pi_t)(xw * xw + yw * yw);
+                stk[sp++] = (unsigned short)w;
+              }
+            } else {
+              const pi_t piv = s_pi[v] + (pi_t)(xv * xv + yv * yv);
+              const int j = v - n;
+              for (int k = (int)tf16[j + 1] - 1; k >= (int)tf16[j]; --k) {
+                const int w = ai16[k];
+                if (w == pv) continue;
+                if (s_parent[w] != UNVIS16) { bad = 1; continue; }
+                s_parent[w] = (unsigned short)v;
+                const int wxy = s_xy[w], xw = (wxy << 16) >> 16, yw = wxy >> 16;
+                const int dx = xv - xw, dy = yv - yw;
+                s_pi[w] = piv - (pi_t)(dx * dx + dy * dy) + (pi_t)(xw * xw + yw * yw);
+                stk[sp++] = (unsigned short)w;
+              }
+            }
+          }
+        }
+        for (int v = n; v < root; ++v)       // targets without any arc (zero integer demand): under the root, as in the star
+          if (s_parent[v] == UNVIS16) {
+            s_parent[v] = (unsigned short)root;
+            const int xy = s_xy[v], xr = (xy << 16) >> 16, yr = xy >> 16;
+            s_pi[v] = (pi_t)(BIG - (xr * xr + yr * yr));
+            s_order[cnt] = (unsigned short)v; s_pos[v] = (unsigned short)cnt; ++cnt;
+          }
+        s_i[9] = (bad == 0 && cnt == N) ? 1 : 0;
+      }
+      __syncthreads();
+      forest_done = s_i[9] != 0;
+      if (forest_done) {
+        // flows of the tree arcs (the arc of (i, j) sits in j's slice of the arc list), subtree sizes
+        for (int v = tid; v < n + m; v += EMD_THREADS) {
+          const int pr = s_parent[v];
+          long long f = 0;
+          if (pr != root) {
+            const int i = v < n ? v : pr, j = (v < n ? pr : v) - n;
+            for (int e = tf16[j]; e < (int)tf16[j + 1]; ++e)
+              if (sc.fI[e] == i) { f = sc.fF[e]; break; }
+          }
+          // the adjacency scratch shares the flow array's memory: all reads of it are done (barrier above)
+          FL(v) = f;
+          s_size[v] = 1;
+        }
+        if (tid == 0) { FL(root) = 0; s_size[root] = 1; s_i[4] = 0; }
+        __syncthreads();
+        if (tid == 0) {
+          for (int x = N - 1; x >= 1; --x) { const int v = s_order[x]; s_size[s_parent[v]] += s_size[v]; }
+        }
+        __syncthreads();
+      }
+    }
+    if (!forest_done) {
+      // ---- integer masses and the initial star basis ----------------------------------------------
+      if (star) {
+        for (int i = tid; i < n; i += EMD_THREADS) flow[i] = p.src_int[i];
+        integerize<EMD_THREADS>(p.tgt_mass + t0, m, flow + n, s_scr, s_ll);
+      } else {
+        EMD_SCRATCH(sc);
+        const int64_t* sm = p.hs.mass + (size_t)lev * p.hs.stride;
+        const int64_t* tm = sc.ht.mass + (size_t)lev * sc.ht.stride;
+        for (int v = tid; v < n + m; v += EMD_THREADS) flow[v] = v < n ? sm[v] : tm[v - n];
+      }
+      for (int v = tid; v < n + m; v += EMD_THREADS) {
+        s_parent[v] = (unsigned short)root; s_order[v + 1] = (unsigned short)v; s_pos[v] = (unsigned short)(v + 1);
+        const int xy = s_xy[v], xr = (xy << 16) >> 16, yr = xy >> 16, r2 = xr * xr + yr * yr;
+        s_size[v] = 1; s_pi[v] = v < n ? (pi_t)(-BIG + r2) : (pi_t)(BIG - r2);
+      }
+      if (tid == 0) {
+        s_order[0] = (unsigned short)root; s_pos[root] = 0; s_size[root] = (unsigned short)N; s_parent[root] = NONE16;
+        s_pi[root] = 0; flow[root] = 0; s_i[4] = 0;
+      }
+      __syncthreads();
+      for (int v = tid; v < min(fcap, N); v += EMD_THREADS) s_flow[v] = flow[v];
+      __syncthreads();
+    }
 
     const int n_arcs = n * m;
     // pricing block: LEMON uses sqrt(#arcs); a CTA prices in parallel, so larger blocks (fewer, better pivots and
@@ -225,8 +638,10 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     const bool whole_rows = !WIDE && B % n == 0 && n <= EMD_RMAX_T * EMD_THREADS;   // n_arcs and every block start are multiples of n
     int next_arc = 0;
     long long it = 0;
-    int status = 0;
     unsigned round = 0;
+    // numItermax of the reference bounds the pivots on the ORIGINAL problem (level 0); the coarse levels only construct
+    // its start basis and run to their optimum
+    const long long level_max_iter = lev == 0 ? p.max_iter : LLONG_MAX;
     __syncthreads();
 
 #ifdef STM_EMD_PROFILE
@@ -405,7 +820,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       n_scanned += scanned;
 #endif
       if (best_e < 0) break;                      // optimal
-      if (it >= p.max_iter) { status = 1; break; }
+      if (it >= level_max_iter) { status = 1; break; }
       ++it;
       const int ej = best_e / n, ei = best_e - ej * n;
       const int u_i = ei, u_j = n + ej;
@@ -558,12 +973,133 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
 #endif
     }
 #ifdef STM_EMD_PROFILE
-    if (tid == 0 && g < 2)
-      printf("[emd prof] g=%d n=%d m=%d pivots=%lld cycles/pivot: price %.0f walk %.0f leave %.0f update %.0f | arcs scanned/pivot %.0f cycle len %.1f subtree %.1f range %.1f | blocks/pivot %.2f, per block: scan %.0f reduce %.0f cycles\n",
-             g, n, m, it, (double)c_price / it, (double)c_walk / it, (double)c_leave / it, (double)c_update / it,
+    if (tid == 0 && g < 2 && it > 0)
+      printf("[emd prof] g=%d lev=%d n=%d m=%d pivots=%lld cycles/pivot: price %.0f walk %.0f leave %.0f update %.0f | arcs scanned/pivot %.0f cycle len %.1f subtree %.1f range %.1f | blocks/pivot %.2f, per block: scan %.0f reduce %.0f cycles\n",
+             g, lev, n, m, it, (double)c_price / it, (double)c_walk / it, (double)c_leave / it, (double)c_update / it,
              (double)n_scanned / it, (double)sum_len / it, (double)sum_s / it, (double)sum_range / it,
              (double)n_blocks / it, (double)c_scan / n_blocks, (double)c_red / n_blocks);
 #endif
+    it_total += it;
+    if (status != 0) break;
+    if (lev > 0) {
+      EMD_SCRATCH(sc);
+      // ---- refinement: this level's optimum -> feasible forest of level lev - 1 --------------------------------
+      // Stage 1, per coarse source I: north-west corner between its children (in order) and its arcs (by increasing
+      // target) gives pieces (fine source, arc, flow).  Stage 2, per coarse target J: north-west corner between the
+      // pieces of its arcs (by increasing source) and its children gives the fine arcs, grouped by fine target.
+      const int nS = n, nT = m;
+      const int32_t* cs = p.hs.child + (size_t)lev * (p.hs.stride + 1);
+      const int32_t* ct = sc.ht.child + (size_t)lev * (sc.ht.stride + 1);
+      const int64_t* fs = p.hs.mass + (size_t)(lev - 1) * p.hs.stride;
+      const int64_t* ft = sc.ht.mass + (size_t)(lev - 1) * sc.ht.stride;
+      const int mf = s_lv[lev - 1];
+      int Ec = 0;
+      {   // real tree arcs with positive flow, compacted in node order
+        const int per = (nS + nT + EMD_THREADS - 1) / EMD_THREADS;
+        const int b = min(nS + nT, tid * per), e = min(nS + nT, b + per);
+        int c = 0;
+        for (int v = b; v < e; ++v) c += (s_parent[v] != root && FL(v) > 0) ? 1 : 0;
+        int at = cta_excl_scan<EMD_THREADS>(c, s_ws, &Ec);
+        for (int v = b; v < e; ++v) {
+          const int pr = s_parent[v];
+          const long long f = FL(v);
+          if (pr != root && f > 0) {
+            sc.aI[at] = v < nS ? v : pr; sc.aJ[at] = (v < nS ? pr : v) - nS; sc.aF[at] = f;
+            ++at;
+          }
+        }
+      }
+      for (int k = tid; k <= nS; k += EMD_THREADS) sc.offS[k] = 0;
+      for (int k = tid; k <= nT; k += EMD_THREADS) sc.offT[k] = 0;
+      __syncthreads();
+      for (int e = tid; e < Ec; e += EMD_THREADS) { atomicAdd(&sc.offS[sc.aI[e] + 1], 1); atomicAdd(&sc.offT[sc.aJ[e] + 1], 1); }
+      __syncthreads();
+      cta_prefix_inplace<EMD_THREADS>(sc.offS, nS + 1, s_ws);
+      cta_prefix_inplace<EMD_THREADS>(sc.offT, nT + 1, s_ws);
+      for (int k = tid; k <= nS; k += EMD_THREADS) sc.curS[k] = sc.offS[k];
+      for (int k = tid; k <= nT; k += EMD_THREADS) sc.curT[k] = sc.offT[k];
+      __syncthreads();
+      for (int e = tid; e < Ec; e += EMD_THREADS) sc.lstS[atomicAdd(&sc.curS[sc.aI[e]], 1)] = e;
+      __syncthreads();
+      for (int I = tid; I < nS; I += EMD_THREADS) {      // arcs of I by increasing target
+        const int a = sc.offS[I], b = sc.offS[I + 1];
+        for (int x = a + 1; x < b; ++x) {
+          const int ke = sc.lstS[x], kj = sc.aJ[ke];
+          int y = x - 1;
+          while (y >= a && sc.aJ[sc.lstS[y]] > kj) { sc.lstS[y + 1] = sc.lstS[y]; --y; }
+          sc.lstS[y + 1] = ke;
+        }
+      }
+      if (tid == 0) sc.pcFirst[0] = 0;
+      __syncthreads();
+      // stage 1: count, offsets, write
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int I = tid; I < nS; I += EMD_THREADS) {
+          int a = cs[I];
+          const int a_end = cs[I + 1];
+          long long ra = a < a_end ? fs[a] : 0;
+          for (int r = sc.offS[I]; r < sc.offS[I + 1]; ++r) {
+            long long rb = sc.aF[sc.lstS[r]];
+            int np = pass == 0 ? 0 : sc.pcFirst[r];
+            while (rb > 0 && a < a_end) {
+              const long long f = ra < rb ? ra : rb;
+              if (f > 0) { if (pass == 1) { sc.pI[np] = a; sc.pF[np] = f; } ++np; }
+              ra -= f; rb -= f;
+              if (ra == 0) { ++a; ra = a < a_end ? fs[a] : 0; }
+            }
+            if (pass == 0) sc.pcFirst[r + 1] = np;
+          }
+        }
+        __syncthreads();
+        if (pass == 0) cta_prefix_inplace<EMD_THREADS>(sc.pcFirst, Ec + 1, s_ws);
+      }
+      // arcs (ranks in the (I, J) order) of every coarse target, by increasing source
+      for (int r = tid; r < Ec; r += EMD_THREADS) sc.lstT[atomicAdd(&sc.curT[sc.aJ[sc.lstS[r]]], 1)] = r;
+      __syncthreads();
+      for (int J = tid; J < nT; J += EMD_THREADS) {
+        const int a = sc.offT[J], b = sc.offT[J + 1];
+        for (int x = a + 1; x < b; ++x) {
+          const int key = sc.lstT[x];
+          int y = x - 1;
+          while (y >= a && sc.lstT[y] > key) { sc.lstT[y + 1] = sc.lstT[y]; --y; }
+          sc.lstT[y + 1] = key;
+        }
+      }
+      if (tid == 0) sc.aoff[0] = 0;
+      __syncthreads();
+      // stage 2: count, offsets, write
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int J = tid; J < nT; J += EMD_THREADS) {
+          int b = ct[J];
+          const int b_end = ct[J + 1];
+          long long rb = b < b_end ? ft[b] : 0;
+          int E = pass == 0 ? 0 : sc.aoff[J];
+          if (pass == 1 && b < b_end) sc.tfirst[b] = E;
+          for (int q = sc.offT[J]; q < sc.offT[J + 1]; ++q) {
+            const int r = sc.lstT[q];
+            for (int pz = sc.pcFirst[r]; pz < sc.pcFirst[r + 1]; ++pz) {
+              long long ra = sc.pF[pz];
+              while (ra > 0 && b < b_end) {
+                const long long f = ra < rb ? ra : rb;
+                if (f > 0) { if (pass == 1) { sc.fI[E] = sc.pI[pz]; sc.fJ[E] = b; sc.fF[E] = f; } ++E; }
+                ra -= f; rb -= f;
+                if (rb == 0) { ++b; rb = b < b_end ? ft[b] : 0; if (pass == 1 && b < b_end) sc.tfirst[b] = E; }
+              }
+            }
+          }
+          if (pass == 0) sc.aoff[J + 1] = E;
+          else for (int bb = b + 1; bb < b_end; ++bb) sc.tfirst[bb] = E;     // trailing children without demand
+        }
+        __syncthreads();
+        if (pass == 0) cta_prefix_inplace<EMD_THREADS>(sc.aoff, nT + 1, s_ws);
+      }
+      if (tid == 0) { const int Eall = sc.aoff[nT]; sc.tfirst[mf] = Eall; s_i[8] = Eall; }
+      __syncthreads();
+    }
+    }   // levels
+    if (status >= 4 && !star) { star = true; continue; }   // a multiscale start that hit an internal limit: redo from the star
+    break;
+    }   // attempts
     // ---- objective: real tree arcs only ------------------------------------------------------------
     double part = 0.0;
     for (int v = tid; v < n + m; v += EMD_THREADS) {
@@ -580,7 +1116,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     if (tid == 0) {
       p.out_cost[g] = total / EMD_SCALE;
       p.out_status[g] = status;
-      if (p.out_iters) p.out_iters[g] = it;
+      if (p.out_iters) p.out_iters[g] = it_total;
     }
   }
 }
@@ -589,14 +1125,38 @@ inline size_t emd_node_bytes(bool wide) { return (wide ? 8 : 4) + 4 + 5 * 2; }  
 inline size_t emd_smem_bytes(int64_t cap_nodes, int64_t flow_nodes = 0, bool wide = false) {
   return (size_t)flow_nodes * 8 + (size_t)cap_nodes * emd_node_bytes(wide) + 4 * (size_t)EMD_MAXPATH * 2 + 64;
 }
-inline int64_t emd_ws_cap(int64_t n_src, int64_t max_tgt) { return (n_src + max_tgt + 1 + 7) & ~7LL; }
+inline int64_t emd_ws_cap(int64_t n_src, int64_t max_tgt) { return (n_src + max_tgt + 2 + 7) & ~7LL; }
+inline int64_t emd_pow2(int64_t n) { int64_t p = 1; while (p < n) p <<= 1; return p; }
+
+// global part of the workspace shared by all CTAs (queue counter, source hierarchy), then the per-CTA slices
+struct EmdGlobalLayout {
+  size_t counter, hdr, src_int, sortbuf, codeA, codeB, hs_mass, hs_xy, hs_child, cta0, cta_bytes, total;
+};
+inline EmdGlobalLayout emd_global_layout(int64_t n_src, int64_t max_tgt, int64_t n_ctas) {
+  EmdGlobalLayout g;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
+  g.counter = take(256);
+  g.hdr = take(256);
+  g.src_int = take(8 * n_src);
+  g.sortbuf = take(8 * emd_pow2(n_src));
+  g.codeA = take(4 * n_src);
+  g.codeB = take(4 * n_src);
+  g.hs_mass = take(8 * (size_t)EMD_LV * n_src);
+  g.hs_xy = take(4 * (size_t)EMD_LV * n_src);
+  g.hs_child = take(4 * (size_t)EMD_LV * (n_src + 1));
+  g.cta_bytes = (emd_scratch_layout(nullptr, emd_ws_cap(n_src, max_tgt), max_tgt > 0 ? max_tgt : 1, nullptr) + 255) & ~(size_t)255;
+  g.cta0 = off;
+  g.total = off + g.cta_bytes * (size_t)n_ctas + 256;
+  return g;
+}
 
 }  // namespace
 }  // namespace stm
 
 extern "C" int64_t stm_emd_workspace_bytes(int32_t n_src, int64_t max_tgt, int32_t n_ctas) {
   if (n_src < 0 || max_tgt < 0 || n_ctas <= 0) return -1;
-  return 256 + (int64_t)n_src * 8 + (int64_t)n_ctas * stm::emd_ws_cap(n_src, max_tgt) * 8 + 256;
+  return (int64_t)stm::emd_global_layout(n_src, max_tgt, n_ctas).total;
 }
 
 namespace stm {
@@ -604,7 +1164,7 @@ namespace {
 int emd_launch(bool wide, const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
                const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
                const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
-               int64_t max_iter, int32_t block_size,
+               int64_t max_iter, int32_t block_size, uint32_t flags,
                void* workspace, int64_t workspace_bytes, int32_t n_ctas,
                double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream) {
   STM_CHECK_ARG(G >= 0, "G < 0");
@@ -613,31 +1173,44 @@ int emd_launch(bool wide, const int32_t* src_x, const int32_t* src_y, const doub
   STM_CHECK_ARG(tgt_ptr && tgt_x && tgt_y && tgt_mass && out_cost && out_status, "null pointer");
   STM_CHECK_ARG(max_tgt >= 0 && n_ctas > 0 && max_iter >= 0 && block_size >= 0, "bad size argument");
   STM_CHECK_ARG(workspace && workspace_bytes >= stm_emd_workspace_bytes(n_src, max_tgt, n_ctas), "workspace too small");
+  STM_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int dev = 0, max_optin = 0;
   STM_CHECK_CUDA(cudaGetDevice(&dev));
   STM_CHECK_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   // node capacity of one CTA: the whole tree lives in shared memory; larger problems get status 3
-  int64_t cap = emd_ws_cap(n_src, max_tgt);
+  const int64_t ws_cap = emd_ws_cap(n_src, max_tgt);
+  int64_t cap = ws_cap;
   const int64_t max_cap = (((int64_t)max_optin - 4096 - (int64_t)emd_smem_bytes(0)) / (int64_t)emd_node_bytes(wide)) & ~7LL;   // static smem + reserve
   if (cap > max_cap) cap = max_cap;
   char* ws = static_cast<char*>(workspace);
+  const EmdGlobalLayout gl = emd_global_layout(n_src, max_tgt, n_ctas);
   EmdArgs a{};
   a.src_x = src_x; a.src_y = src_y; a.src_mass = src_mass; a.n_src = n_src;
   a.tgt_ptr = tgt_ptr; a.tgt_x = tgt_x; a.tgt_y = tgt_y; a.tgt_mass = tgt_mass;
-  a.G = G; a.cap_nodes = (int32_t)cap; a.max_iter = max_iter; a.block_size = block_size;
-  a.counter = reinterpret_cast<unsigned int*>(ws);
-  a.src_int = reinterpret_cast<int64_t*>(ws + 256);
-  a.flow_ws = a.src_int + n_src;
+  a.G = G; a.cap_nodes = (int32_t)cap; a.cap_tgt = (int32_t)(max_tgt > 0 ? max_tgt : 1);
+  a.max_iter = max_iter; a.block_size = block_size; a.flags = flags;
+  a.counter = reinterpret_cast<unsigned int*>(ws + gl.counter);
+  a.src_hdr = reinterpret_cast<int32_t*>(ws + gl.hdr);
+  a.src_int = reinterpret_cast<int64_t*>(ws + gl.src_int);
+  a.hs.mass = reinterpret_cast<int64_t*>(ws + gl.hs_mass);
+  a.hs.xy = reinterpret_cast<int32_t*>(ws + gl.hs_xy);
+  a.hs.child = reinterpret_cast<int32_t*>(ws + gl.hs_child);
+  a.hs.stride = n_src;
+  a.cta_ws = ws + gl.cta0; a.cta_ws_bytes = (int64_t)gl.cta_bytes;
   a.order = order;
   a.out_cost = out_cost; a.out_status = out_status; a.out_iters = out_iters;
-  STM_CHECK_CUDA(cudaMemsetAsync(a.counter, 0, 256, st));
-  emd_prep_kernel<<<1, EMD_PREP_THREADS, 0, st>>>(src_mass, n_src, a.src_int);
+  STM_CHECK_CUDA(cudaMemsetAsync(ws + gl.counter, 0, 512, st));
+  emd_prep_kernel<<<1, EMD_PREP_THREADS, 0, st>>>(src_x, src_y, src_mass, n_src, a.src_int,
+                                                  reinterpret_cast<unsigned long long*>(ws + gl.sortbuf), (int)emd_pow2(n_src),
+                                                  reinterpret_cast<uint32_t*>(ws + gl.codeA), reinterpret_cast<uint32_t*>(ws + gl.codeB),
+                                                  a.hs, a.src_hdr);
   STM_CHECK_CUDA(cudaGetLastError());
+  // the kernel carves the scratch of a CTA with its own cap (<= ws_cap), so the slices never exceed what was sized
   const size_t tree_smem = emd_smem_bytes((int)cap, 0, wide);
   const int grid = n_ctas < G ? n_ctas : G;
-  // Problems that leave room for only one CTA per SM get 1,024 threads (pricing is the dominant phase and
-  // scales with the thread count); small problems run several 256-thread CTAs per SM.
+  // Problems that leave room for only one CTA per SM get 512 threads and the register-resident pricing path;
+  // small problems run several 256-thread CTAs per SM.
   const bool one_per_sm = tree_smem * 2 + 2048 > (size_t)max_optin;
   // what is left of a CTA's share of the SM's shared memory (without lowering the CTAs per SM) holds arc flows
   const int64_t per_sm = one_per_sm ? 1 : std::min<int64_t>(8, (int64_t)max_optin / (int64_t)(tree_smem + 1024));
@@ -662,19 +1235,19 @@ int emd_launch(bool wide, const int32_t* src_x, const int32_t* src_y, const doub
 extern "C" int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
                                      const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
                                      const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
-                                     int64_t max_iter, int32_t block_size,
+                                     int64_t max_iter, int32_t block_size, uint32_t flags,
                                      void* workspace, int64_t workspace_bytes, int32_t n_ctas,
                                      double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream) {
   return stm::emd_launch(false, src_x, src_y, src_mass, n_src, tgt_ptr, tgt_x, tgt_y, tgt_mass, G, max_tgt, order, max_iter,
-                         block_size, workspace, workspace_bytes, n_ctas, out_cost, out_status, out_iters, stream);
+                         block_size, flags, workspace, workspace_bytes, n_ctas, out_cost, out_status, out_iters, stream);
 }
 
 extern "C" int stm_emd_spots_batched_wide(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
                                           const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
                                           const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,
-                                          int64_t max_iter, int32_t block_size,
+                                          int64_t max_iter, int32_t block_size, uint32_t flags,
                                           void* workspace, int64_t workspace_bytes, int32_t n_ctas,
                                           double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream) {
   return stm::emd_launch(true, src_x, src_y, src_mass, n_src, tgt_ptr, tgt_x, tgt_y, tgt_mass, G, max_tgt, order, max_iter,
-                         block_size, workspace, workspace_bytes, n_ctas, out_cost, out_status, out_iters, stream);
+                         block_size, flags, workspace, workspace_bytes, n_ctas, out_cost, out_status, out_iters, stream);
 }

@@ -39,7 +39,7 @@ def test_emd_batch_matches_oracle_and_pivot_sequence(cuda_device, n, ms, R):
     src, tg = _random_problem(np.random.default_rng(n), n, ms, R)
     # default block size: optimum must agree
     cost0, status0 = emd_batched(src, tg)
-    cost, status, iters = emd_batched(src, tg, block_size=777, return_iters=True)
+    cost, status, iters = emd_batched(src, tg, block_size=777, return_iters=True, star_start=True)
     for g, t in enumerate(tg):
         c, st, it = eo.emd_network_simplex(*src, *t, block_size=777)
         assert status0[g] == 0 and abs(cost0[g] - c) <= 1e-12 * max(1.0, c)
@@ -51,8 +51,8 @@ def test_emd_batch_matches_oracle_and_pivot_sequence(cuda_device, n, ms, R):
 def test_emd_iteration_limit_and_empty(cuda_device):
     from stminer_b200.Algorithm.distance import emd_batched
     src, tg = _random_problem(np.random.default_rng(3), 282, [150], 17)
-    full, st, it = emd_batched(src, tg, block_size=500, return_iters=True)
-    cut, st1, it1 = emd_batched(src, tg, max_iter=int(it[0]) // 2, block_size=500, return_iters=True)
+    full, st, it = emd_batched(src, tg, block_size=500, return_iters=True, star_start=True)
+    cut, st1, it1 = emd_batched(src, tg, max_iter=int(it[0]) // 2, block_size=500, return_iters=True, star_start=True)
     ref, rst, rit = eo.emd_network_simplex(*src, *tg[0], max_iter=int(it[0]) // 2, block_size=500)
     assert st[0] == 0 and st1[0] == 1 and rst == 1 and it1[0] == rit
     assert abs(cut[0] - ref) <= 1e-12 * ref          # same sub-optimal basis as the oracle (POT semantics)
@@ -103,7 +103,7 @@ def test_emd_one_dimensional_images_deep_trees(cuda_device, n, m):
     tx = np.sort(rng.choice(span, size=m, replace=False)).astype(np.int32)
     src = (sx, np.zeros(n, dtype=np.int32), rng.gamma(2.0, 1.0, n) + 0.05)
     tgt = (tx, np.full(m, 3, dtype=np.int32), rng.gamma(2.0, 1.0, m) + 0.05)
-    cost, status, iters = emd_batched(src, [tgt], return_iters=True, block_size=4 * n)
+    cost, status, iters = emd_batched(src, [tgt], return_iters=True, block_size=4 * n, star_start=True)
     c, st, it = eo.emd_network_simplex(*src, *tgt, block_size=4 * n)
     assert status[0] == st == 0 and iters[0] == it
     assert abs(cost[0] - c) <= 1e-12 * max(1.0, c)
@@ -130,7 +130,7 @@ def test_emd_batch_mixes_int32_and_64bit_problems(cuda_device):
     src, tg = _random_problem(rng, 300, [200, 150, 260], 40)
     far = (tg[1][0] + 3000, tg[1][1] + 1700, tg[1][2])
     targets = [tg[0], far, tg[2]]
-    cost, status, iters = emd_batched(src, targets, block_size=500, return_iters=True)
+    cost, status, iters = emd_batched(src, targets, block_size=500, return_iters=True, star_start=True)
     for g, t in enumerate(targets):
         c, st, it = eo.emd_network_simplex(*src, *t, block_size=500)
         assert status[g] == st == 0 and iters[g] == it, g
@@ -146,9 +146,68 @@ def test_emd_one_cta_per_sm_kernel_matches_oracle(cuda_device):
     n, m, R = 3600, 2200, 60
     src, tg = _random_problem(rng, n, [m], R)
     B = 9 * n
-    cost, status, iters = emd_batched(src, tg, block_size=B, return_iters=True)
+    cost, status, iters = emd_batched(src, tg, block_size=B, return_iters=True, star_start=True)
     c, st, it = eo.emd_network_simplex(*src, *tg[0], block_size=B)
     assert status[0] == st == 0 and iters[0] == it
     assert abs(cost[0] - c) <= 1e-12 * max(1.0, c)
     cost_d, status_d = emd_batched(src, tg)                       # the kernel's own default block size: same optimum
     assert status_d[0] == 0 and abs(cost_d[0] - c) <= 1e-12 * max(1.0, c)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# multiscale start basis (the default): same optimum, and the same pivots as the oracle's restatement of the scheme
+# ---------------------------------------------------------------------------------------------------------------------
+GOLD_LARGE = os.path.join(os.path.dirname(__file__), "golden", "emd_large.npz")
+
+
+@pytest.mark.parametrize("n,ms,R,B", [(282, [150, 282, 31, 1, 90], 17, 777), (1200, [700, 400, 1100], 40, 5000),
+                                      (50, list(range(1, 40, 3)), 8, 100), (3600, [2200, 900], 60, 9 * 3600)])
+def test_emd_multiscale_matches_oracle_levels(cuda_device, n, ms, R, B):
+    """Default start (Morton hierarchy, coarse-to-fine refinement): cost, status and the pivot count over all levels
+    equal the oracle's stm_oracle_emd_ms for the same block size; the optimum equals the star start's."""
+    from stminer_b200.Algorithm.distance import emd_batched
+    src, tg = _random_problem(np.random.default_rng(n + 1), n, ms, R)
+    cost, status, iters = emd_batched(src, tg, block_size=B, return_iters=True)
+    cost_d, status_d = emd_batched(src, tg)                                # the kernel's default block sizes
+    for g, t in enumerate(tg):
+        c, st, it, lev = eo.emd_multiscale(*src, *t, block_size=B)
+        c_star, st_star, _ = eo.emd_network_simplex(*src, *t)
+        assert status[g] == st == 0 and status_d[g] == 0 and st_star == 0
+        assert iters[g] == it, (g, iters[g], it, lev[:8])
+        assert abs(cost[g] - c) <= 1e-12 * max(1.0, c)
+        assert abs(cost[g] - c_star) <= 1e-11 * max(1.0, c_star)
+        assert abs(cost_d[g] - c_star) <= 1e-11 * max(1.0, c_star)
+
+
+def test_emd_multiscale_iteration_limit_applies_to_the_problem_itself(cuda_device):
+    """numItermax bounds the pivots on the original problem (finest level); the coarse levels always run to their
+    optimum.  Same sub-optimal basis cost as the oracle, status 1."""
+    from stminer_b200.Algorithm.distance import emd_batched
+    src, tg = _random_problem(np.random.default_rng(3), 600, [400], 30)
+    c_full, st_full, it_full, lev = eo.emd_multiscale(*src, *tg[0], block_size=900)
+    assert st_full == 0 and lev[0] > 20
+    cap = int(lev[0]) // 2
+    cut, st1, it1 = emd_batched(src, tg, max_iter=cap, block_size=900, return_iters=True)
+    c_cut, st_cut, it_cut, lev_cut = eo.emd_multiscale(*src, *tg[0], max_iter=cap, block_size=900)
+    assert st1[0] == st_cut == 1 and lev_cut[0] == cap and it1[0] == it_cut
+    assert abs(cut[0] - c_cut) <= 1e-12 * c_cut and cut[0] > c_full
+
+
+def test_emd_visium_size_matches_independent_lp_golden(cuda_device):
+    """Visium-size problems (4,992 source spots x 800-3,300 target spots) against optima computed by HiGHS through
+    column generation with a full n x m dual-feasibility certificate (tests/golden/make_golden_emd_large.py) — an
+    independent solver, neither the kernel nor oracle/emd_oracle.c.  Both start bases; rtol 1e-7 = the LP solver's
+    feasibility tolerance (the north-star bar for global_distance is rtol 1e-4)."""
+    from stminer_b200.Algorithm.distance import emd_batched
+    z = np.load(GOLD_LARGE)
+    for c in range(int(z["n"])):
+        p = "c%d_" % c
+        src = (z[p + "sx"], z[p + "sy"], z[p + "sm"]); tgt = (z[p + "tx"], z[p + "ty"], z[p + "tm"])
+        ref = float(z[p + "cost"])
+        cost, status = emd_batched(src, [tgt])
+        if status[0] == 3 and len(src[0]) + len(tgt[0]) > 11000:
+            continue                                                      # beyond one CTA: covered by the large-problem test
+        assert status[0] == 0, (c, status)
+        assert abs(cost[0] - ref) <= 1e-7 * ref, (c, cost[0], ref)
+        cost_s, status_s = emd_batched(src, [tgt], star_start=True)
+        assert status_s[0] == 0 and abs(cost_s[0] - cost[0]) <= 1e-11 * ref

@@ -61,3 +61,27 @@ def test_calculate_ot_distance_staging_and_properties():
     d1 = eo.calculate_ot_distance(a, csr_matrix(b_img))
     d2 = eo.calculate_ot_distance(csr_matrix(7.5 * img), csr_matrix(0.2 * b_img))
     assert abs(d1 - d2) < 1e-9 * d1
+
+
+GOLD_LARGE = os.path.join(os.path.dirname(__file__), "golden", "emd_large.npz")
+
+
+@pytest.mark.parametrize("c,d", list(cases()))
+def test_multiscale_start_reaches_the_same_optimum(c, d):
+    cost, status, pivots, lev = eo.emd_multiscale(d["sx"], d["sy"], d["sm"], d["tx"], d["ty"], d["tm"])
+    assert status == 0 and pivots == lev.sum()
+    assert abs(cost - float(d["cost"])) <= 1e-9 * max(1.0, float(d["cost"]))
+    cost2, status2, _, _ = eo.emd_multiscale(d["sx"], d["sy"], d["sm"], d["tx"], d["ty"], d["tm"], block_size=23)
+    assert status2 == 0 and abs(cost2 - cost) <= 1e-11 * max(1.0, cost)
+
+
+def test_oracle_matches_visium_size_lp_golden():
+    """The oracle (multiscale start; the star start takes ~10 s per problem) against the independent Visium-size LP
+    optima of tests/golden/emd_large.npz (HiGHS + column generation + full dual-feasibility certificate)."""
+    z = np.load(GOLD_LARGE)
+    for c in range(int(z["n"])):
+        p = "c%d_" % c
+        cost, status, pivots, lev = eo.emd_multiscale(z[p + "sx"], z[p + "sy"], z[p + "sm"], z[p + "tx"], z[p + "ty"], z[p + "tm"])
+        ref = float(z[p + "cost"])
+        assert status == 0
+        assert abs(cost - ref) <= 1e-7 * ref, (c, cost, ref)
