@@ -430,6 +430,9 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     for (int attempt = 0; attempt < 2; ++attempt) {
     it_total = 0; status = 0;
     int L = 1;
+#ifdef STM_EMD_PROFILE
+    const long long c_h0 = clock64();
+#endif
     if (!star) {
       EMD_SCRATCH(sc);
       // ---- target hierarchy: integer masses, Morton order (sorted in the still unused tree memory), levels ----
@@ -456,7 +459,13 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       while (L < EMD_LV && p.src_hdr[L - 1] + s_lv[L - 1] > EMD_COARSEST) ++L;
     }
 
+#ifdef STM_EMD_PROFILE
+    if (tid == 0 && g < 2) printf("[emd prof] g=%d hierarchy %lld cycles, %d levels\n", g, (long long)(clock64() - c_h0), L);
+#endif
     for (int lev = L - 1; lev >= 0; --lev) {
+#ifdef STM_EMD_PROFILE
+    const long long c_l0 = clock64();
+#endif
     n = star ? n0 : p.src_hdr[lev];
     m = star ? m0 : s_lv[lev];
     N = n + m + 1; root = n + m;
@@ -631,7 +640,9 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     const int n_arcs = n * m;
     // pricing block: LEMON uses sqrt(#arcs); a CTA prices in parallel, so larger blocks (fewer, better pivots and
     // fewer barriers per arc) win — 32 arcs per thread measured best on Visium-size problems
-    int B = p.block_size > 0 ? p.block_size : max((int)sqrt((double)n_arcs), ONE_PER_SM ? 32768 : 32 * EMD_THREADS);
+    // on the problem itself; coarse levels (few arcs in all) price a sixteenth of their arcs, at least 4,096
+    int B = p.block_size > 0 ? p.block_size
+                             : max((int)sqrt((double)n_arcs), min(ONE_PER_SM ? 32768 : 32 * EMD_THREADS, max(4096, n_arcs / 16)));
     if (p.block_size <= 0 && n <= EMD_RMAX_T * EMD_THREADS) B = max(1, (B + n / 2) / n) * n;   // whole target rows
     if (B < 10) B = 10;
     if (B > n_arcs) B = n_arcs;
@@ -643,6 +654,9 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     // its start basis and run to their optimum
     const long long level_max_iter = lev == 0 ? p.max_iter : LLONG_MAX;
     __syncthreads();
+#ifdef STM_EMD_PROFILE
+    const long long c_l1 = clock64();
+#endif
 
 #ifdef STM_EMD_PROFILE
     long long c_price = 0, c_walk = 0, c_leave = 0, c_update = 0, n_scanned = 0, c_t0 = 0, sum_len = 0, sum_s = 0, sum_range = 0;
@@ -678,23 +692,36 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
             // Fast path (the default block size is a whole number of target rows): every thread keeps ITS sources'
             // terms in registers for the whole block and meets each target row with no shared-memory traffic
             // beyond the row's three broadcast words — six integer instructions per arc.
+            // Layout by level size: the CTA splits into `groups` row groups of `teff` threads; a group's thread ti owns
+            // sources ti, ti + teff, ... (all EMD_RMAX_T register slots: the per-row overhead — three shared words, the
+            // unpacking, the loop — is amortised over as many arcs as possible) and the groups share the block's rows
+            // (rows gidx, gidx + groups, ...), so the small coarse levels of the multiscale start use all lanes too.
             int sx[EMD_RMAX_T], sy[EMD_RMAX_T], sp[EMD_RMAX_T];
+            const int teff = (((n + EMD_RMAX_T - 1) / EMD_RMAX_T) + 31) & ~31;
+            const int groups = EMD_THREADS / teff;
+            const int gidx = tid / teff;
+            const int i0 = tid - gidx * teff;
 #pragma unroll
             for (int r = 0; r < EMD_RMAX_T; ++r) {
-              const int i = tid + r * EMD_THREADS;
-              const int xy = i < n ? s_xy[i] : 0;
+              const int i = i0 + r * teff;
+              const bool valid = i < n && gidx < groups;
+              const int xy = valid ? s_xy[i] : 0;
               sx[r] = (xy << 16) >> 16; sy[r] = xy >> 16;
-              sp[r] = i < n ? s_pi[i] : INT_MAX / 2;     // never the minimum
+              sp[r] = valid ? s_pi[i] : INT_MAX / 2;     // never the minimum
             }
             // The scan only tracks the thread's minimum (an add, two IMADs and a share of a 3-input min per arc); the
             // arc that attains the block minimum is located afterwards by the few threads whose minimum equals it.
             const int j0 = next_arc / n;
-            int j = j0;
-            for (int rr = cnt / n; rr > 0; --rr) {
+            const int rows = cnt / n;
+            const int rr0 = gidx < groups ? gidx : rows;       // lanes beyond the last row group sit the block out
+            int j = j0 + gidx;
+            while (j >= m) j -= m;
+            for (int rr = rr0; rr < rows; rr += groups) {
               const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
 #pragma unroll
               for (int r = 0; r < EMD_RMAX_T; ++r) brc = min(brc, sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj)));
-              if (++j >= m) j = 0;
+              j += groups;
+              while (j >= m) j -= m;
             }
             // ---- level 1: the block's most negative reduced cost --------------------------------------------
             {
@@ -709,19 +736,21 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
               // ---- level 2: its first position in block order (rows from the block start, sources ascending) ----
               unsigned myk = 0xffffffffu;
               if (brc == g_rc) {
-                j = j0;
-                for (int rr = cnt / n; rr > 0 && myk == 0xffffffffu; --rr) {
+                j = j0 + gidx;
+                while (j >= m) j -= m;
+                for (int rr = rr0; rr < rows && myk == 0xffffffffu; rr += groups) {
                   const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
 #pragma unroll
                   for (int r = 0; r < EMD_RMAX_T; ++r) {
                     const int rc = sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj));
                     if (rc == g_rc && myk == 0xffffffffu) {
-                      int k = j * n + tid + r * EMD_THREADS - next_arc;
+                      int k = j * n + i0 + r * teff - next_arc;
                       if (k < 0) k += n_arcs;
                       myk = (unsigned)k;
                     }
                   }
-                  if (++j >= m) j = 0;
+                  j += groups;
+                  while (j >= m) j -= m;
                 }
               }
               const unsigned w_k = __reduce_min_sync(FULL_MASK, myk);
@@ -980,6 +1009,9 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
              (double)n_blocks / it, (double)c_scan / n_blocks, (double)c_red / n_blocks);
 #endif
     it_total += it;
+#ifdef STM_EMD_PROFILE
+    const long long c_l2 = clock64();
+#endif
     if (status != 0) break;
     if (lev > 0) {
       EMD_SCRATCH(sc);
@@ -1096,6 +1128,11 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       if (tid == 0) { const int Eall = sc.aoff[nT]; sc.tfirst[mf] = Eall; s_i[8] = Eall; }
       __syncthreads();
     }
+#ifdef STM_EMD_PROFILE
+    if (tid == 0 && g < 2)
+      printf("[emd prof] g=%d lev=%d nodes %d: basis %lld, simplex %lld (%lld pivots), refine %lld cycles\n", g, lev, N,
+             (long long)(c_l1 - c_l0), (long long)(c_l2 - c_l1), it, (long long)(clock64() - c_l2));
+#endif
     }   // levels
     if (status >= 4 && !star) { star = true; continue; }   // a multiscale start that hit an internal limit: redo from the star
     break;
