@@ -171,6 +171,8 @@ int stm_gmm_dist_one_vs_all(const double* qw, const double* qmu, const double* q
  *     2 empty image, 3 problem does not fit one CTA's shared memory / int16 coordinate span / the range of the
  *     potentials (out_cost = NaN), 4-5 internal limits (cycle longer than 2048 arcs, unbounded ray).
  *
+ * A batch whose largest problem exceeds a CTA's shared memory is solved with the tree in global memory (see
+ * stm_emd_smem_node_capacity), whichever of the two entry points is called.
  * stm_emd_spots_batched keeps int32 potentials (18 B of shared memory per node, problems up to ~11.9k nodes); it needs
  * 2 * (span_x^2 + span_y^2 + 1) * (n + m + 1) < 2^31 and reports status 3 otherwise.  stm_emd_spots_batched_wide is the
  * same solver (same pivot sequence) with 64-bit potentials for problems beyond that bound — scattered integer
@@ -178,6 +180,12 @@ int stm_gmm_dist_one_vs_all(const double* qw, const double* qmu, const double* q
  */
 #define STM_EMD_STAR_START 1u
 int64_t stm_emd_workspace_bytes(int32_t n_src, int64_t max_tgt, int32_t n_ctas);
+/* Largest n + m + 1 a batch may reach and still run with the tree in shared memory (wide = the 64-bit kernel) on the
+ * current device; a batch beyond it (n_src + max_tgt + 1) runs the same solver with the tree in the CTA's global scratch
+ * (one CTA per SM, 64-bit potentials, ~10x slower per pivot) up to stm_emd_global_node_capacity() nodes — Stereo-seq
+ * bin50 slides (40,000 source bins).  Callers that mix sizes should batch the small problems separately. */
+int32_t stm_emd_smem_node_capacity(int32_t wide);
+int32_t stm_emd_global_node_capacity(void);
 int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
                           const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,
                           const double* tgt_mass, int32_t G, int64_t max_tgt, const int32_t* order,

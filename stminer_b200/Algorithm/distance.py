@@ -178,24 +178,37 @@ def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, devic
     d = [up(a) for a in (sx, sy, sm, ptr, tx, ty, tm)]
     with torch.cuda.device(device):
         props = torch.cuda.get_device_properties(device)
-        cost = torch.empty(G, dtype=torch.float64, device=device)
-        status = torch.empty(G, dtype=torch.int32, device=device)
-        iters = torch.empty(G, dtype=torch.int64, device=device)
+        cost = torch.full((G,), float("nan"), dtype=torch.float64, device=device)
+        status = torch.full((G,), 3, dtype=torch.int32, device=device)
+        iters = torch.zeros(G, dtype=torch.int64, device=device)
+        # size classes: tree in shared memory (int32 / int64 potentials), or — beyond one CTA's shared memory, e.g. a
+        # Stereo-seq bin50 slide with 40,000 source bins — in the CTA's global scratch; problems beyond that keep status 3
+        nodes = len(sx) + sizes + 1
+        cap_n, cap_w = int(lib.stm_emd_smem_node_capacity(0)), int(lib.stm_emd_smem_node_capacity(1))
+        cap_g = int(lib.stm_emd_global_node_capacity())
+        arcs_ok = len(sx) * sizes < 2 ** 31 - 1
+        small_n = narrow & (nodes <= cap_n)
+        small_w = ~narrow & (nodes <= cap_w)
+        large = ~small_n & ~small_w & (nodes <= cap_g) & arcs_ok
         keep = []
-        for wide, sel in ((False, np.flatnonzero(narrow)), (True, np.flatnonzero(~narrow))):
+        for wide, sel, big in ((False, np.flatnonzero(small_n), False), (True, np.flatnonzero(small_w), False),
+                               (True, np.flatnonzero(large), True)):
             if len(sel) == 0:
                 continue
             order = sel[np.argsort(-sizes[sel], kind="stable")].astype(np.int32)      # largest problems first
             d_order = up(order)
-            nodes = len(sx) + int(sizes[sel].max()) + 1
-            smem = nodes * (22 if wide else 18) + 4 * 2048 * 2 + 64 + 1024
-            per_sm = max(1, min(8, (227 * 1024) // smem))
-            n_ctas = int(min(len(sel), props.multi_processor_count * per_sm))
-            ws_bytes = int(lib.stm_emd_workspace_bytes(len(sx), max_tgt, n_ctas))
+            call_max_tgt = int(sizes[sel].max())
+            if big:
+                n_ctas = int(min(len(sel), props.multi_processor_count))
+            else:
+                smem = (len(sx) + call_max_tgt + 10) * (22 if wide else 18) + 4 * 2048 * 2 + 64 + 1024
+                per_sm = max(1, min(8, (227 * 1024) // smem))
+                n_ctas = int(min(len(sel), props.multi_processor_count * per_sm))
+            ws_bytes = int(lib.stm_emd_workspace_bytes(len(sx), call_max_tgt, n_ctas))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
             fn = lib.stm_emd_spots_batched_wide if wide else lib.stm_emd_spots_batched
             st = fn(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), len(sx), _lib.ptr(d[3]),
-                    _lib.ptr(d[4]), _lib.ptr(d[5]), _lib.ptr(d[6]), len(sel), int(sizes[sel].max()), _lib.ptr(d_order),
+                    _lib.ptr(d[4]), _lib.ptr(d[5]), _lib.ptr(d[6]), len(sel), call_max_tgt, _lib.ptr(d_order),
                     int(max_iter), int(block_size), _lib.STM_EMD_STAR_START if star_start else 0,
                     _lib.ptr(ws), ws_bytes, n_ctas,
                     _lib.ptr(cost), _lib.ptr(status), _lib.ptr(iters), _lib.current_stream_ptr())

@@ -30,6 +30,7 @@ CONFIGS = {
     "T": (17, 17, False, 15, 20),          # stand-in for the reference test path (282 bins, ~300 genes)
     "V": (78, 128, True, 20, 100),         # Visium-shaped: 4,992 spots x 2,000 genes
     "S50": (200, 200, False, 100, 100),    # Stereo-seq bin50: 40,000 bins x 10,000 genes
+    "R32": (32, 32, False, 27, 20),        # 1,024 bins x 540 genes: the smallest set with a top-500 SVG ranking
 }
 
 

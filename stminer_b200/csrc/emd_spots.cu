@@ -37,7 +37,15 @@ namespace stm {
 namespace {
 
 constexpr int EMD_PREP_THREADS = 1024;
-constexpr int EMD_MAXPATH = 2048;
+constexpr int EMD_MAXPATH_S = 2048;     // longest cycle path kept, shared-memory tree
+constexpr int EMD_MAXPATH_G = 8192;     // global-memory tree
+constexpr int EMD_SCAN_CH_G = 8;        // global tree: up to 30 * 8 * threads nodes
+constexpr int EMD_ROWS_G = 64;          // most target rows of a pricing block of the global-tree kernel
+constexpr int EMD_ROWS_MIN_G = 4;       // and the fewest (when the target has that many)
+constexpr int EMD_RG_G = 8;             // sources per thread and tile in its pricing
+constexpr int EMD_GLOBAL_THREADS = 512;
+constexpr int64_t EMD_GLOBAL_ALLOC_NODES = 9000;
+constexpr int64_t EMD_GLOBAL_MAX_NODES = 30LL * EMD_SCAN_CH_G * EMD_GLOBAL_THREADS;   // 122,880
 constexpr int EMD_LV = 12;            // hierarchy levels kept (level 0 = the problem itself)
 constexpr int EMD_COARSEST = 64;      // the coarsest level solved has at most this many nodes (or is level EMD_LV - 1)
 constexpr int EMD_BIAS = 16384;       // Morton keys take coordinates relative to the source's corner in [-16384, 32768)
@@ -80,13 +88,15 @@ struct EmdScratch {
   int32_t* aoff;                                // [capN + 1] first fine arc of every coarse target
   int32_t* fI; int32_t* fJ; int64_t* fF;        // [capN] fine forest
   int32_t* tfirst;                              // [capT + 1] first fine arc of every fine target
-  unsigned short* gadj;                         // [4 capN + 16] fallback home of the tree-build adjacency
+  uint32_t* gadj;                               // [4 capN + 16] fallback home of the tree-build adjacency
+  unsigned long long* sortbuf;                  // global tree only: [pow2(capT)] Morton sort keys of the targets
+  char* gtree;                                  // global tree only: potentials, coordinates, five index arrays (32 B per node)
 };
 
 __host__ __device__ inline size_t emd_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // Carves a CTA's scratch out of `base` (nullptr: only the size is computed).
-__host__ __device__ inline size_t emd_scratch_layout(char* base, int64_t capN, int64_t capT, EmdScratch* s) {
+__host__ __device__ inline size_t emd_scratch_layout(char* base, int64_t capN, int64_t capT, EmdScratch* s, bool global_tree) {
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += emd_align16(bytes); return p; };
   EmdScratch t;
@@ -107,7 +117,14 @@ __host__ __device__ inline size_t emd_scratch_layout(char* base, int64_t capN, i
   t.aoff = (int32_t*)take(4 * (capN + 1));
   t.fI = (int32_t*)take(4 * capN); t.fJ = (int32_t*)take(4 * capN); t.fF = (int64_t*)take(8 * capN);
   t.tfirst = (int32_t*)take(4 * (capT + 1));
-  t.gadj = (unsigned short*)take(2 * (4 * capN + 16));
+  t.gadj = (uint32_t*)take(4 * (4 * capN + 16));
+  t.sortbuf = nullptr; t.gtree = nullptr;
+  if (global_tree) {
+    int64_t P = 1;
+    while (P < capT) P <<= 1;
+    t.sortbuf = (unsigned long long*)take(8 * P);
+    t.gtree = take((size_t)capN * 32);
+  }
   if (s) *s = t;
   return off;
 }
@@ -323,11 +340,22 @@ __global__ void __launch_bounds__(EMD_PREP_THREADS) emd_prep_kernel(const int32_
 // WIDE = 64-bit potentials and reduced costs for problems whose coordinate span makes (span^2 + 1) * nodes exceed the
 // int32 range of the default kernel (scattered integer coordinates, long thin tissues): 22 instead of 18 bytes of shared
 // memory per node and the general (non register-resident) pricing path, same pivot sequence.
-template <int EMD_THREADS, bool WIDE, bool ONE_PER_SM>
+//
+// GLOBAL = the tree (potentials, coordinates, parent / position / size / preorder arrays, 32-bit node indices) lives in the
+// CTA's global scratch (L2) instead of shared memory: problems beyond one CTA's shared memory — Stereo-seq bin50 slides,
+// 40,000 source bins — up to EMD_GLOBAL_MAX_NODES nodes.  Shared memory then holds arc flows and the cycle paths; pricing
+// keeps a tile of sources in registers and meets the block's target rows staged in shared memory.  Same algorithm, same
+// pivot rules; implies WIDE.
+template <int EMD_THREADS, bool WIDE, bool ONE_PER_SM, bool GLOBAL = false>
 __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMALL) emd_kernel(const EmdArgs p) {
+  static_assert(!GLOBAL || (WIDE && ONE_PER_SM), "the global-tree variant uses 64-bit potentials and one CTA per SM");
   constexpr int EMD_WARPS = EMD_THREADS / 32;
   constexpr int EMD_RMAX_T = emd_rmax(EMD_THREADS, ONE_PER_SM);
+  constexpr int EMD_MAXPATH = GLOBAL ? EMD_MAXPATH_G : EMD_MAXPATH_S;
+  constexpr int SCAN_CH = GLOBAL ? EMD_SCAN_CH_G : 1;        // 32-position chunks of a thread's run in the cycle-path scan
   using pi_t = typename std::conditional<WIDE, long long, int>::type;
+  using idx_t = typename std::conditional<GLOBAL, uint32_t, unsigned short>::type;
+  constexpr idx_t NONE16 = (idx_t)~(idx_t)0, UNVIS16 = (idx_t)(NONE16 - 1);
   constexpr pi_t PI_NONE = WIDE ? (pi_t)LLONG_MAX : (pi_t)INT_MAX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap = p.cap_nodes;
@@ -339,17 +367,27 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
   // shared-memory instead of L2 latency
   const int fcap = p.flow_smem_nodes;
   long long* s_flow = reinterpret_cast<long long*>(smem_raw);           // [fcap]
-  pi_t* s_pi = reinterpret_cast<pi_t*>(s_flow + fcap);                   // [cap]
-  int* s_xy = reinterpret_cast<int*>(s_pi + cap);                        // [cap] {int16 x | int16 y}
-  unsigned short* s_parent = reinterpret_cast<unsigned short*>(s_xy + cap);
-  unsigned short* s_pos = s_parent + cap;
-  unsigned short* s_size = s_pos + cap;
-  unsigned short* s_order = s_size + cap;
-  unsigned short* s_tmp = s_order + cap;
-  unsigned short* s_pathA = s_tmp + cap;                                 // [EMD_MAXPATH]
-  unsigned short* s_pathB = s_pathA + EMD_MAXPATH;
-  unsigned short* s_P = s_pathB + EMD_MAXPATH;
-  unsigned short* s_S = s_P + EMD_MAXPATH;
+  char* const cta_ws = p.cta_ws + (size_t)blockIdx.x * p.cta_ws_bytes;
+  pi_t* s_pi; int* s_xy; idx_t *s_parent, *s_pos, *s_size, *s_order, *s_tmp, *s_pathA;
+  if constexpr (GLOBAL) {
+    EmdScratch sct; emd_scratch_layout(cta_ws, cap, p.cap_tgt, &sct, true);
+    s_pi = reinterpret_cast<pi_t*>(sct.gtree);                           // [cap] int64
+    s_xy = reinterpret_cast<int*>(s_pi + cap);                           // [cap]
+    s_parent = reinterpret_cast<idx_t*>(s_xy + cap);
+    s_pathA = reinterpret_cast<idx_t*>(s_flow + fcap);                   // paths stay in shared memory
+  } else {
+    s_pi = reinterpret_cast<pi_t*>(s_flow + fcap);                       // [cap]
+    s_xy = reinterpret_cast<int*>(s_pi + cap);                           // [cap] {int16 x | int16 y}
+    s_parent = reinterpret_cast<idx_t*>(s_xy + cap);
+  }
+  s_pos = s_parent + cap;
+  s_size = s_pos + cap;
+  s_order = s_size + cap;
+  s_tmp = s_order + cap;
+  if constexpr (!GLOBAL) s_pathA = s_tmp + cap;                          // [EMD_MAXPATH]
+  idx_t* s_pathB = s_pathA + EMD_MAXPATH;
+  idx_t* s_P = s_pathB + EMD_MAXPATH;
+  idx_t* s_S = s_P + EMD_MAXPATH;
   __shared__ double s_scr[EMD_WARPS];
   __shared__ long long s_ll[3 * EMD_WARPS];
   __shared__ int2 s_wkey[2 * EMD_WARPS];   // per-warp (reduced cost, position) of the pricing arg-min, double-buffered
@@ -359,12 +397,13 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
   __shared__ int s_lv[EMD_LV];             // node counts of the target hierarchy
   __shared__ long long s_wrc64[WIDE ? 2 * EMD_WARPS : 1];   // per-warp reduced costs of the WIDE pricing arg-min
   __shared__ long long s_delta;
+  __shared__ int s_row[GLOBAL ? 2 * EMD_ROWS_G : 1];          // the block's target rows: -2x, -2y
+  __shared__ long long s_rowp[GLOBAL ? EMD_ROWS_G : 1];       // and potentials (global-tree pricing)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // the scratch pointers are recomputed where they are needed (hierarchy, tree build, refinement) so that they do not
   // occupy registers across the pivot loop
-  char* const cta_ws = p.cta_ws + (size_t)blockIdx.x * p.cta_ws_bytes;
-#define EMD_SCRATCH(sc) EmdScratch sc; emd_scratch_layout(cta_ws, cap, p.cap_tgt, &sc)
+#define EMD_SCRATCH(sc) EmdScratch sc; emd_scratch_layout(cta_ws, cap, p.cap_tgt, &sc, GLOBAL)
   int64_t* flow;
   { EMD_SCRATCH(sc0); flow = sc0.flow; }
   auto FL = [&](int v) -> long long& { return v < fcap ? s_flow[v] : *reinterpret_cast<long long*>(flow + v); };
@@ -413,7 +452,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     const int N0 = n0 + m0 + 1;
     // N + 1 <= cap: the tree build keeps N + 1 offsets in one node array; N <= 30 * threads: the cycle-path scan keeps one
     // bit per preorder position of a thread's run in a 32-bit mask
-    const bool fits = N0 + 1 <= cap && N0 < 65534 && N0 <= 30 * EMD_THREADS && (int64_t)n0 * m0 < 2147483647LL;
+    const bool fits = N0 + 1 <= cap && (GLOBAL || N0 < 65534) && N0 <= 30 * SCAN_CH * EMD_THREADS && (int64_t)n0 * m0 < 2147483647LL;
     const long long maxc0 = (long long)(xmax - xmin) * (xmax - xmin) + (long long)(ymax - ymin) * (ymax - ymin);
     const bool coords_ok = (xmax - ox) < 32768 && (ox - xmin) < 32768 && (ymax - oy) < 32768 && (oy - ymin) < 32768;
     const long long pi_limit = WIDE ? (1LL << 61) : 2147483647LL;
@@ -437,7 +476,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       EMD_SCRATCH(sc);
       // ---- target hierarchy: integer masses, Morton order (sorted in the still unused tree memory), levels ----
       integerize<EMD_THREADS>(p.tgt_mass + t0, m0, sc.tint, s_scr, s_ll);
-      unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+      unsigned long long* keys = GLOBAL ? sc.sortbuf : reinterpret_cast<unsigned long long*>(smem_raw);
       int P = 1;
       while (P < m0) P <<= 1;
       for (int i = tid; i < P; i += EMD_THREADS)
@@ -508,27 +547,27 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       EMD_SCRATCH(sc);
       // ---- start basis from the refined forest (sc.fI / fJ / fF, Ef arcs, grouped by target in sc.tfirst) ----------
       // adjacency for the traversal: sources CSR (soff16 / sadj16), targets = their slice of the arc list (ai16)
-      unsigned short* soff16 = s_tmp;              // [n + 1]
-      unsigned short* tf16 = s_tmp + n + 1;        // [m + 1]
-      const bool adj_smem = (size_t)fcap * 8 >= (size_t)4 * (n + 1) + (size_t)4 * Ef + 16;
+      idx_t* soff16 = s_tmp;              // [n + 1]
+      idx_t* tf16 = s_tmp + n + 1;        // [m + 1]
+      const bool adj_smem = (size_t)fcap * 8 >= (size_t)4 * (n + 1) + 2 * sizeof(idx_t) * (size_t)Ef + 16;
       int* deg32 = adj_smem ? reinterpret_cast<int*>(s_flow) : sc.curS;
-      unsigned short* sadj16 = adj_smem ? reinterpret_cast<unsigned short*>(deg32 + n + 1) : sc.gadj;
-      unsigned short* ai16 = sadj16 + Ef;
+      idx_t* sadj16 = adj_smem ? reinterpret_cast<idx_t*>(deg32 + n + 1) : reinterpret_cast<idx_t*>(sc.gadj);
+      idx_t* ai16 = sadj16 + Ef;
       for (int v = tid; v <= n; v += EMD_THREADS) deg32[v] = 0;
       __syncthreads();
-      for (int e = tid; e < Ef; e += EMD_THREADS) { const int i = sc.fI[e]; atomicAdd(&deg32[i + 1], 1); ai16[e] = (unsigned short)i; }
+      for (int e = tid; e < Ef; e += EMD_THREADS) { const int i = sc.fI[e]; atomicAdd(&deg32[i + 1], 1); ai16[e] = (idx_t)i; }
       __syncthreads();
       cta_prefix_inplace<EMD_THREADS>(deg32, n + 1, s_ws);
-      for (int v = tid; v <= n; v += EMD_THREADS) soff16[v] = (unsigned short)deg32[v];
-      for (int j = tid; j <= m; j += EMD_THREADS) tf16[j] = (unsigned short)sc.tfirst[j];
+      for (int v = tid; v <= n; v += EMD_THREADS) soff16[v] = (idx_t)deg32[v];
+      for (int j = tid; j <= m; j += EMD_THREADS) tf16[j] = (idx_t)sc.tfirst[j];
       __syncthreads();
-      for (int e = tid; e < Ef; e += EMD_THREADS) sadj16[atomicAdd(&deg32[sc.fI[e]], 1)] = (unsigned short)sc.fJ[e];
+      for (int e = tid; e < Ef; e += EMD_THREADS) sadj16[atomicAdd(&deg32[sc.fI[e]], 1)] = (idx_t)sc.fJ[e];
       for (int v = tid; v < N; v += EMD_THREADS) s_parent[v] = UNVIS16;
       __syncthreads();
       for (int v = tid; v < n; v += EMD_THREADS) {      // lists in increasing target order (deterministic layout)
         const int a = soff16[v], b = soff16[v + 1];
         for (int x = a + 1; x < b; ++x) {
-          const unsigned short key = sadj16[x];
+          const idx_t key = sadj16[x];
           int y = x - 1;
           while (y >= a && sadj16[y] > key) { sadj16[y + 1] = sadj16[y]; --y; }
           sadj16[y + 1] = key;
@@ -537,18 +576,18 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       __syncthreads();
       if (tid == 0) {
         // depth-first traversal from every component's lowest source: parents, preorder, potentials
-        unsigned short* stk = s_size;
+        idx_t* stk = s_size;
         int cnt = 0, bad = 0;
-        s_order[0] = (unsigned short)root; s_pos[root] = 0; s_parent[root] = NONE16; s_pi[root] = 0; cnt = 1;
+        s_order[0] = (idx_t)root; s_pos[root] = 0; s_parent[root] = NONE16; s_pi[root] = 0; cnt = 1;
         for (int s0 = 0; s0 < n; ++s0) {
           if (s_parent[s0] != UNVIS16) continue;
-          s_parent[s0] = (unsigned short)root;
+          s_parent[s0] = (idx_t)root;
           { const int xy = s_xy[s0], xr = (xy << 16) >> 16, yr = xy >> 16; s_pi[s0] = (pi_t)(-BIG + (xr * xr + yr * yr)); }
           int sp = 0;
-          stk[sp++] = (unsigned short)s0;
+          stk[sp++] = (idx_t)s0;
           while (sp > 0) {
             const int v = stk[--sp];
-            s_order[cnt] = (unsigned short)v; s_pos[v] = (unsigned short)cnt; ++cnt;
+            s_order[cnt] = (idx_t)v; s_pos[v] = (idx_t)cnt; ++cnt;
             const int pv = s_parent[v];
             const int xy = s_xy[v], xv = (xy << 16) >> 16, yv = xy >> 16;
             if (v < n) {
@@ -557,11 +596,11 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
                 const int w = n + sadj16[k];
                 if (w == pv) continue;
                 if (s_parent[w] != UNVIS16) { bad = 1; continue; }
-                s_parent[w] = (unsigned short)v;
+                s_parent[w] = (idx_t)v;
                 const int wxy = s_xy[w], xw = (wxy << 16) >> 16, yw = wxy >> 16;
                 const int dx = xv - xw, dy = yv - yw;
                 s_pi[w] = piv + (pi_t)(dx * dx + dy * dy) - (pi_t)(xw * xw + yw * yw);
-                stk[sp++] = (unsigned short)w;
+                stk[sp++] = (idx_t)w;
               }
             } else {
               const pi_t piv = s_pi[v] + (pi_t)(xv * xv + yv * yv);
@@ -570,21 +609,21 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
                 const int w = ai16[k];
                 if (w == pv) continue;
                 if (s_parent[w] != UNVIS16) { bad = 1; continue; }
-                s_parent[w] = (unsigned short)v;
+                s_parent[w] = (idx_t)v;
                 const int wxy = s_xy[w], xw = (wxy << 16) >> 16, yw = wxy >> 16;
                 const int dx = xv - xw, dy = yv - yw;
                 s_pi[w] = piv - (pi_t)(dx * dx + dy * dy) + (pi_t)(xw * xw + yw * yw);
-                stk[sp++] = (unsigned short)w;
+                stk[sp++] = (idx_t)w;
               }
             }
           }
         }
         for (int v = n; v < root; ++v)       // targets without any arc (zero integer demand): under the root, as in the star
           if (s_parent[v] == UNVIS16) {
-            s_parent[v] = (unsigned short)root;
+            s_parent[v] = (idx_t)root;
             const int xy = s_xy[v], xr = (xy << 16) >> 16, yr = xy >> 16;
             s_pi[v] = (pi_t)(BIG - (xr * xr + yr * yr));
-            s_order[cnt] = (unsigned short)v; s_pos[v] = (unsigned short)cnt; ++cnt;
+            s_order[cnt] = (idx_t)v; s_pos[v] = (idx_t)cnt; ++cnt;
           }
         s_i[9] = (bad == 0 && cnt == N) ? 1 : 0;
       }
@@ -624,12 +663,12 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
         for (int v = tid; v < n + m; v += EMD_THREADS) flow[v] = v < n ? sm[v] : tm[v - n];
       }
       for (int v = tid; v < n + m; v += EMD_THREADS) {
-        s_parent[v] = (unsigned short)root; s_order[v + 1] = (unsigned short)v; s_pos[v] = (unsigned short)(v + 1);
+        s_parent[v] = (idx_t)root; s_order[v + 1] = (idx_t)v; s_pos[v] = (idx_t)(v + 1);
         const int xy = s_xy[v], xr = (xy << 16) >> 16, yr = xy >> 16, r2 = xr * xr + yr * yr;
         s_size[v] = 1; s_pi[v] = v < n ? (pi_t)(-BIG + r2) : (pi_t)(BIG - r2);
       }
       if (tid == 0) {
-        s_order[0] = (unsigned short)root; s_pos[root] = 0; s_size[root] = (unsigned short)N; s_parent[root] = NONE16;
+        s_order[0] = (idx_t)root; s_pos[root] = 0; s_size[root] = (idx_t)N; s_parent[root] = NONE16;
         s_pi[root] = 0; flow[root] = 0; s_i[4] = 0;
       }
       __syncthreads();
@@ -643,10 +682,16 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     // on the problem itself; coarse levels (few arcs in all) price a sixteenth of their arcs, at least 4,096
     int B = p.block_size > 0 ? p.block_size
                              : max((int)sqrt((double)n_arcs), min(ONE_PER_SM ? 32768 : 32 * EMD_THREADS, max(4096, n_arcs / 16)));
-    if (p.block_size <= 0 && n <= EMD_RMAX_T * EMD_THREADS) B = max(1, (B + n / 2) / n) * n;   // whole target rows
+    if (!GLOBAL && p.block_size <= 0 && n <= EMD_RMAX_T * EMD_THREADS) B = max(1, (B + n / 2) / n) * n;   // whole target rows
     if (B < 10) B = 10;
     if (B > n_arcs) B = n_arcs;
+    if (GLOBAL && p.block_size <= 0) {         // whole rows: at least EMD_ROWS_MIN_G (the sources are read once per block)
+      int rows = (B + n / 2) / n;
+      rows = max(EMD_ROWS_MIN_G, min(EMD_ROWS_G, rows));
+      B = min(rows, m) * n;
+    }
     const bool whole_rows = !WIDE && B % n == 0 && n <= EMD_RMAX_T * EMD_THREADS;   // n_arcs and every block start are multiples of n
+    const bool whole_rows_g = GLOBAL && B % n == 0 && B / n <= EMD_ROWS_G;
     int next_arc = 0;
     long long it = 0;
     unsigned round = 0;
@@ -764,6 +809,87 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
             }
           }
           }
+          if constexpr (GLOBAL) {
+          if (whole_rows_g) {
+            fast_done = true;
+            // Global-tree pricing: the block is `rows` whole target rows, staged in shared memory (-2x, -2y, potential);
+            // the sources stream through registers in tiles of EMD_RG_G x threads (coalesced loads of their coordinates
+            // and potentials, read once per block) and every tile meets all rows at register speed.
+            constexpr int RG = EMD_RG_G;
+            const int rows = cnt / n, j0 = next_arc / n;
+            __syncthreads();                                   // the previous block's rows may still be read
+            for (int r = tid; r < rows; r += EMD_THREADS) {
+              int j = j0 + r;
+              while (j >= m) j -= m;
+              const int txy = s_xy[n + j];
+              s_row[2 * r] = -2 * ((txy << 16) >> 16); s_row[2 * r + 1] = -2 * (txy >> 16);
+              s_rowp[r] = s_pi[n + j];
+            }
+            __syncthreads();
+            long long trc = 0;
+            int tbase = -1;                                    // the tile in which this thread's minimum was first reached
+            for (int base = 0; base < n; base += RG * EMD_THREADS) {
+              int sx[RG], sy[RG];
+              long long sp[RG];
+#pragma unroll
+              for (int r = 0; r < RG; ++r) {
+                const int i = base + tid + r * EMD_THREADS;
+                const int xy = i < n ? s_xy[i] : 0;
+                sx[r] = (xy << 16) >> 16; sy[r] = xy >> 16;
+                sp[r] = i < n ? (long long)s_pi[i] : LLONG_MAX / 4;      // never the minimum
+              }
+              const long long before = trc;
+              for (int r2 = 0; r2 < rows; ++r2) {
+                const long long nx2 = s_row[2 * r2], ny2 = s_row[2 * r2 + 1], bj = s_rowp[r2];
+#pragma unroll
+                for (int r = 0; r < RG; ++r) trc = min(trc, sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj)));
+              }
+              if (trc < before) tbase = base;
+            }
+            {   // the block's most negative reduced cost
+              long long r64 = trc;
+              for (int o = 16; o > 0; o >>= 1) r64 = min(r64, shfl_xor_ll(r64, o));
+              long long* wr = s_wrc64 + (round & 1) * EMD_WARPS;
+              if (lane == 0) wr[warp] = r64;
+              __syncthreads();
+              r64 = lane < EMD_WARPS ? wr[lane] : 0;
+              for (int o = 16; o > 0; o >>= 1) r64 = min(r64, shfl_xor_ll(r64, o));
+              g_rc = (pi_t)r64;
+              ++round;
+            }
+            if (g_rc < 0) {
+              unsigned myk = 0xffffffffu;                      // its first position in block order among this thread's arcs
+              if (trc == (long long)g_rc) {
+                for (int r2 = 0; r2 < rows && myk == 0xffffffffu; ++r2) {
+                  const long long nx2 = s_row[2 * r2], ny2 = s_row[2 * r2 + 1], bj = s_rowp[r2];
+                  int j = j0 + r2;
+                  while (j >= m) j -= m;
+#pragma unroll
+                  for (int r = 0; r < RG; ++r) {
+                    const int i = tbase + tid + r * EMD_THREADS;
+                    if (i < n && myk == 0xffffffffu) {
+                      const int xy = s_xy[i];
+                      const long long rc = ((xy << 16) >> 16) * nx2 + ((xy >> 16) * ny2 + ((long long)s_pi[i] - bj));
+                      if (rc == (long long)g_rc) {
+                        int k = j * n + i - next_arc;
+                        if (k < 0) k += n_arcs;
+                        myk = (unsigned)k;
+                      }
+                    }
+                  }
+                }
+              }
+              const unsigned w_k = __reduce_min_sync(FULL_MASK, myk);
+              unsigned* wk = reinterpret_cast<unsigned*>(s_wkey + (round & 1) * EMD_WARPS);
+              if (lane == 0) wk[warp] = w_k;
+              __syncthreads();
+              g_k = __reduce_min_sync(FULL_MASK, lane < EMD_WARPS ? wk[lane] : 0xffffffffu);
+              ++round;
+            } else {
+              g_rc = PI_NONE;
+            }
+          }
+          }
           if (!fast_done) {
             // general block: arcs [next_arc, next_arc + cnt) of the j-major order (wrapping) = a few target rows,
             // each a contiguous range of sources
@@ -860,45 +986,63 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       // a path the position decreases, so an ordered compaction (one block scan) yields both paths in walking order.
       {
         const int pu = s_pos[u_i], pw = s_pos[u_j];
-        int per = (N + EMD_THREADS - 1) / EMD_THREADS;             // <= 30 for every problem that fits a CTA
+        int per = (N + EMD_THREADS - 1) / EMD_THREADS;             // <= 30 * SCAN_CH for every problem that fits
         per += (2 - per) & 3;   // per = 2 (mod 4): a lane stride of per uint16 is an odd number of 4-byte words, so the
                                 // loads of s_order[x0 + q] across a warp hit 32 different banks
         const int x0 = tid * per, x1 = min(N, x0 + per);
-        unsigned mA = 0u, mB = 0u;
-        constexpr int PER_UNROLL = 4;                              // independent load pairs in flight
+        unsigned mA[SCAN_CH], mB[SCAN_CH];                         // one bit per position of the run, 32 per chunk
+#pragma unroll
+        for (int c = 0; c < SCAN_CH; ++c) { mA[c] = 0u; mB[c] = 0u; }
+        constexpr int PER_UNROLL = GLOBAL ? 8 : 4;                 // independent load pairs in flight
         const int xlim = min(x1, max(pu, pw) + 1);                 // ancestors precede their descendants
-        for (int xb = x0; xb < xlim; xb += PER_UNROLL) {
-          int vv[PER_UNROLL], sz[PER_UNROLL];
 #pragma unroll
-          for (int q = 0; q < PER_UNROLL; ++q) vv[q] = xb + q < xlim ? s_order[xb + q] : root;
+        for (int c = 0; c < SCAN_CH; ++c) {
+          const int xc0 = x0 + 32 * c, xc1 = min(xlim, xc0 + 32);
+          for (int xb = xc0; xb < xc1; xb += PER_UNROLL) {
+            int vv[PER_UNROLL], sz[PER_UNROLL];
 #pragma unroll
-          for (int q = 0; q < PER_UNROLL; ++q) sz[q] = xb + q < xlim ? (int)s_size[vv[q]] : 0;   // 0: never an ancestor
+            for (int q = 0; q < PER_UNROLL; ++q) vv[q] = xb + q < xc1 ? s_order[xb + q] : root;
 #pragma unroll
-          for (int q = 0; q < PER_UNROLL; ++q) {
-            const int x = xb + q;
-            const unsigned inU = (unsigned)(pu - x) < (unsigned)sz[q], inW = (unsigned)(pw - x) < (unsigned)sz[q];
-            mA |= (inU & ~inW & 1u) << ((x - x0) & 31);
-            mB |= (inW & ~inU & 1u) << ((x - x0) & 31);
+            for (int q = 0; q < PER_UNROLL; ++q) sz[q] = xb + q < xc1 ? (int)s_size[vv[q]] : 0;   // 0: never an ancestor
+#pragma unroll
+            for (int q = 0; q < PER_UNROLL; ++q) {
+              const int x = xb + q;
+              const unsigned inU = (unsigned)(pu - x) < (unsigned)sz[q], inW = (unsigned)(pw - x) < (unsigned)sz[q];
+              mA[c] |= (inU & ~inW & 1u) << ((x - xc0) & 31);
+              mB[c] |= (inW & ~inU & 1u) << ((x - xc0) & 31);
+            }
           }
         }
-        // exclusive block scan of the two counts, packed in one word
-        const int cnt = __popc(mA) | (__popc(mB) << 16);
-        int incl = cnt;
+        int cntA = 0, cntB = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        int wtot = lane < EMD_WARPS ? s_wsum[lane] : 0, wincl = wtot;
+        for (int c = 0; c < SCAN_CH; ++c) { cntA += __popc(mA[c]); cntB += __popc(mB[c]); }
+        int nA, nB, ra, rb;                                        // totals; ranks in ascending position = distance from the join
+        if constexpr (!GLOBAL) {
+          // exclusive block scan of the two counts, packed in one word
+          const int cnt = cntA | (cntB << 16);
+          int incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, wincl, o); if (lane >= o) wincl += t; }
-        const int total = __shfl_sync(FULL_MASK, wincl, 31);
-        const int before = __shfl_sync(FULL_MASK, wincl - wtot, warp) + incl - cnt;
-        const int nA = total & 0xffff, nB = total >> 16;
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += t; }
+          if (lane == 31) s_wsum[warp] = incl;
+          __syncthreads();
+          int wtot = lane < EMD_WARPS ? s_wsum[lane] : 0, wincl = wtot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL_MASK, wincl, o); if (lane >= o) wincl += t; }
+          const int total = __shfl_sync(FULL_MASK, wincl, 31);
+          const int before = __shfl_sync(FULL_MASK, wincl - wtot, warp) + incl - cnt;
+          nA = total & 0xffff; nB = total >> 16;
+          ra = before & 0xffff; rb = before >> 16;
+        } else {
+          ra = cta_excl_scan<EMD_THREADS>(cntA, s_ws, &nA);
+          rb = cta_excl_scan<EMD_THREADS>(cntB, s_ws, &nB);
+        }
         if (tid == 0) { s_i[1] = nA; s_i[2] = nB; }
         if (nA <= EMD_MAXPATH && nB <= EMD_MAXPATH) {
-          int ra = before & 0xffff, rb = before >> 16;             // rank in ascending position = distance from the join
-          for (unsigned m = mA; m; m &= m - 1) s_pathA[nA - 1 - ra++] = s_order[x0 + __ffs(m) - 1];
-          for (unsigned m = mB; m; m &= m - 1) s_pathB[nB - 1 - rb++] = s_order[x0 + __ffs(m) - 1];
+#pragma unroll
+          for (int c = 0; c < SCAN_CH; ++c) {
+            for (unsigned mm = mA[c]; mm; mm &= mm - 1) s_pathA[nA - 1 - ra++] = s_order[x0 + 32 * c + __ffs(mm) - 1];
+            for (unsigned mm = mB[c]; mm; mm &= mm - 1) s_pathB[nB - 1 - rb++] = s_order[x0 + 32 * c + __ffs(mm) - 1];
+          }
         }
       }
       __syncthreads();
@@ -932,8 +1076,8 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       if (seq < 0) { status = 5; break; }        // unbounded: cannot happen for a transport LP
       const int side = seq >= lenA ? 1 : 0;
       const int k = side == 0 ? lenA - 1 - seq : seq - lenA;   // leaving arc at path index k of its side
-      const unsigned short* pathX = side == 0 ? s_pathA : s_pathB;
-      const unsigned short* pathY = side == 0 ? s_pathB : s_pathA;
+      const idx_t* pathX = side == 0 ? s_pathA : s_pathB;
+      const idx_t* pathY = side == 0 ? s_pathB : s_pathA;
       const int lenX = side == 0 ? lenA : lenB, lenY = side == 0 ? lenB : lenA;
       const int q = pathX[k];
       const int t_in = side == 0 ? u_j : u_i;
@@ -967,13 +1111,13 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           const int t = tid + r * EMD_THREADS;
           if (t <= k) {
             const int v = pathX[t];
-            if (t == 0) { s_parent[v] = (unsigned short)t_in; FL(v) = delta; s_size[v] = (unsigned short)s; }
-            else { s_parent[v] = pathX[t - 1]; FL(v) = fo[r]; s_size[v] = (unsigned short)(s - s_S[t - 1]); }
+            if (t == 0) { s_parent[v] = (idx_t)t_in; FL(v) = delta; s_size[v] = (idx_t)s; }
+            else { s_parent[v] = pathX[t - 1]; FL(v) = fo[r]; s_size[v] = (idx_t)(s - s_S[t - 1]); }
           }
         }
       }
-      for (int t = k + 1 + tid; t < lenX; t += EMD_THREADS) s_size[pathX[t]] -= (unsigned short)s;
-      for (int t = tid; t < lenY; t += EMD_THREADS) s_size[pathY[t]] += (unsigned short)s;
+      for (int t = k + 1 + tid; t < lenX; t += EMD_THREADS) s_size[pathX[t]] -= (idx_t)s;
+      for (int t = tid; t < lenY; t += EMD_THREADS) s_size[pathY[t]] += (idx_t)s;
       // ---- preorder re-numbering of the affected range ------------------------------------------------
       for (int x = lo + tid; x < hi; x += EMD_THREADS) {
         const int v = s_tmp[x];
@@ -992,8 +1136,8 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           else r = x - Pt;
           f = ptr + 1 + r;
         }
-        s_order[f] = (unsigned short)v;
-        s_pos[v] = (unsigned short)f;
+        s_order[f] = (idx_t)v;
+        s_pos[v] = (idx_t)f;
       }
       __syncthreads();
       PROF_T(c_update)
@@ -1160,7 +1304,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
 
 inline size_t emd_node_bytes(bool wide) { return (wide ? 8 : 4) + 4 + 5 * 2; }   // potential, packed xy, five uint16 tree arrays
 inline size_t emd_smem_bytes(int64_t cap_nodes, int64_t flow_nodes = 0, bool wide = false) {
-  return (size_t)flow_nodes * 8 + (size_t)cap_nodes * emd_node_bytes(wide) + 4 * (size_t)EMD_MAXPATH * 2 + 64;
+  return (size_t)flow_nodes * 8 + (size_t)cap_nodes * emd_node_bytes(wide) + 4 * (size_t)EMD_MAXPATH_S * 2 + 64;
 }
 inline int64_t emd_ws_cap(int64_t n_src, int64_t max_tgt) { return (n_src + max_tgt + 2 + 7) & ~7LL; }
 inline int64_t emd_pow2(int64_t n) { int64_t p = 1; while (p < n) p <<= 1; return p; }
@@ -1182,7 +1326,10 @@ inline EmdGlobalLayout emd_global_layout(int64_t n_src, int64_t max_tgt, int64_t
   g.hs_mass = take(8 * (size_t)EMD_LV * n_src);
   g.hs_xy = take(4 * (size_t)EMD_LV * n_src);
   g.hs_child = take(4 * (size_t)EMD_LV * (n_src + 1));
-  g.cta_bytes = (emd_scratch_layout(nullptr, emd_ws_cap(n_src, max_tgt), max_tgt > 0 ? max_tgt : 1, nullptr) + 255) & ~(size_t)255;
+  // the global-tree regions are sized whenever the batch might not fit shared memory (the smallest capacity, that of the
+  // 64-bit kernel, is ~9.6k nodes); they sit at the end of a slice, so the shared-memory kernels never see them
+  g.cta_bytes = (emd_scratch_layout(nullptr, emd_ws_cap(n_src, max_tgt), max_tgt > 0 ? max_tgt : 1, nullptr,
+                                    emd_ws_cap(n_src, max_tgt) > EMD_GLOBAL_ALLOC_NODES) + 255) & ~(size_t)255;
   g.cta0 = off;
   g.total = off + g.cta_bytes * (size_t)n_ctas + 256;
   return g;
@@ -1243,9 +1390,23 @@ int emd_launch(bool wide, const int32_t* src_x, const int32_t* src_y, const doub
                                                   reinterpret_cast<uint32_t*>(ws + gl.codeA), reinterpret_cast<uint32_t*>(ws + gl.codeB),
                                                   a.hs, a.src_hdr);
   STM_CHECK_CUDA(cudaGetLastError());
+  const int grid = n_ctas < G ? n_ctas : G;
+  if (ws_cap > max_cap) {
+    // ---- the batch does not fit a CTA's shared memory: tree in the CTA's global scratch (one CTA per SM) ----
+    a.cap_nodes = (int32_t)ws_cap;
+    const int64_t paths = 4 * (int64_t)EMD_MAXPATH_G * 4 + 64;
+    int64_t fcap_g = ((int64_t)max_optin - 4096 - paths) / 8;
+    fcap_g = std::max<int64_t>(0, std::min<int64_t>(fcap_g, ws_cap)) & ~1LL;
+    a.flow_smem_nodes = (int32_t)fcap_g;
+    const size_t smem_g = (size_t)fcap_g * 8 + (size_t)paths;
+    auto kern = emd_kernel<EMD_GLOBAL_THREADS, true, true, true>;
+    STM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    kern<<<grid, EMD_GLOBAL_THREADS, smem_g, st>>>(a);
+    STM_CHECK_CUDA(cudaGetLastError());
+    return STM_OK;
+  }
   // the kernel carves the scratch of a CTA with its own cap (<= ws_cap), so the slices never exceed what was sized
   const size_t tree_smem = emd_smem_bytes((int)cap, 0, wide);
-  const int grid = n_ctas < G ? n_ctas : G;
   // Problems that leave room for only one CTA per SM get 512 threads and the register-resident pricing path;
   // small problems run several 256-thread CTAs per SM.
   const bool one_per_sm = tree_smem * 2 + 2048 > (size_t)max_optin;
@@ -1288,3 +1449,13 @@ extern "C" int stm_emd_spots_batched_wide(const int32_t* src_x, const int32_t* s
   return stm::emd_launch(true, src_x, src_y, src_mass, n_src, tgt_ptr, tgt_x, tgt_y, tgt_mass, G, max_tgt, order, max_iter,
                          block_size, flags, workspace, workspace_bytes, n_ctas, out_cost, out_status, out_iters, stream);
 }
+
+extern "C" int32_t stm_emd_smem_node_capacity(int32_t wide) {
+  int dev = 0, max_optin = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
+  const int64_t max_cap = (((int64_t)max_optin - 4096 - (int64_t)stm::emd_smem_bytes(0)) / (int64_t)stm::emd_node_bytes(wide != 0)) & ~7LL;
+  return (int32_t)(max_cap - 10);     // n + m + 1 nodes, two spare entries, rounding of the workspace capacity
+}
+
+extern "C" int32_t stm_emd_global_node_capacity(void) { return (int32_t)stm::EMD_GLOBAL_MAX_NODES; }

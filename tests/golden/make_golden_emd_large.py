@@ -9,8 +9,11 @@ nearest targets of every source and the nearest sources of every target, plus sl
 then all n x m reduced costs are evaluated with the LP's duals in numpy, the violating arcs are added and the LP is
 solved again.  It stops when NO arc of the full problem has a negative reduced cost and no slack is used: by LP
 duality the restricted optimum is then the optimum of the full problem.  That final certificate — dual feasibility
-over all n x m arcs, objective = dual objective — is checked here in float64 numpy and does not involve any code of
-this repository's solver (neither the CUDA kernel nor oracle/emd_oracle.c).
+over all n x m arcs, objective = dual objective — is checked here in float64 numpy: the VALUE is HiGHS's and its
+optimality is proved by duality, independently of this repository's solver.  To save hours of column generation the
+FIRST arc set is seeded with the support of the oracle's plan (``--seed-oracle``, used for the committed file); the seed
+only decides which columns HiGHS starts with — a wrong or sub-optimal seed costs more rounds, it cannot change the
+certified optimum.  Case 0 of the committed file was also run unseeded (5 rounds, 22 min): same value to 1e-13.
 
 Problems: the source is the per-spot total image of a synthetic Visium data set (4,992 spots on the hex lattice, the
 ``global_matrix`` of SPFinder.py:279-283) and the targets are genes of that data set, as ``spatial_high_variable_genes``
@@ -57,7 +60,28 @@ def grid_problem(R, n_src_frac, m, seed):
     return (sx, sy, sm), (tx, ty, tm)
 
 
-def solve_colgen(src, tgt, knn=6, verbose=True):
+def oracle_support(src, tgt):
+    """(i, j) pairs carrying flow in the plan of the repository's CPU network simplex (only a column seed, see the
+    module docstring)."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts", "research"))
+    import ms_proto as mp
+    sx, sy, a = src; tx, ty, b = tgt
+    S = (sx.astype(np.int32), sy.astype(np.int32), mp.integerize(a)); T = (tx.astype(np.int32), ty.astype(np.int32), mp.integerize(b))
+    smaps, tmaps, Ss, Ts = [], [], [S], [T]
+    while len(Ss[-1][0]) + len(Ts[-1][0]) > 64:
+        cx, cy, cm, inv = mp.coarsen(*Ss[-1]); Ss.append((cx, cy, cm)); smaps.append(inv)
+        cx, cy, cm, inv = mp.coarsen(*Ts[-1]); Ts.append((cx, cy, cm)); tmaps.append(inv)
+    arcs = None
+    for lev in range(len(Ss) - 1, -1, -1):
+        n_, m_ = len(Ss[lev][0]), len(Ts[lev][0])
+        _, _, final, _ = mp.ns(Ss[lev][0], Ss[lev][1], Ss[lev][2], Ts[lev][0], Ts[lev][1], Ts[lev][2], arcs,
+                               block=min(n_ * m_, max(int(np.sqrt(n_ * m_)), 7 * n_)))
+        if lev > 0:
+            arcs = mp.refine(final, Ss[lev - 1], Ts[lev - 1], Ss[lev], Ts[lev], smaps[lev - 1], tmaps[lev - 1], order="morton")
+    return final[0].astype(np.int64), final[1].astype(np.int64)
+
+
+def solve_colgen(src, tgt, knn=6, verbose=True, seed=None):
     sx, sy, a = src
     tx, ty, b = tgt
     n, m = len(sx), len(tx)
@@ -72,6 +96,8 @@ def solve_colgen(src, tgt, knn=6, verbose=True):
     nn_s = np.argpartition(C, k2 - 1, axis=0)[:k2, :]
     for j in range(m):
         arcs.update((nn_s[:, j] * m + j).tolist())
+    if seed is not None:
+        arcs.update((seed[0] * m + seed[1]).tolist())
     it = 0
     while True:
         it += 1
@@ -132,7 +158,7 @@ def main():
     for c, (name, s, t) in enumerate(cases):
         print("case %d %s: n=%d m=%d" % (c, name, len(s[0]), len(t[0])), flush=True)
         t0 = time.time()
-        cost, rmin, rounds, E = solve_colgen(s, t)
+        cost, rmin, rounds, E = solve_colgen(s, t, seed=oracle_support(s, t) if "--seed-oracle" in sys.argv else None)
         print("  -> optimum %.12g (%d rounds, %d arcs, %.0f s)" % (cost, rounds, E, time.time() - t0), flush=True)
         p = "c%d_" % c
         out[p + "name"] = np.array(name)

@@ -61,12 +61,37 @@ def test_emd_iteration_limit_and_empty(cuda_device):
     assert s2.tolist() == [0, 2]
 
 
-def test_emd_too_large_for_one_cta_reports_status_3(cuda_device):
+def test_emd_beyond_one_cta_runs_with_the_tree_in_global_memory(cuda_device):
+    """Problems whose tree does not fit a CTA's shared memory (> ~11.9k nodes: Visium HD, Stereo-seq bins) run the same
+    solver with the tree in the CTA's global scratch: same optimum and — at an explicit block size — the same pivots per
+    level as the oracle.  A batch that mixes sizes is split by the host; results stay in target order."""
     from stminer_b200.Algorithm.distance import emd_batched
     rng = np.random.default_rng(0)
     n = 9000
-    src = (rng.integers(0, 300, n), rng.integers(0, 300, n), rng.random(n) + 0.1)
-    tgt = (rng.integers(0, 300, 4000), rng.integers(0, 300, 4000), rng.random(4000) + 0.1)
+    cells = rng.permutation(150 * 150)[:n]
+    src = (cells // 150, cells % 150, rng.random(n) + 0.1)
+    tgs = []
+    for m in (4000, 700, 5200):
+        t = rng.permutation(150 * 150)[:m]
+        tgs.append((t // 150, t % 150, rng.random(m) + 0.1))
+    cost, status, iters = emd_batched(src, tgs, return_iters=True)
+    costB, statusB, itersB = emd_batched(src, tgs, block_size=40000, return_iters=True)
+    for g, t in enumerate(tgs):
+        c, st, it, lev = eo.emd_multiscale(*src, *t, block_size=40000)
+        assert status[g] == statusB[g] == st == 0, (g, status, statusB)
+        assert abs(cost[g] - c) <= 1e-11 * c and abs(costB[g] - c) <= 1e-11 * c, (g, cost[g], costB[g], c)
+        assert itersB[g] == it, (g, itersB[g], it, lev[:8])
+
+
+def test_emd_node_capacity_limit_reports_status_3(cuda_device):
+    """Beyond the global-tree capacity (or 2^31 arcs) a problem is refused with status 3 and NaN, never a wrong value."""
+    from stminer_b200 import _lib
+    from stminer_b200.Algorithm.distance import emd_batched
+    cap = int(_lib.load().stm_emd_global_node_capacity())
+    rng = np.random.default_rng(1)
+    n = cap - 100
+    src = (np.arange(n) // 400, np.arange(n) % 400, rng.random(n) + 0.1)
+    tgt = (np.arange(300) // 400, np.arange(300) % 400, rng.random(300) + 0.1)
     cost, status = emd_batched(src, [tgt])
     assert status[0] == 3 and np.isnan(cost[0])
 
@@ -204,10 +229,13 @@ def test_emd_visium_size_matches_independent_lp_golden(cuda_device):
         p = "c%d_" % c
         src = (z[p + "sx"], z[p + "sy"], z[p + "sm"]); tgt = (z[p + "tx"], z[p + "ty"], z[p + "tm"])
         ref = float(z[p + "cost"])
-        cost, status = emd_batched(src, [tgt])
-        if status[0] == 3 and len(src[0]) + len(tgt[0]) > 11000:
-            continue                                                      # beyond one CTA: covered by the large-problem test
+        cost, status = emd_batched(src, [tgt])      # the last case (12,979 x 3,000) runs with the tree in global memory
         assert status[0] == 0, (c, status)
         assert abs(cost[0] - ref) <= 1e-7 * ref, (c, cost[0], ref)
         cost_s, status_s = emd_batched(src, [tgt], star_start=True)
-        assert status_s[0] == 0 and abs(cost_s[0] - cost[0]) <= 1e-11 * ref
+        if len(src[0]) + len(tgt[0]) < 11000:
+            assert status_s[0] == 0 and abs(cost_s[0] - cost[0]) <= 1e-11 * ref
+        else:
+            # from the artificial star (the start of POT, which the reference calls with numItermax=200000) the 16k-node
+            # problem is still sub-optimal after 200,000 pivots: status 1 and a larger cost, as POT would return
+            assert status_s[0] == 1 and cost_s[0] > cost[0]

@@ -23,22 +23,54 @@ def test_em_parity_fixed_init(cuda_device, config, K, nt, rep):
     W, MU, COV, ok = oracle_inits(sm, K, seed=11)
     res = _fit(sm, K, (W, MU, COV))
     ref = oracle_fit_all(sm, K, W, MU, COV, ok)
-    n_checked = 0
-    n_iter_mismatch = 0
-    for g in range(sm.n_genes):
+    n_mismatch = _check_against_oracle(sm, res, ref, ok, W, MU, COV)
+    print("n_iter mismatch rate %s K=%d: %d / %d" % (config, K, n_mismatch, int(ok.sum())))
+    assert n_mismatch <= max(1, 0.02 * ok.sum())
+
+
+def _check_against_oracle(sm, res, ref, ok, W, MU, COV, genes=None):
+    """Every fitted gene is compared (rtol 1e-4).  A gene whose FP32 stop rule fired one iteration earlier / later than
+    the float64 oracle's (|delta lower bound| within FP32 noise of tol) is compared with the oracle STOPPED AT THE SAME
+    ITERATION instead of being skipped; the number of such genes is returned."""
+    from oracle import gmm_oracle as go
+    n_mismatch = 0
+    for g in (range(sm.n_genes) if genes is None else genes):
         if not ok[g]:
             assert res["status"][g] == 1
             continue
         assert res["status"][g] == 0
-        if res["n_iter"][g] != ref[g]["n_iter"]:
-            n_iter_mismatch += 1      # stop rule crossed the tolerance within FP32 noise; counted, not compared
-            continue
-        assert bool(res["converged"][g]) == ref[g]["converged"]
-        assert abs(res["lower_bound"][g] - ref[g]["lower_bound"]) < 1e-4
-        assert_gmm_close(res, g, ref[g], what="gene %d" % g)
-        n_checked += 1
-    assert n_checked >= 0.9 * ok.sum()
-    assert n_iter_mismatch <= max(1, 0.05 * ok.sum())
+        r = ref[g]
+        if res["n_iter"][g] != r["n_iter"]:
+            n_mismatch += 1
+            assert abs(int(res["n_iter"][g]) - int(r["n_iter"])) <= 1, (g, res["n_iter"][g], r["n_iter"])
+            xy, c = sm.gene_spots(g)
+            r = go.weighted_em(xy, c, W[g], MU[g], COV[g], tol=-1.0, max_iter=int(res["n_iter"][g]))
+        else:
+            assert bool(res["converged"][g]) == r["converged"]
+        assert abs(res["lower_bound"][g] - r["lower_bound"]) < 1e-4
+        assert_gmm_close(res, g, r, what="gene %d" % g)
+    return n_mismatch
+
+
+def test_em_parity_s50_bench_sample(cuda_device):
+    """32 genes of the S50 configuration (40,000 bins; the generator, grid and seed of the set bench.py times, fewer
+    templates), incl. its longest genes, from the reference's own kind of start (KMeans init) against the float64
+    oracle: rtol 1e-4, equal n_iter."""
+    from stminer_b200.Simulate import simulate_spot_matrix
+    sm_all = simulate_spot_matrix("S50", seed=0, n_templates=8, replicas=4)
+    nnz = np.diff(sm_all.col_ptr)
+    pick = sorted(set(np.argsort(-nnz)[:6].tolist() + np.argsort(nnz)[:4].tolist()
+                      + np.random.default_rng(0).permutation(sm_all.n_genes)[:22].tolist()))
+    sm = sm_all.select(np.array(pick))
+    K = 20
+    W, MU, COV, ok = oracle_inits(sm, K, seed=5)
+    res = _fit(sm, K, (W, MU, COV))
+    ref = oracle_fit_all(sm, K, W, MU, COV, ok)
+    assert ok.sum() >= 24 and int(np.diff(sm.col_ptr).max()) > 10000
+    n_mismatch = _check_against_oracle(sm, res, ref, ok, W, MU, COV)
+    print("S50 sample: %d genes, nnz %d..%d, n_iter mismatches %d" % (sm.n_genes, np.diff(sm.col_ptr).min(),
+                                                                    np.diff(sm.col_ptr).max(), n_mismatch))
+    assert n_mismatch <= 1
 
 
 def test_em_matches_sklearn_golden(cuda_device):
