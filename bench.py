@@ -7,12 +7,16 @@ A "step" is one pass of the hot path over one batch: the count-weighted GMM fit 
 k-means++/Lloyd initialisation + EM, K=20, reg_covar=tol=1e-3, max_iter=100 — the reference's
 ``fit_pattern`` defaults) of every gene of the synthetic Stereo-seq bin50 data set
 (40,000 bins x 10,000 genes, BASELINE.json configs[2], the configuration the genes/s target is quoted on).
-With N ranks every rank fits its own 10,000-gene data set (weak scaling, no data-path collective).
+With N ranks the genes of that ONE data set are cut into contiguous, nnz-balanced ranges, one per rank (BASELINE
+configs[2]: "genes sharded over 1/2/4/8 B200" — strong scaling); a step then ends with the one packed NCCL
+all-gather that replicates the fitted parameters on every rank.
 
-One JSON line is printed by rank 0.  ``value`` is genes/s with inputs resident in HBM; ``e2e`` is the same
-metric through the host-buffer API (pinned H2D of the CSC matrix + fit + D2H of the parameters inside the
-timed region); ``pairs`` reports the second half of the metric (SVG-pair GMM distances/s on 4,000 fitted
-genes, 7,998,000 pairs, pair slices sharded over the ranks and all-gathered with NCCL).
+One JSON line is printed by rank 0.  ``value`` is genes/s with the shards resident in HBM (fit + all-gather);
+``e2e`` is the same metric through the host-buffer API ``sharding.fit_genes_sharded`` (pinned H2D of the rank's
+columns + fit + all-gather + D2H of the parameters inside the timed region); ``pairs`` reports the second half of
+the metric (SVG-pair GMM distances/s on 4,000 fitted genes, 7,998,000 pairs, pair slices sharded over the ranks and
+all-gathered in place); ``emd`` the spot-level EMD of ``spatial_high_variable_genes`` on Visium-size problems,
+sharded over the ranks as well.
 """
 from __future__ import annotations
 
@@ -45,7 +49,7 @@ def parse():
     ap.add_argument("--pairs-genes", type=int, default=4000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="genes in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--emd-genes", type=int, default=148, help="Visium-size spot-EMD problems in the emd leg (0 = skip)")
+    ap.add_argument("--emd-genes", type=int, default=1184, help="Visium-size spot-EMD problems in the emd leg (0 = skip)")
     ap.add_argument("--s10-genes", type=int, default=296, help="long (Stereo-seq bin10-shaped) genes in the s10 leg (0 = skip)")
     ap.add_argument("--no-mds", action="store_true", help="skip the MDS (cluster_gene) leg")
     return ap.parse_args()
@@ -119,7 +123,7 @@ def _cpu_fit_one(args):
     from oracle import gmm_oracle as go
     t = time.perf_counter()
     gm = go.fit_gmm_reference(xy, c, K)
-    return time.perf_counter() - t, (0 if gm is None else int(gm.n_iter_))
+    return time.perf_counter() - t, (0 if gm is None else int(gm.n_iter_)), (float("nan") if gm is None else float(gm.lower_bound_))
 
 
 class CpuReference:
@@ -139,6 +143,8 @@ class CpuReference:
         t = time.perf_counter()
         res = self.pool.map(_cpu_fit_one, jobs, chunksize=1)
         wall = time.perf_counter() - t
+        self.last_idx = idx
+        self.last_lower_bound = np.array([r[2] for r in res])
         return len(jobs) / wall, wall, float(np.mean([r[0] for r in res])), len(jobs)
 
     def close(self):
@@ -157,13 +163,22 @@ def _noop(_):
     return 0
 
 
+def _cpu_pairs(job):
+    """distribution_distance (distance.py:13-36) of the pairs (ia[k], ib[k]) on one core: (seconds, pairs, distances)."""
+    W, MU, COV, ia, ib = job
+    from oracle import dist_oracle as do
+    t = time.perf_counter()
+    d = np.array([do.distribution_distance(W[a], MU[a], COV[a], W[b], MU[b], COV[b]) for a, b in zip(ia, ib)])
+    return time.perf_counter() - t, len(ia), d
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     sm = workload(args.workload, seed=0, genes=args.genes)
-    per_step = args.cpu_sample or max(cores, 8)
+    per_step = args.cpu_sample or 6 * max(cores, 8)      # several fits per core and step: the wall is not one slow gene
     rates, walls = [], []
     cpu = CpuReference(cores)
     for s in range(args.warmup + args.steps):
@@ -186,16 +201,17 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, sm, world):
+    """The workload description — the same dict in both arms (nothing here depends on the arm)."""
     names = {"S50": "synthetic Stereo-seq bin50: 40,000 bins x 10,000 genes, K=20 (BASELINE configs[2])",
              "V": "synthetic Visium-shaped: 4,992 spots x 2,000 genes, K=20 (BASELINE configs[1])",
              "T": "synthetic 17x17 test-path stand-in, K=20"}
-    return {"workload": names[args.workload], "genes_per_gpu": sm.n_genes, "spots": sm.n_spots,
-            "nnz_per_gpu": sm.nnz, "n_comp": K_COMP, "reg_covar": 1e-3, "tol": 1e-3, "max_iter": 100,
-            "init": "on-device weighted k-means++ + Lloyd (replaces sklearn KMeans)",
-            "sharding": "genes: one independent data set per rank (weak); pairs: contiguous slices + all-gather",
-            "input_encoding": "uint16 spot + int16 value (4 B/value)" if sm.is_compact else "int32 spot + float32 value",
-            "l2": "L2 flushed (256 MiB write) between timed steps; S50 inputs (%.0f MB) also exceed the 126 MB L2"
-                  % (sm.nnz * (4 if sm.is_compact else 8) / 1e6)}
+    return {"workload": names[args.workload], "genes": sm.n_genes, "spots": sm.n_spots,
+            "nnz": sm.nnz, "n_comp": K_COMP, "reg_covar": 1e-3, "tol": 1e-3, "max_iter": 100,
+            "init": "each arm's own initialisation: sklearn KMeans (reference arm) / on-device weighted k-means++ + Lloyd (GPU arm)",
+            "sharding": "GPU arm: the genes of the one data set in contiguous nnz-balanced ranges, one per rank (strong "
+                        "scaling), one packed all-gather per step; pairs and EMD problems sharded likewise",
+            "l2": "GPU arm: L2 flushed (256 MiB write) between timed steps; the inputs (4 B per stored value) also exceed "
+                  "the 126 MB L2 at one GPU"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -205,19 +221,27 @@ def run_ours(args, rank, world, local_rank):
     from stminer_b200 import _lib
     from stminer_b200.Algorithm.distribution import fit_spot_matrix, fit_spot_matrix_host
     from stminer_b200.Algorithm.distance import gmm_pair_distances
-    from stminer_b200.sharding import allgather_pairs, pair_slice
+    from stminer_b200.sharding import gmm_pairs_sharded
     from stminer_b200.staging import DeviceSpotMatrix
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()
-    # host copy in the 4 B / value wire format (uint16 spot, int16 value) when the matrix allows it, page-locked
-    sm = workload(args.workload, seed=rank, genes=args.genes).compact().pin_memory()
+    from stminer_b200.sharding import fit_genes_sharded, pack_fit_result, shard_genes_contiguous
+    # ONE data set for all ranks (strong scaling); host copy in the 4 B / value wire format (uint16 spot, int16 value),
+    # page-locked.  Rank r owns the contiguous gene range [bounds[r], bounds[r + 1]).
+    sm = workload(args.workload, seed=0, genes=args.genes).compact().pin_memory()
     G = sm.n_genes
-    dsm = DeviceSpotMatrix(sm, device=dev)
+    bounds = shard_genes_contiguous(sm.col_ptr, world)
+    g0, g1 = int(bounds[rank]), int(bounds[rank + 1])
+    shard = sm.slice_genes(g0, g1)
+    dsm = DeviceSpotMatrix(shard, device=dev)
     order, buckets = dsm.plan(K_COMP, _lib.fit_flags(device_init=True, compact=dsm.compact))
     n_launch = int((buckets > 0).sum())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    n_max = int(np.diff(bounds).max())
+    C = 7 * K_COMP + 4
+    gbuf = torch.empty((world * n_max, C), dtype=torch.float64, device=dev)      # packed results of all ranks
 
     def barrier():
         if world > 1:
@@ -231,49 +255,68 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def step(res):
+        """One step of the hot path: fit this rank's genes; with several ranks pack the seven output arrays into the
+        rank's slot of the gather buffer and replicate them with one in-place all-gather."""
+        res = fit_spot_matrix(dsm, K_COMP, init=None, seed=1, out=res)
+        if world > 1:
+            gbuf[rank * n_max:rank * n_max + (g1 - g0)] = pack_fit_result(res, K_COMP)
+            dist.all_gather_into_tensor(gbuf, gbuf[rank * n_max:(rank + 1) * n_max])
+        return res
+
     res = None
     for _ in range(args.warmup):
-        res = fit_spot_matrix(dsm, K_COMP, init=None, seed=1, out=res)
+        res = step(res)
     barrier()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # ---- timed: exactly `steps` steps, device-resident inputs -------------------------------------
+    # ---- timed: exactly `steps` steps, shards resident in HBM ----------------------------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall = time.perf_counter()
     for s in range(args.steps):
         flush.fill_(s)                       # evict L2 between timed steps (not timed)
+        if world > 1:
+            dist.barrier()                   # every step starts together on all ranks (the all-gather ends it together)
         ev[s][0].record()
-        res = fit_spot_matrix(dsm, K_COMP, init=None, seed=1, out=res)
+        res = step(res)
         ev[s][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall
     step_ms = [a.elapsed_time(b) for a, b in ev]
     dev_ms = max_over_ranks(float(np.sum(step_ms)))
     ms_per_step = dev_ms / args.steps
-    value = world * G / (ms_per_step / 1e3)
+    value = G / (ms_per_step / 1e3)
 
-    host = res.to_host()
-    n_iter = host["n_iter"].astype(np.float64)
-    nnz = sm.nnz_per_gene().astype(np.float64)
-    ok = host["status"] == 0
-    flops = FLOP_PER_SPOT_COMP_ITER * float((nnz * n_iter * ok).sum()) * K_COMP
-    em_tflops = flops / (float(np.mean(step_ms)) / 1e3) / 1e12
+    host_local = res.to_host()
+    n_iter_l = host_local["n_iter"].astype(np.float64)
+    nnz_l = shard.nnz_per_gene().astype(np.float64)
+    ok_l = host_local["status"] == 0
+    flops_local = FLOP_PER_SPOT_COMP_ITER * float((nnz_l * n_iter_l * ok_l).sum()) * K_COMP
+    flops = flops_local
+    if world > 1:
+        t = torch.tensor([flops_local], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        flops = float(t.item())
+    em_tflops = flops / (ms_per_step / 1e3) / 1e12          # whole job (all ranks) over the step time
 
-    # ---- e2e: host buffers in / out through the public API ----------------------------------------
+    # ---- e2e: host buffers in / out through the public sharded API -----------------------------------
     for _ in range(2):
-        fit_spot_matrix_host(sm, K_COMP, init=None, device=dev, seed=1)
+        fit_genes_sharded(sm, K_COMP, init=None, device=dev, seed=1)
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
-        out = fit_spot_matrix_host(sm, K_COMP, init=None, device=dev, seed=1)
+        host = fit_genes_sharded(sm, K_COMP, init=None, device=dev, seed=1)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
-    h2d = int(sm.col_ptr.nbytes + sm.row_idx.nbytes + sm.val.nbytes + sm.spot_x.nbytes + sm.spot_y.nbytes
-              + 4 * sm.n_genes)   # + the per-chunk gene order
-    d2h = int(sum(v.nbytes for v in out.values()))
+    # bytes copied per step, summed over the ranks: every rank uploads its own columns (+ the spot table and its chunk
+    # orders) and reads the gathered parameters back
+    h2d = int(sm.col_ptr.nbytes + sm.row_idx.nbytes + sm.val.nbytes + world * (sm.spot_x.nbytes + sm.spot_y.nbytes) + 4 * G)
+    d2h = int(world * G * C * 8)
+    n_iter = host["n_iter"].astype(np.float64)
+    ok = host["status"] == 0
 
     # ---- second half of the metric: SVG-pair distances -------------------------------------------
     Gp = min(args.pairs_genes, int(ok.sum()))
@@ -282,11 +325,9 @@ def run_ours(args, rank, world, local_rank):
     MU = torch.from_numpy(host["means"][sel]).to(dev)
     COV = torch.from_numpy(host["covariances"][sel]).to(dev)
     total_pairs = Gp * (Gp - 1) // 2
-    pb, pe = pair_slice(total_pairs, rank, world)
 
     def pairs_step():
-        local = gmm_pair_distances(W, MU, COV, pb, pe, device=dev)
-        return allgather_pairs(local, total_pairs) if world > 1 else local
+        return gmm_pairs_sharded(W, MU, COV, device=dev)      # slice -> kernel writes its slot -> in-place all-gather
     for _ in range(2):
         pairs_step()
     barrier()
@@ -299,11 +340,12 @@ def run_ours(args, rank, world, local_rank):
     pairs_ms = max_over_ranks(e0.elapsed_time(e1) / 3)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- third kernel of the path: exact spot-level EMD (global image vs gene image), Visium-size problems ---
+    # ---- third kernel of the path: exact spot-level EMD (global image vs gene image), Visium-size problems, ----
+    # ---- sharded over the ranks like the loop of spatial_high_variable_genes (strong scaling) --------------
     emd = None
-    if args.emd_genes > 0 and rank == 0 and world == 1:      # single-GPU extras: keep the multi-rank runs short
+    if args.emd_genes > 0:
         from scipy import sparse as _sp
-        from stminer_b200.Algorithm.distance import emd_batched
+        from stminer_b200.sharding import emd_sharded
         from stminer_b200.Simulate import simulate_spot_matrix
         nt = max(1, (args.emd_genes + 3) // 4)
         vsm = simulate_spot_matrix("V", seed=0, n_templates=nt, replicas=4, truncate_int16=False)
@@ -313,16 +355,20 @@ def run_ours(args, rank, world, local_rank):
         for gi in range(min(args.emd_genes, vsm.n_genes)):
             a_, b_ = vsm.col_ptr[gi], vsm.col_ptr[gi + 1]
             tg.append((vsm.spot_x[vsm.row_idx[a_:b_]], vsm.spot_y[vsm.row_idx[a_:b_]], vsm.val[a_:b_].astype(np.float64)))
-        emd_batched(src, tg[:4], device=dev)                                  # warm-up (module load, allocator)
-        torch.cuda.synchronize()
+        emd_sharded(src, tg[:4 * world], device=dev)                          # warm-up (module load, allocator)
+        barrier()
         t_e = time.perf_counter()
-        ecost, estatus, eiters = emd_batched(src, tg, device=dev, return_iters=True)
-        torch.cuda.synchronize()
-        t_e = time.perf_counter() - t_e
+        ecost, estatus = emd_sharded(src, tg, device=dev)
+        barrier()
+        t_e = max_over_ranks(time.perf_counter() - t_e)
         emd = {"metric": "spot_emd_problems_per_sec", "value": len(tg) / t_e, "unit": "problems/s",
                "problems": len(tg), "source_spots": int(len(src[0])), "mean_target_spots": float(np.mean([len(t[0]) for t in tg])),
-               "seconds": t_e, "mean_pivots": float(eiters.mean()), "optimal": int((estatus == 0).sum()),
-               "note": "exact network simplex, numItermax=200000 as the reference; includes H2D/D2H of the problem data"}
+               "seconds": t_e, "optimal": int((estatus == 0).sum()),
+               "sharding": "problems dealt longest-first over %d rank(s), one all-gather of (cost, status)" % world,
+               "note": "exact network simplex with the multiscale start basis, numItermax=200000 as the reference; wall "
+                       "time of sharding.emd_sharded incl. H2D/D2H of the problem data and the gather",
+               "issue_slot_util": ncu_metric("emd_issue_active_pct"),
+               "ncu_file": "profiles/r2_ncu_emd_visium.txt"}
 
     # ---- the step after the distance matrix: cluster() = SMACOF MDS (4 restarts, 20 components) on the G x G matrix ----
     mds = None
@@ -406,29 +452,35 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": "genes_per_sec_gmm_fit", "value": value, "unit": "genes/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, sm, world),
-        "e2e": {"value": world * G / e2e_s, "unit": "genes/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s},
-        "gpu_launches": args.steps * n_launch,
+        "e2e": {"value": G / e2e_s, "unit": "genes/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s,
+                "api": "stminer_b200.sharding.fit_genes_sharded (what fit_gmms calls): host CSC matrix in, host parameter "
+                       "arrays out, on every rank"},
+        "gpu_launches": args.steps * n_launch * world,
+        "input_encoding": "uint16 spot + int16 value (4 B/value)" if sm.is_compact else "int32 spot + float32 value",
         "roofline": {"bound": "fp32_fma", "achieved": em_tflops, "peak": fma_peak, "unit": "TFLOP/s",
                      "frac": em_tflops / fma_peak,
                      # ncu --set full of this command's step launches (profiles/r1h_ncu_bench_step.txt):
                      # dram__bytes_read+write = 374.3 MB (large bucket) + 150.4 MB (medium) vs 506 MB of input
-                     "traffic": 524.6e6 if (args.workload == "S50" and not args.genes and sm.is_compact) else None,
-                     "traffic_unit": "bytes per step (sum over the step's bucket launches)",
+                     "traffic": ncu_metric("em_dram_bytes_per_step") if (args.workload == "S50" and not args.genes and world == 1) else None,
+                     "traffic_unit": "bytes per step (sum over the step's bucket launches), dram__bytes_read + write of the "
+                                     "committed ncu --set full capture (profiles/r2_ncu_metrics.json)",
                      "kernel": "gmm_em_kernel (%d nnz-bucket launches per step, run concurrently)" % n_launch,
                      "peak_source": "measured here with stm_bench_fma (FFMA chains); nominal %.1f TFLOP/s; "
                                     "MEASURED_PEAKS.json has no FP32 figure" % NOMINAL_FP32_TFLOPS,
                      "algorithmic_flops_per_step": flops,
                      "note": "EM sweeps only: 30 FLOP x nnz_g x K x n_iter_g; the k-means++/Lloyd init inside the "
                              "same launch is not credited",
-                     "hbm_frac": (sm.nnz * (4 if sm.is_compact else 8) + G * K_COMP * 7 * 8) / (float(np.mean(step_ms)) / 1e3) / 1e9 / peak_hbm()},
+                     "hbm_frac": (sm.nnz * (4 if sm.is_compact else 8) + G * K_COMP * 7 * 8) / (ms_per_step / 1e3) / 1e9 / (world * peak_hbm())},
         "pairs": {"metric": "svg_pair_gmm_distances_per_sec", "value": total_pairs / (pairs_ms / 1e3),
                   "unit": "pairs/s", "genes": Gp, "pairs": total_pairs, "ms": pairs_ms,
-                  "sharding": "contiguous pair slices per rank + NCCL all-gather" if world > 1 else "single GPU"},
+                  "sharding": "contiguous pair slices per rank written into the gather buffer + one in-place NCCL all-gather" if world > 1 else "single GPU",
+                  "issue_slot_util": ncu_metric("dist_issue_active_pct"), "ncu_file": "profiles/r2_ncu_dist.txt"},
         "fit": {"mean_n_iter": float(n_iter[ok].mean()), "genes_ok": int(ok.sum()), "genes_dropped": int((~ok).sum()),
-                "bucket_counts_cluster16_8_4_2_large_medium_small": buckets.tolist(), "wall_ms_per_step": 1e3 * t_wall / args.steps},
+                "genes_per_rank": np.diff(bounds).tolist(),
+                "bucket_counts_cluster16_8_4_2_large_medium_small_rank0": buckets.tolist(), "wall_ms_per_step": 1e3 * t_wall / args.steps},
         "emd": emd,
         "mds": mds,
         "s10": s10,
@@ -440,19 +492,44 @@ def run_ours(args, rank, world, local_rank):
         cpu = CpuReference(cores)
         rate, wall, mean_fit, n = cpu.rate(sm, n_sample)
         cpu.close()
-        # the other two stages of the path, on bounded samples, one core each (the reference runs them serially)
+        # quality of the on-device initialisation against the reference's (sklearn KMeans) on the SAME sample genes: final
+        # lower bound (mean log-likelihood per count) of the GPU fit minus that of the CPU fit
+        lb_gpu = host["lower_bound"][cpu.last_idx]
+        lb_cpu = cpu.last_lower_bound
+        both = np.isfinite(lb_cpu) & (host["status"][cpu.last_idx] == 0)
+        line["fit"]["lower_bound_vs_cpu"] = {
+            "genes": int(both.sum()), "gpu_mean": float(lb_gpu[both].mean()), "cpu_mean": float(lb_cpu[both].mean()),
+            "mean_diff": float((lb_gpu[both] - lb_cpu[both]).mean()),
+            "frac_gpu_within_0.01_or_better": float(np.mean(lb_gpu[both] >= lb_cpu[both] - 0.01)),
+            "note": "same genes as cpu_baseline.sample; CPU = sklearn GaussianMixture.lower_bound_ (KMeans init, unseeded), "
+                    "GPU = on-device k-means++ (exponential race) + capped Lloyd init; nats per count"}
+        # the other two stages of the path, on bounded samples (the reference runs them serially on one core)
         try:
-            from oracle import dist_oracle as do
+            n_p = 10240
             Wh, MUh, COVh = host["weights"][sel], host["means"][sel], host["covariances"][sel]
-            do.distribution_distance(Wh[0], MUh[0], COVh[0], Wh[1], MUh[1], COVh[1])          # numba compile
-            n_p = 24
-            t_c = time.perf_counter()
-            for q in range(n_p):
-                do.distribution_distance(Wh[q], MUh[q], COVh[q], Wh[q + 1], MUh[q + 1], COVh[q + 1])
-            t_c = time.perf_counter() - t_c
-            line["pairs"]["cpu_pairs_per_sec_1_core"] = n_p / t_c
+            rngp = np.random.default_rng(1)
+            ia = rngp.integers(0, len(sel), n_p); ib = (ia + 1 + rngp.integers(0, len(sel) - 1, n_p)) % len(sel)
+            chunks = np.array_split(np.arange(n_p), cores)
+            import multiprocessing as mp
+            with mp.get_context("spawn").Pool(cores, initializer=_pool_init) as pool:
+                pool.map(_cpu_pairs, [(Wh[:2], MUh[:2], COVh[:2], np.array([0]), np.array([1]))] * cores)   # numba compile
+                t_c = time.perf_counter()
+                outp = pool.map(_cpu_pairs, [(Wh, MUh, COVh, ia[c], ib[c]) for c in chunks])
+                t_c = time.perf_counter() - t_c
+            one_core = float(np.mean([o[1] / max(o[0], 1e-9) for o in outp]))
+            line["pairs"]["cpu_pairs_per_sec"] = n_p / t_c
+            line["pairs"]["cpu_pairs_per_sec_1_core"] = one_core
+            line["pairs"]["cpu_cores"] = cores
             line["pairs"]["cpu_note"] = ("reference arithmetic (K^2 njit Hellinger calls + scipy LSAP per pair, "
-                                         "distance.py:13-36) on %d pairs, one core" % n_p)
+                                         "distance.py:13-36) on %d random pairs of the fitted genes over a %d-process pool "
+                                         "(the reference itself has no parallel path for this stage)" % (n_p, cores))
+            # agreement of the device result on the sampled pairs
+            fullh = full.cpu().numpy()
+            lin = lambda i, j: (i * (2 * Gp - i - 1)) // 2 + (j - i - 1)
+            ref_d = np.concatenate([o[2] for o in outp])
+            ii = np.minimum(ia, ib); jj = np.maximum(ia, ib)
+            got_d = fullh[[lin(int(i), int(j)) for i, j in zip(ii, jj)]]
+            line["pairs"]["max_rel_diff_vs_cpu_sample"] = float(np.max(np.abs(got_d - ref_d) / np.maximum(np.abs(ref_d), 1e-12)))
         except Exception as e:        # pragma: no cover
             line["pairs"]["cpu_note"] = "cpu sample failed: %r" % (e,)
         if emd is not None:
@@ -463,9 +540,9 @@ def run_ours(args, rank, world, local_rank):
                 c_cpu, st_cpu, it_cpu = eo.emd_network_simplex(*src, *tg[small])
                 t_c = time.perf_counter() - t_c
                 emd["cpu_seconds_per_problem_1_core"] = t_c
-                emd["cpu_note"] = ("C restatement of the network simplex (POT is not installable here) on the smallest "
-                                   "problem of the batch (%d target spots, %d pivots), one core; GPU cost agrees to %.1e"
-                                   % (len(tg[small][0]), it_cpu, abs(c_cpu - float(ecost[small])) / max(1.0, abs(c_cpu))))
+                emd["cpu_note"] = ("C restatement of POT's network simplex from the artificial star (POT is not installable "
+                                   "here) on the smallest problem of the batch (%d target spots, %d pivots), one core; GPU cost "
+                                   "agrees to %.1e" % (len(tg[small][0]), it_cpu, abs(c_cpu - float(ecost[small])) / max(1.0, abs(c_cpu))))
             except Exception as e:    # pragma: no cover
                 emd["cpu_note"] = "cpu sample failed: %r" % (e,)
         line["cpu_baseline"] = {"value": rate, "unit": "genes/s", "cores": cores, "kind": "port",
@@ -473,6 +550,15 @@ def run_ours(args, rank, world, local_rank):
                                           "sklearn GaussianMixture.fit, KMeans init included), process-per-gene "
                                           "pool, 1 BLAS thread each; %.1f s wall, %.2f s mean per fit" % (n, wall, mean_fit)}
     print(json.dumps(line), flush=True)
+
+
+def ncu_metric(name):
+    """A number taken from the committed ncu captures of this command (profiles/r2_ncu_metrics.json, written by
+    scripts/ncu_summary.py from the .ncu-rep files); None when the file or the entry is missing."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_metrics.json"))).get(name)
+    except Exception:
+        return None
 
 
 def peak_hbm():

@@ -33,8 +33,9 @@ def _dev(a, device):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
 
 
-def gmm_pair_distances(W, MU, COV, pair_begin: int = 0, pair_end: Optional[int] = None, device=None):
-    """Distances of the linearised upper-triangle pairs [pair_begin, pair_end) as a CUDA float64 tensor."""
+def gmm_pair_distances(W, MU, COV, pair_begin: int = 0, pair_end: Optional[int] = None, device=None, out=None):
+    """Distances of the linearised upper-triangle pairs [pair_begin, pair_end) as a CUDA float64 tensor (``out``: a
+    contiguous float64 CUDA tensor of that length to write into, e.g. this rank's slot of a gather buffer)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     device = torch.device(device if device is not None else "cuda")
@@ -42,7 +43,11 @@ def gmm_pair_distances(W, MU, COV, pair_begin: int = 0, pair_end: Optional[int] 
     G, K = int(w.shape[0]), int(w.shape[1])
     total = G * (G - 1) // 2
     pair_end = total if pair_end is None else int(pair_end)
-    out = torch.empty((max(pair_end - pair_begin, 0),), dtype=torch.float64, device=device)
+    n_out = max(pair_end - pair_begin, 0)
+    if out is None:
+        out = torch.empty((n_out,), dtype=torch.float64, device=device)
+    elif out.numel() != n_out or out.dtype != torch.float64 or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError("out must be a contiguous float64 tensor of %d entries on %s" % (n_out, device))
     with torch.cuda.device(device):
         st = lib.stm_gmm_dist_pairs(_lib.ptr(w), _lib.ptr(mu), _lib.ptr(cov), G, K, int(pair_begin), pair_end,
                                     _lib.ptr(out), _lib.current_stream_ptr())

@@ -140,6 +140,7 @@ def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_
     # compute lanes; measured on B200 / S50: 25.5 ms against 28.8 ms for four equal chunks on one lane (23.9 ms resident)
     fractions = kw.pop("chunk_fractions", (0.03, 0.1, 0.25, 0.5, 0.75, 1.0) if n_chunks == 6 else None)
     two_lanes = kw.pop("two_lanes", True)
+    return_device = kw.pop("return_device", False)     # the device-resident FitResult instead of the host dict
     cuts = sm.nnz_balanced_chunks(n_chunks, fractions=fractions)
     from ..staging import StreamedDeviceSpotMatrix
     with torch.cuda.device(dev):
@@ -172,8 +173,11 @@ def fit_spot_matrix_host(sm: SpotMatrix, n_comp: int, init=None, device=None, n_
             keep.append((view, out))
         for lane in lanes[1:]:
             compute.wait_stream(lane)
-        host = full.to_host()
         compute.wait_stream(copy)
+        if return_device:
+            full._keepalive = (whole, keep)
+            return full
+        host = full.to_host()
     return host
 
 

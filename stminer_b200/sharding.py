@@ -31,10 +31,25 @@ def shard_genes_lpt(nnz: np.ndarray, world_size: int) -> List[np.ndarray]:
 
 
 def pair_slice(total_pairs: int, rank: int, world_size: int) -> Tuple[int, int]:
-    """Contiguous slice [begin, end) of the linearised upper triangle owned by ``rank``."""
-    base, rem = divmod(int(total_pairs), world_size)
-    begin = rank * base + min(rank, rem)
-    return begin, begin + base + (1 if rank < rem else 0)
+    """Contiguous slice [begin, end) of the linearised upper triangle owned by ``rank``: every rank owns
+    ceil(total / world) pairs except the last ones, which own what is left — so the ranks' slices, laid out at a fixed
+    stride, ARE the pair vector and the all-gather needs neither padding nor a re-assembly copy."""
+    n_max = -(-int(total_pairs) // world_size) if total_pairs > 0 else 0
+    begin = min(int(total_pairs), rank * n_max)
+    return begin, min(int(total_pairs), begin + n_max)
+
+
+def shard_genes_contiguous(col_ptr: np.ndarray, world_size: int) -> np.ndarray:
+    """Gene boundaries [world_size + 1] of contiguous gene ranges with (nearly) equal numbers of stored values: rank r
+    owns genes [b[r], b[r + 1]).  Contiguous ranges are views of the CSC matrix (no host gather before the upload) and
+    their results are contiguous rows of the gathered arrays; with thousands of genes per rank the work (stored values x
+    EM iterations) balances as well as a longest-first deal."""
+    col_ptr = np.asarray(col_ptr, dtype=np.int64)
+    G = len(col_ptr) - 1
+    targets = np.linspace(0, int(col_ptr[-1]), world_size + 1)
+    b = np.searchsorted(col_ptr, targets, side="left").astype(np.int64)
+    b[0], b[-1] = 0, G
+    return np.maximum.accumulate(np.minimum(b, G))
 
 
 def allgather_rows(local, owned_idx: List[np.ndarray], group=None):
@@ -46,10 +61,11 @@ def allgather_rows(local, owned_idx: List[np.ndarray], group=None):
     rank = dist.get_rank(group)
     n_max = max(len(ix) for ix in owned_idx)
     G = sum(len(ix) for ix in owned_idx)
-    pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[:len(owned_idx[rank])] = local
     gathered = torch.empty((world * n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(gathered, pad, group=group)
+    mine = gathered[rank * n_max:(rank + 1) * n_max]
+    mine[:len(owned_idx[rank])] = local
+    mine[len(owned_idx[rank]):] = 0
+    dist.all_gather_into_tensor(gathered, mine, group=group)           # in place: the input is this rank's slot
     out = torch.empty((G,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     for r in range(world):
         ix = torch.as_tensor(owned_idx[r], dtype=torch.long, device=local.device)
@@ -57,21 +73,35 @@ def allgather_rows(local, owned_idx: List[np.ndarray], group=None):
     return out
 
 
-def allgather_pairs(local, total_pairs: int, group=None):
-    """All-gather the contiguous pair slices into the full pair vector (length ``total_pairs``)."""
+def pair_gather_buffer(total_pairs: int, world_size: int, dtype, device):
+    """Buffer of world x ceil(total / world) entries whose first ``total_pairs`` entries are the pair vector once every
+    rank has written its slice at ``pair_slice`` and ``allgather_pairs_inplace`` has run."""
     import torch
+    n_max = -(-int(total_pairs) // world_size) if total_pairs > 0 else 0
+    return torch.empty((world_size * n_max,), dtype=dtype, device=device)
+
+
+def allgather_pairs_inplace(buf, total_pairs: int, group=None):
+    """In-place all-gather of the slices the ranks wrote into ``buf`` (see ``pair_gather_buffer``); returns the view
+    ``buf[:total_pairs]`` — no padding copy, no concatenation."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    n_max = -(-int(total_pairs) // world)
-    pad = torch.zeros((n_max,), dtype=local.dtype, device=local.device)
-    pad[:local.numel()] = local
-    gathered = torch.empty((world * n_max,), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(gathered, pad, group=group)
-    parts = []
-    for r in range(world):
-        b, e = pair_slice(total_pairs, r, world)
-        parts.append(gathered[r * n_max:r * n_max + (e - b)])
-    return torch.cat(parts)
+    rank = dist.get_rank(group)
+    n_max = buf.numel() // world
+    dist.all_gather_into_tensor(buf, buf[rank * n_max:(rank + 1) * n_max], group=group)
+    return buf[:int(total_pairs)]
+
+
+def allgather_pairs(local, total_pairs: int, group=None):
+    """All-gather the contiguous pair slices into the full pair vector (length ``total_pairs``); ``local`` is this rank's
+    slice.  (One copy of the local slice into the gather buffer; ``gmm_pairs_sharded`` writes there directly.)"""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    buf = pair_gather_buffer(total_pairs, world, local.dtype, local.device)
+    b, e = pair_slice(total_pairs, rank, world)
+    buf[b:e] = local
+    return allgather_pairs_inplace(buf, total_pairs, group=group)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -96,32 +126,72 @@ def _collective_device(group=None):
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
 
 
-def fit_genes_sharded(sm, n_comp: int, init=None, group=None, compute=None, **kw) -> dict:
-    """GMM fit of every gene of the SpotMatrix ``sm`` with the genes dealt LPT-wise over the ranks:
-    each rank uploads and fits only its own columns, one all-gather per output array replicates the result.
-    Returns the same host dict as ``fit_spot_matrix_host``, in ``sm`` gene order, on every rank."""
+FIT_FIELDS = ("weights", "means", "covariances", "n_iter", "converged", "lower_bound", "status")
+
+
+def pack_fit_result(res, K: int):
+    """One [n, 7K + 4] float64 tensor holding every output array of a fit (device ``FitResult`` or host dict): the
+    gather of a stage is ONE collective instead of seven.  The int32 fields are exact in float64."""
     import torch
+    if isinstance(res, dict):
+        cols = [torch.from_numpy(np.ascontiguousarray(res[k])).to(torch.float64).reshape(len(res["status"]), -1) for k in FIT_FIELDS]
+    else:
+        n = res.status.shape[0]
+        cols = [getattr(res, k).to(torch.float64).reshape(n, -1) for k in FIT_FIELDS]
+    return torch.cat(cols, dim=1)
+
+
+def unpack_fit_rows(rows: np.ndarray, K: int) -> dict:
+    """Inverse of ``pack_fit_result`` on a host array [G, 7K + 4]."""
+    G = rows.shape[0]
+    return dict(weights=np.ascontiguousarray(rows[:, :K]), means=np.ascontiguousarray(rows[:, K:3 * K]).reshape(G, K, 2),
+                covariances=np.ascontiguousarray(rows[:, 3 * K:7 * K]).reshape(G, K, 2, 2),
+                n_iter=rows[:, 7 * K].astype(np.int32), converged=rows[:, 7 * K + 1].astype(np.int32),
+                lower_bound=np.ascontiguousarray(rows[:, 7 * K + 2]), status=rows[:, 7 * K + 3].astype(np.int32))
+
+
+def gather_fit_rows(packed, bounds: np.ndarray, group=None):
+    """All-gather of the ranks' packed rows (rank r holds genes [bounds[r], bounds[r + 1])) — one in-place collective on
+    a buffer with a fixed stride per rank; returns the host array [G, C] in gene order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lens = np.diff(bounds)
+    n_max = int(lens.max())
+    buf = torch.empty((world * n_max, packed.shape[1]), dtype=packed.dtype, device=packed.device)
+    buf[rank * n_max:rank * n_max + packed.shape[0]] = packed
+    dist.all_gather_into_tensor(buf, buf[rank * n_max:(rank + 1) * n_max], group=group)
+    h = buf.cpu().numpy()
+    return np.concatenate([h[r * n_max:r * n_max + int(lens[r])] for r in range(world)], axis=0)
+
+
+def fit_genes_sharded(sm, n_comp: int, init=None, group=None, compute=None, **kw) -> dict:
+    """GMM fit of every gene of the SpotMatrix ``sm`` with the genes cut into one contiguous, nnz-balanced range per
+    rank: each rank uploads and fits only its own columns (a view of the host matrix, no gather), the
+    fitted arrays are packed into one device buffer and replicated by ONE all-gather, and read back once.
+    Returns the same host dict as ``fit_spot_matrix_host``, in ``sm`` gene order, on every rank."""
     rank, world = group_rank_world(group)
     if compute is None:
         from .Algorithm.distribution import fit_spot_matrix_host as compute
+        kw = dict(kw, return_device=True) if world > 1 else kw
     if world == 1:
         return compute(sm, n_comp, init=init, **kw)
-    owned = shard_genes_lpt(sm.nnz_per_gene(), world)
-    mine = owned[rank]
-    sub_init = None if init is None else tuple(np.asarray(a)[mine] for a in init)
-    local = compute(sm.select(mine), n_comp, init=sub_init, **kw)
-    dev = _collective_device(group)
-    out = {}
-    for k, v in local.items():
-        out[k] = allgather_rows(torch.from_numpy(np.ascontiguousarray(v)).to(dev), owned, group=group).cpu().numpy()
-    return out
+    bounds = shard_genes_contiguous(sm.col_ptr, world)
+    g0, g1 = int(bounds[rank]), int(bounds[rank + 1])
+    sub_init = None if init is None else tuple(np.asarray(a)[g0:g1] for a in init)
+    local = compute(sm.slice_genes(g0, g1), n_comp, init=sub_init, **kw)
+    packed = pack_fit_result(local, n_comp).to(_collective_device(group))
+    return unpack_fit_rows(gather_fit_rows(packed, bounds, group=group), int(n_comp))
 
 
 def gmm_pairs_sharded(W, MU, COV, group=None, device=None, compute=None):
     """All pair distances of G mixtures with the linearised upper triangle cut into one contiguous slice per rank;
-    returns the full pair vector (tensor on the collective's device) on every rank."""
+    every rank computes its slice straight into its slot of the gather buffer and one in-place all-gather makes the
+    pair vector (tensor on the collective's device) complete on every rank."""
     import torch
     rank, world = group_rank_world(group)
+    own_kernel = compute is None
     if compute is None:
         from .Algorithm.distance import gmm_pair_distances as compute
     G = int(W.shape[0])
@@ -129,8 +199,13 @@ def gmm_pairs_sharded(W, MU, COV, group=None, device=None, compute=None):
     if world == 1:
         return compute(W, MU, COV, 0, total, device=device)
     b, e = pair_slice(total, rank, world)
+    cdev = _collective_device(group)
+    if own_kernel and cdev.type == "cuda":
+        buf = pair_gather_buffer(total, world, torch.float64, cdev)
+        compute(W, MU, COV, b, e, device=cdev, out=buf[b:e])
+        return allgather_pairs_inplace(buf, total, group=group)
     local = compute(W, MU, COV, b, e, device=device)
-    return allgather_pairs(local.to(_collective_device(group)), total, group=group)
+    return allgather_pairs(local.to(cdev), total, group=group)
 
 
 def emd_sharded(src, targets, group=None, compute=None, **kw):

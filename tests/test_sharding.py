@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from stminer_b200.sharding import allgather_pairs, allgather_rows, pair_slice, shard_genes_lpt
+from stminer_b200.sharding import allgather_pairs, allgather_rows, pair_slice, shard_genes_contiguous, shard_genes_lpt
 
 
 def test_shard_genes_lpt_balances_and_partitions():
@@ -21,13 +21,26 @@ def test_shard_genes_lpt_balances_and_partitions():
         assert loads.max() <= loads.mean() * 1.05 + nnz.max()
 
 
+def test_shard_genes_contiguous_balances_stored_values():
+    rng = np.random.default_rng(1)
+    nnz = (rng.pareto(1.5, 5000) * 1000 + 100).astype(np.int64)
+    col_ptr = np.concatenate([[0], np.cumsum(nnz)])
+    for world in (1, 2, 4, 8):
+        b = shard_genes_contiguous(col_ptr, world)
+        assert b[0] == 0 and b[-1] == 5000 and (np.diff(b) >= 0).all() and len(b) == world + 1
+        loads = np.diff(col_ptr[b])
+        assert loads.max() <= loads.mean() + nnz.max()
+    assert shard_genes_contiguous(np.array([0, 3, 5]), 8)[-1] == 2            # more ranks than genes: empty ranges
+
+
 def test_pair_slice_covers_triangle():
     for total, world in ((7998000, 8), (10, 3), (0, 4), (5, 8)):
         cuts = [pair_slice(total, r, world) for r in range(world)]
         assert cuts[0][0] == 0 and cuts[-1][1] == total
         assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
         sizes = [e - b for b, e in cuts]
-        assert max(sizes) - min(sizes) <= 1
+        n_max = -(-total // world) if total else 0          # fixed stride: all slices full except the trailing ones
+        assert all(b == min(total, r * n_max) for r, (b, e) in enumerate(cuts)) and max(sizes, default=0) <= n_max
 
 
 def _worker(rank, world, port, G, total_pairs):
@@ -71,8 +84,10 @@ def _stage_worker(rank, world, port):
             nnz = m.nnz_per_gene().astype(np.float64)
             tot = np.array([m.val[m.col_ptr[g]:m.col_ptr[g + 1]].sum() for g in range(m.n_genes)], dtype=np.float64)
             extra = 0.0 if init is None else np.asarray(init[0]).sum(axis=1)
+            G_ = m.n_genes
             return {"weights": np.repeat((nnz + extra)[:, None], n_comp, axis=1), "means": np.tile(tot[:, None, None], (1, n_comp, 2)),
-                    "status": (nnz > 0).astype(np.int32)}
+                    "covariances": np.tile((nnz * 0.5)[:, None, None, None], (1, n_comp, 2, 2)), "n_iter": (nnz % 7).astype(np.int32),
+                    "converged": (nnz % 2).astype(np.int32), "lower_bound": -tot / 3.0, "status": (nnz > 0).astype(np.int32)}
         init = (np.arange(sm.n_genes * K, dtype=np.float64).reshape(sm.n_genes, K),)
         for ini in (None, init):
             a = fit_genes_sharded(sm, K, init=ini, compute=fake_fit)
