@@ -460,16 +460,16 @@ def run_ours(args, rank, world, local_rank):
                        "arrays out, on every rank"},
         "gpu_launches": args.steps * n_launch * world,
         "input_encoding": "uint16 spot + int16 value (4 B/value)" if sm.is_compact else "int32 spot + float32 value",
-        "roofline": {"bound": "fp32_fma", "achieved": em_tflops, "peak": fma_peak, "unit": "TFLOP/s",
-                     "frac": em_tflops / fma_peak,
+        "roofline": {"bound": "fp32_fma", "achieved": em_tflops, "peak": world * fma_peak, "unit": "TFLOP/s",
+                     "frac": em_tflops / (world * fma_peak),
                      # ncu --set full of this command's step launches (profiles/r1h_ncu_bench_step.txt):
                      # dram__bytes_read+write = 374.3 MB (large bucket) + 150.4 MB (medium) vs 506 MB of input
                      "traffic": ncu_metric("em_dram_bytes_per_step") if (args.workload == "S50" and not args.genes and world == 1) else None,
                      "traffic_unit": "bytes per step (sum over the step's bucket launches), dram__bytes_read + write of the "
                                      "committed ncu --set full capture (profiles/r2_ncu_metrics.json)",
                      "kernel": "gmm_em_kernel (%d nnz-bucket launches per step, run concurrently)" % n_launch,
-                     "peak_source": "measured here with stm_bench_fma (FFMA chains); nominal %.1f TFLOP/s; "
-                                    "MEASURED_PEAKS.json has no FP32 figure" % NOMINAL_FP32_TFLOPS,
+                     "peak_source": "measured here with stm_bench_fma (FFMA chains) on one GPU x n_gpus; nominal %.1f TFLOP/s per "
+                                    "GPU; MEASURED_PEAKS.json has no FP32 figure" % NOMINAL_FP32_TFLOPS,
                      "algorithmic_flops_per_step": flops,
                      "note": "EM sweeps only: 30 FLOP x nnz_g x K x n_iter_g; the k-means++/Lloyd init inside the "
                              "same launch is not credited",

@@ -72,6 +72,13 @@ constexpr int KM_LMAX = 6;                // greedy k-means++ candidates: 2 + fl
 #ifndef STM_EM_PREFETCH
 #define STM_EM_PREFETCH 0     // load the next step's spots before computing the current one (manual software pipelining)
 #endif
+#ifndef STM_EM_NOMAX
+#define STM_EM_NOMAX 0        // 1 = E-step without the per-spot max over the components: the log-density offsets are shifted by their
+                              // maximum over the components once per iteration (an upper bound of every log density), so ex2 cannot
+                              // overflow; a spot whose densities ALL underflow (> ~12 sigma from every component) takes a slow path.
+                              // 12 % fewer instructions in the sweep, parity green — and no gain (23.92 vs 23.80 ms on S50): the sweep
+                              // is not issue-bound, see profiles/r2_tuning_log.txt
+#endif
 #ifndef STM_EM_LL_BATCH
 #define STM_EM_LL_BATCH 0     // fold the FP32 log-likelihood partial into FP64 every 8 steps instead of every step
 #endif
@@ -216,6 +223,28 @@ __device__ __forceinline__ bool refresh_component(int k, double* s_d, float* s_p
   float* pq = s_par + (L::F_PP - L::F_PAR) + ((sub * (KT / 2) + (j >> 1)) * 6) * 2 + (j & 1);
   if (j < 2 * (KT / 2)) { pq[0] = a00; pq[2] = b0; pq[4] = a01; pq[6] = a11; pq[8] = b1; pq[10] = c2; }
   return ok;
+}
+
+// STM_EM_NOMAX: shift the K log-density offsets c_k (s_par[8k + 5] and the pair-interleaved copy) by their maximum, kept in
+// s_d[D_MISC + 7] and added back when the lower bound is formed.  lp_k(x) = c_k - |t_k(x)|^2 <= c_k, so after the shift every
+// ex2 argument is <= 0.  Called by the whole CTA between two barriers.
+template <typename L>
+__device__ __forceinline__ void shift_log_offsets(int K, double* s_d, float* s_par, int tid) {
+  constexpr int KT = L::KT_;
+  if (tid < 32) {
+    float c = -INFINITY;
+    for (int k = tid; k < K; k += 32) c = fmaxf(c, s_par[8 * k + 5]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(FULL_MASK, c, o));
+    for (int k = tid; k < K; k += 32) {
+      const float v = s_par[8 * k + 5] - c;
+      s_par[8 * k + 5] = v;
+      const int sub = k / KT, j = k % KT;
+      float* pq = s_par + (L::F_PP - L::F_PAR) + ((sub * (KT / 2) + (j >> 1)) * 6) * 2 + (j & 1);
+      if (j < 2 * (KT / 2)) pq[10] = v;
+    }
+    if (tid == 0) s_d[L::D_MISC + 7] = (double)c;
+  }
 }
 
 __device__ __forceinline__ int pack_xy(int x, int y) {
@@ -393,6 +422,75 @@ __device__ __forceinline__ void em_sweep_packed(const Src& src, int i_begin, int
     f2 qp[S][NPA];
     float qs[S];
 #endif
+#if STM_EM_NOMAX
+    // the offsets are shifted so that every log density is <= 0 (shift_log_offsets): no max pass, ex2 straight away
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const f2 xx = f2_make(x[s], x[s]), yy = f2_make(y[s], y[s]);
+      m[s] = 0.f;
+      f2 sp = f2_make(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        t0p[s][q] = f2_fma(xx, pp[q][0], pp[q][1]);
+        t1p[s][q] = f2_fma(xx, pp[q][2], f2_fma(yy, pp[q][3], pp[q][4]));
+#if STM_EM_QMOMENT
+        qp[s][q] = f2_fma(t0p[s][q], t0p[s][q], f2_mul(t1p[s][q], t1p[s][q]));
+        const f2 d = f2_sub(pp[q][5], qp[s][q]);
+#else
+        const f2 d = f2_sub(pp[q][5], f2_fma(t0p[s][q], t0p[s][q], f2_mul(t1p[s][q], t1p[s][q])));
+#endif
+        lpp[s][q] = f2_make(ex2_approx(d.x), ex2_approx(d.y));
+        sp = f2_add(sp, lpp[s][q]);
+      }
+      sum[s] = sp.x + sp.y;
+      if constexpr (R == 1) {
+        t0s[s] = fmaf(x[s], ps[0], ps[1]);
+        t1s[s] = fmaf(x[s], ps[2], fmaf(y[s], ps[3], ps[4]));
+#if STM_EM_QMOMENT
+        qs[s] = fmaf(t0s[s], t0s[s], t1s[s] * t1s[s]);
+        lps[s] = ex2_approx(ps[5] - qs[s]);
+#else
+        lps[s] = ex2_approx(fmaf(-t0s[s], t0s[s], fmaf(-t1s[s], t1s[s], ps[5])));
+#endif
+        sum[s] += lps[s];
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int o = 1; o < GS; o <<= 1) sum[s] += __shfl_xor_sync(FULL_MASK, sum[s], o);
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      // every density of a spot underflowed (farther than ~12 sigma from all components): redo that spot with the max
+      // of its log densities, as the reference's logsumexp does.  Uniform over the warp; practically never taken.
+      const bool tiny = sum[s] < 1e-30f && w[s] > 0.f;
+      if (__any_sync(FULL_MASK, tiny)) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          const f2 d = f2_sub(pp[q][5], f2_fma(t0p[s][q], t0p[s][q], f2_mul(t1p[s][q], t1p[s][q])));
+          mx = fmaxf(mx, fmaxf(d.x, d.y));
+        }
+        if constexpr (R == 1) mx = fmaxf(mx, fmaf(-t0s[s], t0s[s], fmaf(-t1s[s], t1s[s], ps[5])));
+#pragma unroll
+        for (int o = 1; o < GS; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, o));
+        if (!tiny) mx = 0.f;                 // the group's lanes agree on `tiny` (sum and w are group-uniform)
+        float sm2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          const f2 d = f2_sub(pp[q][5], f2_fma(t0p[s][q], t0p[s][q], f2_mul(t1p[s][q], t1p[s][q])));
+          lpp[s][q] = f2_make(ex2_approx(d.x - mx), ex2_approx(d.y - mx));
+          sm2 += lpp[s][q].x + lpp[s][q].y;
+        }
+        if constexpr (R == 1) { lps[s] = ex2_approx(fmaf(-t0s[s], t0s[s], fmaf(-t1s[s], t1s[s], ps[5])) - mx); sm2 += lps[s]; }
+#pragma unroll
+        for (int o = 1; o < GS; o <<= 1) sm2 += __shfl_xor_sync(FULL_MASK, sm2, o);
+        sum[s] = sm2; m[s] = mx;
+      }
+      if (!(w[s] > 0.f)) sum[s] = 1.f;       // padding lanes (weight 0): keep rcp finite
+    }
+#else
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const f2 xx = f2_make(x[s], x[s]), yy = f2_make(y[s], y[s]);
@@ -444,6 +542,7 @@ __device__ __forceinline__ void em_sweep_packed(const Src& src, int i_begin, int
 #pragma unroll
       for (int o = 1; o < GS; o <<= 1) sum[s] += __shfl_xor_sync(FULL_MASK, sum[s], o);
     }
+#endif
     float wl = 0.f;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -1150,6 +1249,10 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
     if (!refresh_component<L>(tid, s_d, s_par)) atomicOr(&s_flag[1], 1);
   }
   __syncthreads();
+#if STM_EM_NOMAX && STM_EM_PACKED
+  shift_log_offsets<L>(K, s_d, s_par, tid);
+  __syncthreads();
+#endif
 
   EM_PROF(pf_assign)
 #if STM_EM_L2_PREFETCH
@@ -1234,9 +1337,16 @@ __global__ void __launch_bounds__(T, MINB) gmm_em_kernel(const EmArgs p) {
       double t = 0.0;
       for (int w = 0; w < WARPS; ++w) t += ll_all[w];
       // log2 domain -> natural log; mean over the N replicated rows (_base.py:332)
+#if STM_EM_NOMAX && STM_EM_PACKED
+      t += s_d[L::D_MISC + 7] * N_total;     // the offset the sweep's coefficients were shifted by (every spot: w * cmax)
+#endif
       s_d[L::D_MISC + 1] = t * 0.69314718055994530942 / N_total;
     }
     __syncthreads();
+#if STM_EM_NOMAX && STM_EM_PACKED
+    shift_log_offsets<L>(K, s_d, s_par, tid);   // the refreshed coefficients, for the next sweep
+    __syncthreads();
+#endif
     lb = s_d[L::D_MISC + 1];
     failed = s_flag[1] != 0;
     const double change = lb - lb_prev;
