@@ -200,6 +200,30 @@ int stm_emd_spots_batched_wide(const int32_t* src_x, const int32_t* src_y, const
                                double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream);
 
 /*
+ * Device-side staging: spot-by-gene CSR matrix -> the gene-major (CSC) arrays stm_gmm_fit_batched reads.
+ *
+ * Replaces the per-gene host staging of the reference's fit path: get_exp_array / _preprocess
+ * STMiner/Algorithm/AlgUtils.py:8-36 (adata[:, gene].X sliced per gene, coo_matrix(..., dtype=int16)), called per gene from
+ * STMiner/Algorithm/distribution.py:122.
+ *
+ *   indptr[n_obs+1] int64, indices int32, data float32: canonical CSR (distinct columns inside a row), rows = observations
+ *   col_map[n_var]   output column of every input column, -1 = gene not selected (one-to-one)
+ *   row_order[n_obs] the input row that holds spot s, spots in the order the output indexes them (row-major (x, y));
+ *                    the rows must sit on distinct spots
+ *   compact != 0     outputs are {uint16 spot, int16 value} (n_obs <= 65,536), else {int32 spot, float32 value}
+ *   out_col_ptr[n_out+1] int64; out_row_idx / out_val sized for every stored entry of the input (an upper bound)
+ * Values are truncated toward zero and wrapped to int16 (AlgUtils.py:35), zeros are dropped, the entries of a column are in
+ * increasing spot index — the arrays SpotMatrix.from_matrix builds on the host.  Stable transposition without atomics:
+ * stm_stage_blocks(n_obs) row blocks, per-(block, column) counters in the workspace.
+ */
+int32_t stm_stage_blocks(int32_t n_obs);
+int64_t stm_stage_workspace_bytes(int32_t n_obs, int32_t n_out);
+int stm_stage_csr_columns(const int64_t* indptr, const int32_t* indices, const float* data, int32_t n_obs,
+                          const int32_t* col_map, int32_t n_out, const int32_t* row_order, uint32_t compact,
+                          void* workspace, int64_t workspace_bytes, int64_t out_capacity,
+                          int64_t* out_col_ptr, void* out_row_idx, void* out_val, void* stream);
+
+/*
  * Metric MDS by SMACOF on a precomputed dissimilarity matrix, float64, whole iteration loop on the device.
  *
  * Replaces: the MDS half of cluster()   STMiner/Algorithm/algorithm.py:54-55

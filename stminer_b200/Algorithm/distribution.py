@@ -229,8 +229,19 @@ def fit_gmms(adata, gene_name_list, n_comp=15, binary=False, threshold=95, max_i
     ``binary`` / ``cut`` / ``threshold`` (``preprocess_array``, distribution.py:133-145) transform the staged counts on
     the host (a per-gene percentile over the dense grid) before the upload.
     """
-    from ..adata_lite import spot_matrix_from_adata
+    from ..adata_lite import column_indices, spot_matrix_from_adata
+    from ..sharding import group_rank_world
+    from ..staging import device_staging_supported, stage_csr_on_device
     gene_name_list = list(gene_name_list)
+    if not (binary or cut) and init_params is None and group_rank_world()[1] == 1:
+        # one process, plain fit: the CSR matrix goes to the device as it is and is staged there (csrc/staging.cu)
+        cols = column_indices(adata, gene_name_list)
+        x, y = np.asarray(adata.obs["x"]), np.asarray(adata.obs["y"])
+        if device_staging_supported(adata.X, x, y, cols):
+            dsm = stage_csr_on_device(adata.X, x, y, list(adata.var_names), columns=cols, device=device)
+            res = fit_spot_matrix(dsm, n_comp, init=None, max_iter=max_iter, reg_covar=reg_covar,
+                                  remove_low_exp_spots=remove_low_exp_spots, seed=seed)
+            return result_to_gmm_dict(dsm.host.genes, res.to_host())
     sm = spot_matrix_from_adata(adata, gene_name_list)
     if binary or cut:
         sm = sm.preprocess_array(binary=binary, cut=cut and not binary, threshold=threshold,

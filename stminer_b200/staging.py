@@ -320,3 +320,101 @@ class _GeneRange:
     @property
     def n_spots(self) -> int:
         return len(self.spot_x)
+
+
+class _StagedHost:
+    """Host-side description of a matrix staged ON the device: what the launch plan and the result assembly need
+    (column pointers, gene names, the spot table) — the stored values themselves never existed on the host."""
+
+    def __init__(self, col_ptr, genes, spot_x, spot_y, compact):
+        self.col_ptr = np.ascontiguousarray(col_ptr, dtype=np.int64)
+        self.genes = list(genes)
+        self.spot_x, self.spot_y = spot_x, spot_y
+        self.is_compact = bool(compact)
+
+    @property
+    def n_genes(self) -> int:
+        return len(self.col_ptr) - 1
+
+    @property
+    def n_spots(self) -> int:
+        return len(self.spot_x)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col_ptr[-1])
+
+    def nnz_per_gene(self) -> np.ndarray:
+        return np.diff(self.col_ptr)
+
+
+def device_staging_supported(X, x, y, columns) -> bool:
+    """The device staging takes a canonical CSR matrix of float32 / small-integer values whose rows sit on DISTINCT (x, y)
+    spots, and a gene selection without repeats; everything else goes through ``SpotMatrix.from_matrix`` on the host."""
+    if not sparse.issparse(X) or X.format != "csr":
+        return False
+    if X.dtype not in (np.float32, np.int16, np.int32, np.uint8, np.uint16, np.int8):
+        return False
+    if X.dtype == np.int32 and X.nnz and (np.abs(X.data).max() >= 2 ** 24):
+        return False
+    if columns is not None and len(set(int(c) for c in columns)) != len(columns):
+        return False
+    key = np.asarray(x).astype(np.int64).ravel() * (int(np.max(y)) + 1 if len(y) else 1) + np.asarray(y).astype(np.int64).ravel()
+    return len(np.unique(key)) == len(key)
+
+
+def stage_csr_on_device(X, x, y, genes, columns=None, device=None) -> DeviceSpotMatrix:
+    """``SpotMatrix.from_matrix`` + upload, done on the device (csrc/staging.cu): the spot-by-gene CSR arrays are
+    uploaded as they are and ONE stable transposition writes the selected genes' columns in the hot path's layout —
+    int16 truncation / wrap (AlgUtils.py:35), zeros dropped, entries by increasing spot index, the 4 B / value encoding
+    when there are at most 65,536 spots.  Same arrays as the host staging produces (tests compare them).  The caller
+    checks ``device_staging_supported`` first."""
+    import torch
+    from . import _lib
+    _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else "cuda")
+    if not X.has_canonical_format:
+        X = X.copy()
+        X.sum_duplicates()
+    x = np.asarray(x).astype(np.int64).ravel()
+    y = np.asarray(y).astype(np.int64).ravel()
+    n_obs, n_var = X.shape
+    ymul = int(y.max()) + 1 if len(y) else 1
+    key = x * ymul + y
+    row_order = np.argsort(key, kind="stable").astype(np.int32)          # spot s (row-major (x, y) order) <- input row
+    skey = key[row_order]
+    if columns is None:
+        columns = np.arange(n_var, dtype=np.int64)
+    columns = np.asarray(columns, dtype=np.int64)
+    n_out = len(columns)
+    col_map = np.full(n_var, -1, dtype=np.int32)
+    col_map[columns] = np.arange(n_out, dtype=np.int32)
+    compact = n_obs <= 65536
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+    with torch.cuda.device(dev):
+        d_indptr = up(X.indptr.astype(np.int64, copy=False))
+        d_indices = up(X.indices.astype(np.int32, copy=False))
+        d_data = up(X.data.astype(np.float32, copy=False))
+        d_map, d_order = up(col_map), up(row_order)
+        cap = int(X.nnz)
+        row_idx = torch.empty(max(cap, 1), dtype=torch.int16 if compact else torch.int32, device=dev)
+        val = torch.empty(max(cap, 1), dtype=torch.int16 if compact else torch.float32, device=dev)
+        col_ptr = torch.empty(n_out + 1, dtype=torch.int64, device=dev)
+        ws_bytes = int(lib.stm_stage_workspace_bytes(n_obs, n_out))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        st = lib.stm_stage_csr_columns(_lib.ptr(d_indptr), _lib.ptr(d_indices), _lib.ptr(d_data), n_obs, _lib.ptr(d_map), n_out,
+                                       _lib.ptr(d_order), 1 if compact else 0, _lib.ptr(ws), ws_bytes, cap,
+                                       _lib.ptr(col_ptr), _lib.ptr(row_idx), _lib.ptr(val), _lib.current_stream_ptr())
+        _lib.check(st, "stm_stage_csr_columns")
+        host_col_ptr = col_ptr.cpu().numpy()                             # the launch plan needs the column lengths
+    spot_x = (skey // ymul).astype(np.int32); spot_y = (skey % ymul).astype(np.int32)
+    dsm = DeviceSpotMatrix.__new__(DeviceSpotMatrix)
+    dsm.host = _StagedHost(host_col_ptr, [genes[c] for c in columns], spot_x, spot_y, compact)
+    dsm.device, dsm.compact, dsm._plans = dev, compact, {}
+    dsm.col_ptr, dsm.row_idx, dsm.val = col_ptr, row_idx, val
+    dsm.spot_x, dsm.spot_y = up(spot_x), up(spot_y)
+    dsm._up = lambda a, k=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+    dsm.h2d_bytes = int(X.indptr.nbytes + X.nnz * 8 + col_map.nbytes + row_order.nbytes + 2 * spot_x.nbytes)
+    dsm._keepalive = (d_indptr, d_indices, d_data, d_map, d_order, ws)
+    return dsm
