@@ -7,7 +7,7 @@ A "step" is one pass of the hot path over one batch: the count-weighted GMM fit 
 k-means++/Lloyd initialisation + EM, K=20, reg_covar=tol=1e-3, max_iter=100 — the reference's
 ``fit_pattern`` defaults) of every gene of the synthetic Stereo-seq bin50 data set
 (40,000 bins x 10,000 genes, BASELINE.json configs[2], the configuration the genes/s target is quoted on).
-With N ranks the genes of that ONE data set are cut into contiguous, nnz-balanced ranges, one per rank (BASELINE
+With N ranks the genes of that ONE data set are dealt over the ranks in chunks of consecutive genes (BASELINE
 configs[2]: "genes sharded over 1/2/4/8 B200" — strong scaling); a step then ends with the one packed NCCL
 all-gather that replicates the fitted parameters on every rank.
 
@@ -211,8 +211,8 @@ def workload_config(args, sm, world):
     return {"workload": names[args.workload], "genes": sm.n_genes, "spots": sm.n_spots,
             "nnz": sm.nnz, "n_comp": K_COMP, "reg_covar": 1e-3, "tol": 1e-3, "max_iter": 100,
             "init": "each arm's own initialisation: sklearn KMeans (reference arm) / on-device weighted k-means++ + Lloyd (GPU arm)",
-            "sharding": "GPU arm: the genes of the one data set in contiguous nnz-balanced ranges, one per rank (strong "
-                        "scaling), one packed all-gather per step; pairs and EMD problems sharded likewise",
+            "sharding": "GPU arm: the genes of the one data set dealt over the ranks in chunks of 16 consecutive genes, longest "
+                        "first (strong scaling), one packed all-gather per step; pairs and EMD problems sharded likewise",
             "l2": "GPU arm: L2 flushed (256 MiB write) between timed steps; the inputs (4 B per stored value) also exceed "
                   "the 126 MB L2 at one GPU"}
 
@@ -230,23 +230,25 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()
-    from stminer_b200.sharding import fit_genes_sharded, pack_fit_result, shard_genes_contiguous
+    from stminer_b200.sharding import (default_chunk_genes, fit_genes_sharded, pack_fit_result, ranges_to_index,
+                                       shard_gene_chunks)
     # ONE data set for all ranks (strong scaling); host copy in the 4 B / value wire format (uint16 spot, int16 value),
-    # page-locked.  Rank r owns the contiguous gene range [bounds[r], bounds[r + 1]).
+    # page-locked.  The genes are dealt over the ranks in chunks of 16 consecutive genes, longest-first.
     if world > 1:                       # rank 0 generates (or finds) the cached data set, the others then load it
         if rank == 0:
             workload(args.workload, seed=0, genes=args.genes)
         dist.barrier()
     sm = workload(args.workload, seed=0, genes=args.genes).compact().pin_memory()
     G = sm.n_genes
-    bounds = shard_genes_contiguous(sm.col_ptr, world)
-    g0, g1 = int(bounds[rank]), int(bounds[rank + 1])
-    shard = sm.slice_genes(g0, g1)
-    dsm = DeviceSpotMatrix(shard, device=dev)
+    parts = shard_gene_chunks(sm.col_ptr, world, default_chunk_genes(sm.n_genes, world))
+    owned = [ranges_to_index(p) for p in parts]
+    n_mine = len(owned[rank])
+    dsm = DeviceSpotMatrix.from_ranges(sm, parts[rank], device=dev)
+    shard = dsm.host
     order, buckets = dsm.plan(K_COMP, _lib.fit_flags(device_init=True, compact=dsm.compact))
     n_launch = int((buckets > 0).sum())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    n_max = int(np.diff(bounds).max())
+    n_max = max(len(ix) for ix in owned)
     C = 7 * K_COMP + 4
     gbuf = torch.empty((world * n_max, C), dtype=torch.float64, device=dev)      # packed results of all ranks
 
@@ -267,7 +269,7 @@ def run_ours(args, rank, world, local_rank):
         rank's slot of the gather buffer and replicate them with one in-place all-gather."""
         res = fit_spot_matrix(dsm, K_COMP, init=None, seed=1, out=res)
         if world > 1:
-            gbuf[rank * n_max:rank * n_max + (g1 - g0)] = pack_fit_result(res, K_COMP)
+            gbuf[rank * n_max:rank * n_max + n_mine] = pack_fit_result(res, K_COMP)
             dist.all_gather_into_tensor(gbuf, gbuf[rank * n_max:(rank + 1) * n_max])
         return res
 
@@ -521,7 +523,7 @@ def run_ours(args, rank, world, local_rank):
                   "sharding": "contiguous pair slices per rank written into the gather buffer + one in-place NCCL all-gather" if world > 1 else "single GPU",
                   "issue_slot_util": ncu_metric("dist_issue_active_pct"), "ncu_file": "profiles/r2_ncu_dist.txt"},
         "fit": {"mean_n_iter": float(n_iter[ok].mean()), "genes_ok": int(ok.sum()), "genes_dropped": int((~ok).sum()),
-                "genes_per_rank": np.diff(bounds).tolist(),
+                "genes_per_rank": [len(ix) for ix in owned],
                 "bucket_counts_cluster16_8_4_2_large_medium_small_rank0": buckets.tolist(), "wall_ms_per_step": 1e3 * t_wall / args.steps},
         "e2e_from_adata": from_adata,
         "emd": emd,

@@ -52,6 +52,33 @@ def shard_genes_contiguous(col_ptr: np.ndarray, world_size: int) -> np.ndarray:
     return np.maximum.accumulate(np.minimum(b, G))
 
 
+def shard_gene_chunks(col_ptr: np.ndarray, world_size: int, chunk_genes: int = 16) -> List[List[Tuple[int, int]]]:
+    """Strong-scaling partition of the genes: runs of ``chunk_genes`` consecutive genes are dealt longest-first (by stored
+    values) onto the least-loaded rank.  Chunks keep the host slices contiguous views (each is one DMA from the page-locked
+    matrix, no host gather), the deal balances the stored values to within one chunk, and consecutive chunks land on
+    different ranks — neighbouring genes (replicates of one pattern, genes of one family) tend to need similar numbers of
+    EM iterations, which a cut into a few long contiguous ranges would pile onto one rank.  Returns, per rank, its
+    (g0, g1) ranges in increasing order; deterministic, so every rank computes the same partition."""
+    col_ptr = np.asarray(col_ptr, dtype=np.int64)
+    G = len(col_ptr) - 1
+    starts = np.arange(0, G, max(1, int(chunk_genes)), dtype=np.int64)
+    ends = np.minimum(starts + max(1, int(chunk_genes)), G)
+    nnz = col_ptr[ends] - col_ptr[starts]
+    import heapq
+    order = np.argsort(-nnz, kind="stable")
+    heap = [(0, 0, r) for r in range(world_size)]          # (stored values, chunks, rank): least loaded first
+    owner = np.empty(len(starts), dtype=np.int64)
+    for c in order.tolist():
+        load, count, r = heapq.heappop(heap)
+        owner[c] = r
+        heapq.heappush(heap, (load + int(nnz[c]), count + 1, r))
+    return [[(int(starts[c]), int(ends[c])) for c in np.flatnonzero(owner == r)] for r in range(world_size)]
+
+
+def ranges_to_index(ranges: List[Tuple[int, int]]) -> np.ndarray:
+    return (np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in ranges]) if ranges else np.zeros(0, dtype=np.int64))
+
+
 def allgather_rows(local, owned_idx: List[np.ndarray], group=None):
     """All-gather per-gene rows.  ``local`` is a tensor [n_local, ...] holding the rows of
     ``owned_idx[rank]``; returns the full tensor [G, ...] in original gene order on every rank."""
@@ -133,11 +160,14 @@ def pack_fit_result(res, K: int):
     """One [n, 7K + 4] float64 tensor holding every output array of a fit (device ``FitResult`` or host dict): the
     gather of a stage is ONE collective instead of seven.  The int32 fields are exact in float64."""
     import torch
+    K = int(K)
+    width = dict(weights=K, means=2 * K, covariances=4 * K, n_iter=1, converged=1, lower_bound=1, status=1)
     if isinstance(res, dict):
-        cols = [torch.from_numpy(np.ascontiguousarray(res[k])).to(torch.float64).reshape(len(res["status"]), -1) for k in FIT_FIELDS]
+        n = len(res["status"])
+        cols = [torch.from_numpy(np.ascontiguousarray(res[k])).to(torch.float64).reshape(n, width[k]) for k in FIT_FIELDS]
     else:
         n = res.status.shape[0]
-        cols = [getattr(res, k).to(torch.float64).reshape(n, -1) for k in FIT_FIELDS]
+        cols = [getattr(res, k).to(torch.float64).reshape(n, width[k]) for k in FIT_FIELDS]
     return torch.cat(cols, dim=1)
 
 
@@ -150,39 +180,113 @@ def unpack_fit_rows(rows: np.ndarray, K: int) -> dict:
                 lower_bound=np.ascontiguousarray(rows[:, 7 * K + 2]), status=rows[:, 7 * K + 3].astype(np.int32))
 
 
-def gather_fit_rows(packed, bounds: np.ndarray, group=None):
-    """All-gather of the ranks' packed rows (rank r holds genes [bounds[r], bounds[r + 1])) — one in-place collective on
-    a buffer with a fixed stride per rank; returns the host array [G, C] in gene order."""
+_PINNED = {}
+
+
+def _pinned_like(t):
+    """A cached page-locked host tensor of the shape / dtype of the CUDA tensor ``t`` (the read-back target of a stage)."""
+    import torch
+    key = (tuple(t.shape), t.dtype)
+    if key not in _PINNED:
+        _PINNED.clear()                      # one live shape at a time is enough for the stage drivers
+        _PINNED[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    return _PINNED[key]
+
+
+def gather_fit_rows(packed, owned_idx: List[np.ndarray], group=None):
+    """All-gather of the ranks' packed rows (rank r holds the genes ``owned_idx[r]``, in that order) — one in-place
+    collective on a buffer with a fixed stride per rank, one read-back; returns the host array [G, C] in gene order."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    lens = np.diff(bounds)
-    n_max = int(lens.max())
+    lens = [len(ix) for ix in owned_idx]
+    n_max = max(lens)
+    G = int(sum(lens))
     buf = torch.empty((world * n_max, packed.shape[1]), dtype=packed.dtype, device=packed.device)
     buf[rank * n_max:rank * n_max + packed.shape[0]] = packed
     dist.all_gather_into_tensor(buf, buf[rank * n_max:(rank + 1) * n_max], group=group)
-    h = buf.cpu().numpy()
-    return np.concatenate([h[r * n_max:r * n_max + int(lens[r])] for r in range(world)], axis=0)
+    if buf.is_cuda:
+        # gene order restored on the device (one indexed copy), then ONE read-back into page-locked memory
+        src = np.concatenate([r * n_max + np.arange(lens[r], dtype=np.int64) for r in range(world)])
+        dst = np.concatenate(owned_idx)
+        perm = np.empty(G, dtype=np.int64)
+        perm[dst] = src
+        ordered = buf.index_select(0, torch.from_numpy(perm).to(buf.device, non_blocking=True))
+        h = _pinned_like(ordered)
+        h.copy_(ordered, non_blocking=True)
+        torch.cuda.current_stream(buf.device).synchronize()
+        return h.numpy().copy()
+    h = buf.numpy()
+    out = np.empty((G, packed.shape[1]), dtype=h.dtype)
+    for r in range(world):
+        out[owned_idx[r]] = h[r * n_max:r * n_max + lens[r]]
+    return out
 
 
-def fit_genes_sharded(sm, n_comp: int, init=None, group=None, compute=None, **kw) -> dict:
-    """GMM fit of every gene of the SpotMatrix ``sm`` with the genes cut into one contiguous, nnz-balanced range per
-    rank: each rank uploads and fits only its own columns (a view of the host matrix, no gather), the
-    fitted arrays are packed into one device buffer and replicated by ONE all-gather, and read back once.
+def default_chunk_genes(n_genes: int, world_size: int) -> int:
+    """Chunk length of ``shard_gene_chunks`` for a sharded fit: 16 genes, longer when that would give a rank more than
+    ~64 chunks (every chunk is a pair of host-to-device copies)."""
+    return max(16, -(-int(n_genes) // (64 * max(1, world_size))))
+
+
+def fit_genes_sharded(sm, n_comp: int, init=None, group=None, compute=None, chunk_genes: int = 0, **kw) -> dict:
+    """GMM fit of every gene of the SpotMatrix ``sm`` with the genes dealt over the ranks in chunks of consecutive
+    genes (``shard_gene_chunks``): each rank uploads only its own columns — every chunk one DMA from the
+    host matrix into its place in the rank's device matrix, no host gather, in three groups so that the fit of a group
+    runs while the next one is still arriving — fits them, packs the fitted arrays into one device buffer, ONE
+    all-gather replicates them and one read-back returns them.
     Returns the same host dict as ``fit_spot_matrix_host``, in ``sm`` gene order, on every rank."""
     rank, world = group_rank_world(group)
-    if compute is None:
-        from .Algorithm.distribution import fit_spot_matrix_host as compute
-        kw = dict(kw, return_device=True) if world > 1 else kw
     if world == 1:
+        if compute is None:
+            from .Algorithm.distribution import fit_spot_matrix_host as compute
         return compute(sm, n_comp, init=init, **kw)
-    bounds = shard_genes_contiguous(sm.col_ptr, world)
-    g0, g1 = int(bounds[rank]), int(bounds[rank + 1])
-    sub_init = None if init is None else tuple(np.asarray(a)[g0:g1] for a in init)
-    local = compute(sm.slice_genes(g0, g1), n_comp, init=sub_init, **kw)
-    packed = pack_fit_result(local, n_comp).to(_collective_device(group))
-    return unpack_fit_rows(gather_fit_rows(packed, bounds, group=group), int(n_comp))
+    parts = shard_gene_chunks(sm.col_ptr, world, chunk_genes or default_chunk_genes(sm.n_genes, world))
+    owned = [ranges_to_index(p) for p in parts]
+    mine = owned[rank]
+    sub_init = None if init is None else tuple(np.asarray(a)[mine] for a in init)
+    if compute is not None:
+        local = compute(sm.select(mine), n_comp, init=sub_init, **kw)
+        packed = pack_fit_result(local, n_comp).to(_collective_device(group))
+    else:
+        import torch
+        from .Algorithm.distribution import _copy_stream, fit_spot_matrix
+        from .staging import DeviceSpotMatrix
+        dev = torch.device(kw.pop("device", None) or "cuda")
+        kw.pop("n_chunks", None)
+        smc = sm.compact()
+        ranges = parts[rank]
+        # groups of ranges holding ~15 / 35 / 50 % of the rank's stored values: the first fit starts early
+        sizes = np.array([smc.col_ptr[b] - smc.col_ptr[a] for a, b in ranges], dtype=np.float64)
+        cum = np.cumsum(sizes) / max(1.0, sizes.sum())
+        cuts = sorted(set([0] + [int(np.searchsorted(cum, f, side="left")) + 1 for f in (0.15, 0.5)] + [len(ranges)]))
+        cuts = [min(c, len(ranges)) for c in cuts]
+        with torch.cuda.device(dev):
+            compute_stream = torch.cuda.current_stream()
+            copy = _copy_stream(dev)
+            copy.wait_stream(compute_stream)
+            packs, keep, at = [], [], 0
+            for c0, c1 in zip(cuts[:-1], cuts[1:]):
+                if c1 <= c0:
+                    continue
+                grp = ranges[c0:c1]
+                n_grp = int(sum(b - a for a, b in grp))
+                with torch.cuda.stream(copy):
+                    dsm = DeviceSpotMatrix.from_ranges(smc, grp, device=dev)
+                    ready = torch.cuda.Event()
+                    ready.record(copy)
+                compute_stream.wait_event(ready)
+                g_init = None if sub_init is None else tuple(a[at:at + n_grp] for a in sub_init)
+                res = fit_spot_matrix(dsm, n_comp, init=g_init, **kw)
+                packs.append(pack_fit_result(res, n_comp))
+                keep.append((dsm, res))
+                at += n_grp
+            packed = torch.cat(packs, dim=0) if packs else torch.zeros((0, 7 * int(n_comp) + 4), dtype=torch.float64, device=dev)
+            out = unpack_fit_rows(gather_fit_rows(packed, owned, group=group), int(n_comp))
+            copy.wait_stream(compute_stream)
+        return out
+    return unpack_fit_rows(gather_fit_rows(packed, owned, group=group), int(n_comp))
 
 
 def gmm_pairs_sharded(W, MU, COV, group=None, device=None, compute=None):

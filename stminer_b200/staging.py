@@ -240,6 +240,42 @@ class DeviceSpotMatrix:
         self.h2d_bytes = sum(a.nbytes for a in (sm.col_ptr, sm.row_idx, sm.val))
         self.h2d_bytes += 0 if spots is not None else sm.spot_x.nbytes + sm.spot_y.nbytes
 
+    @classmethod
+    def from_ranges(cls, sm: "SpotMatrix", ranges, device=None) -> "DeviceSpotMatrix":
+        """The genes of the (g0, g1) ``ranges`` of ``sm``, in that order, as one device matrix: every range is copied
+        straight from the host arrays (async DMA when ``sm`` is page-locked) to its place in the device buffers — no
+        host-side gather.  What a rank of a sharded fit uploads."""
+        import torch
+        from . import _lib
+        _lib.require_cuda()
+        dev = torch.device(device if device is not None else "cuda")
+        lens = [np.diff(sm.col_ptr[a:b + 1]) for a, b in ranges]
+        col_ptr = np.concatenate([[0], np.cumsum(np.concatenate(lens) if lens else np.zeros(0, dtype=np.int64))]).astype(np.int64)
+        nnz = int(col_ptr[-1])
+        pins = getattr(sm, "_pins", None)
+        as_t = lambda a: torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
+        src_row = pins[1] if pins is not None else as_t(np.ascontiguousarray(sm.row_idx))
+        src_val = pins[2] if pins is not None else as_t(np.ascontiguousarray(sm.val))
+        with torch.cuda.device(dev):
+            row_idx = torch.empty(max(nnz, 1), dtype=src_row.dtype, device=dev)
+            val = torch.empty(max(nnz, 1), dtype=src_val.dtype, device=dev)
+            at = 0
+            for a, b in ranges:
+                e0, e1 = int(sm.col_ptr[a]), int(sm.col_ptr[b])
+                row_idx[at:at + e1 - e0].copy_(src_row[e0:e1], non_blocking=True)
+                val[at:at + e1 - e0].copy_(src_val[e0:e1], non_blocking=True)
+                at += e1 - e0
+        genes = [g for a, b in ranges for g in sm.genes[a:b]]
+        out = cls.__new__(cls)
+        out.host = _StagedHost(col_ptr, genes, sm.spot_x, sm.spot_y, sm.is_compact)
+        out.device, out.compact, out._plans = dev, sm.is_compact, {}
+        up = lambda a, k=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+        out.col_ptr, out.row_idx, out.val = up(col_ptr), row_idx, val
+        out.spot_x, out.spot_y = up(sm.spot_x), up(sm.spot_y)
+        out._up = up
+        out.h2d_bytes = int(col_ptr.nbytes + nnz * (src_row.element_size() + src_val.element_size()) + 2 * sm.spot_x.nbytes)
+        return out
+
     def plan(self, K: int, flags: int = 0):
         """(gene_order CUDA tensor, bucket_counts host int32[STM_FIT_N_BUCKETS]) from ``stm_gmm_fit_plan`` for K components."""
         from . import _lib

@@ -7,7 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from stminer_b200.sharding import allgather_pairs, allgather_rows, pair_slice, shard_genes_contiguous, shard_genes_lpt
+from stminer_b200.sharding import (allgather_pairs, allgather_rows, pair_slice, ranges_to_index, shard_gene_chunks,
+                                   shard_genes_contiguous, shard_genes_lpt)
 
 
 def test_shard_genes_lpt_balances_and_partitions():
@@ -31,6 +32,23 @@ def test_shard_genes_contiguous_balances_stored_values():
         loads = np.diff(col_ptr[b])
         assert loads.max() <= loads.mean() + nnz.max()
     assert shard_genes_contiguous(np.array([0, 3, 5]), 8)[-1] == 2            # more ranks than genes: empty ranges
+
+
+def test_shard_gene_chunks_partitions_and_balances():
+    rng = np.random.default_rng(2)
+    nnz = np.repeat((rng.pareto(1.5, 100) * 1000 + 100).astype(np.int64), 50)        # runs of 50 equal genes ("replicates")
+    col_ptr = np.concatenate([[0], np.cumsum(nnz)])
+    for world in (1, 2, 4, 8):
+        parts = shard_gene_chunks(col_ptr, world, chunk_genes=16)
+        idx = [ranges_to_index(p) for p in parts]
+        assert np.array_equal(np.sort(np.concatenate(idx)), np.arange(5000))
+        loads = np.array([nnz[i].sum() for i in idx])
+        assert loads.max() <= loads.mean() + 16 * nnz.max()
+        if world == 8:        # a run of 50 replicates is spread over several ranks, not piled onto one
+            owner = np.empty(5000, dtype=int)
+            for r, i in enumerate(idx):
+                owner[i] = r
+            assert np.mean([len(set(owner[k:k + 50])) for k in range(0, 5000, 50)]) >= 3
 
 
 def test_pair_slice_covers_triangle():
