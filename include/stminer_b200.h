@@ -224,6 +224,21 @@ int stm_stage_csr_columns(const int64_t* indptr, const int32_t* indices, const f
                           int64_t* out_col_ptr, void* out_row_idx, void* out_val, void* stream);
 
 /*
+ * Pattern vote: the accumulation loop of _genes_to_pattern (STMiner/SPFinder.py:459-489, called per label from
+ * get_pattern_array :441-457) for all labels in one pass over the spot-by-gene CSR matrix.
+ *
+ *   col_label[n_var]  label (0 .. n_labels-1, at most 64) of every input column, -1 = gene not in any label
+ *   gene_sum[n_var]   int64 scratch: per-gene totals of the int16-truncated counts (zeroed and filled here)
+ *   out_total[n_labels][n_obs] float64:  sum over the label's genes of  w_gs * 100 / sum_s w_gs   (scale_array, :32-38)
+ *   out_votes[n_labels][n_obs] int32:    number of the label's genes with w_gs != 0 at the spot
+ * The caller scatters the rows onto the (x, y) grid and applies the vote_rate mask.  Deterministic (no floating-point
+ * atomics).
+ */
+int stm_pattern_vote(const int64_t* indptr, const int32_t* indices, const float* data, int32_t n_obs, int32_t n_var,
+                     const int32_t* col_label, int32_t n_labels, int64_t* gene_sum,
+                     double* out_total, int32_t* out_votes, void* stream);
+
+/*
  * Metric MDS by SMACOF on a precomputed dissimilarity matrix, float64, whole iteration loop on the device.
  *
  * Replaces: the MDS half of cluster()   STMiner/Algorithm/algorithm.py:54-55

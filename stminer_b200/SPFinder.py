@@ -189,10 +189,18 @@ class SPFinder:
         else:
             self._highly_variable_genes = list(a.var.index)
         if normalize:                                                 # sc.pp.normalize_total(target_sum=None)
-            if exclude_highly_expressed:
-                raise NotImplementedError("exclude_highly_expressed needs scanpy (not in this image)")
             X = a.X.tocsr().astype(np.float64) if sparse.issparse(a.X) else np.asarray(a.X, dtype=np.float64)
             counts = np.asarray(X.sum(axis=1)).ravel()
+            if exclude_highly_expressed:
+                # scanpy 1.10 normalize_total(exclude_highly_expressed=True, max_fraction=0.05): a gene that holds more
+                # than 5 % of the counts of at least one cell does not enter the size factors
+                if sparse.issparse(X):
+                    big = X.data > np.repeat(counts, np.diff(X.indptr)) * 0.05
+                    hits = np.bincount(X.indices[big], minlength=X.shape[1])
+                else:
+                    hits = (X > counts[:, None] * 0.05).sum(axis=0)
+                keep = np.asarray(hits).ravel() == 0
+                counts = np.asarray(X[:, keep].sum(axis=1)).ravel()
             target = np.median(counts[counts > 0])
             scale = np.where(counts > 0, target / np.where(counts > 0, counts, 1.0), 1.0)
             a.X = sparse.diags(scale) @ X if sparse.issparse(X) else X * scale[:, None]
@@ -344,18 +352,57 @@ class SPFinder:
 
     # ------------------------------------------------------------------ pattern voting
     def get_pattern_array(self, vote_rate: float = 0.0, mode: str = "vote") -> None:
-        """SPFinder.py:441-457."""
+        """SPFinder.py:441-457.  All labels are accumulated in one device pass over the CSR matrix when it qualifies
+        (``_patterns_on_device``); otherwise label by label on the host."""
         self.patterns_binary_matrix_dict = {}
         if mode == "vote":
-            for label in set(self.genes_labels["labels"]):
-                gene_list = list(self.genes_labels[self.genes_labels["labels"] == label]["gene_id"])
-                binary_arr, total_count = self._genes_to_pattern(gene_list, vote_rate)
+            labels = list(set(self.genes_labels["labels"]))
+            lists = {label: list(self.genes_labels[self.genes_labels["labels"] == label]["gene_id"]) for label in labels}
+            done = self._patterns_on_device(lists, vote_rate)
+            for label in labels:
+                binary_arr, total_count = done[label] if done is not None else self._genes_to_pattern(lists[label], vote_rate)
                 self.patterns_matrix_dict[label] = total_count
                 self.patterns_binary_matrix_dict[label] = binary_arr
         elif mode == "test":
             pass                                     # unimplemented in the reference as well (SPFinder.py:452-455)
         else:
             raise ValueError("mode should be vote or test")
+
+    def _patterns_on_device(self, gene_lists: Dict, vote_rate: float):
+        """{label: (binary_arr, total_count)} of ``_genes_to_pattern`` for every label of ``gene_lists`` in ONE pass of
+        the vote kernel over the spot-by-gene CSR matrix (``stm_pattern_vote``); ``None`` when the matrix does not qualify
+        (not canonical CSR float32 / small integers, observations sharing a spot, a gene in two lists, > 64 labels, no
+        CUDA device) — the caller then runs the host loop."""
+        from .adata_lite import column_indices
+        from .staging import device_staging_supported, pattern_vote_on_device
+        try:
+            import torch
+            if not torch.cuda.is_available():
+                return None
+        except ImportError:      # pragma: no cover
+            return None
+        labels = list(gene_lists)
+        x = np.asarray(self.adata.obs["x"]); y = np.asarray(self.adata.obs["y"])
+        if not labels or len(labels) > 64 or not device_staging_supported(self.adata.X, x, y, None):
+            return None
+        n_var = self.adata.X.shape[1]
+        col_label = np.full(n_var, -1, dtype=np.int32)
+        for li, label in enumerate(labels):
+            cols = column_indices(self.adata, gene_lists[label])
+            if len(set(cols.tolist())) != len(cols) or (col_label[cols] >= 0).any():
+                return None
+            col_label[cols] = li
+        total, votes = pattern_vote_on_device(self.adata.X, n_var, col_label, len(labels), device=self.device)
+        shape = (int(x.max()) + 1, int(y.max()) + 1)
+        xi, yi = x.astype(np.int64), y.astype(np.int64)
+        out = {}
+        for li, label in enumerate(labels):
+            total_count = np.zeros(shape, dtype=np.float64); vote_cnt = np.zeros(shape, dtype=np.float64)
+            total_count[xi, yi] = total[li]; vote_cnt[xi, yi] = votes[li]
+            vote_array = (vote_cnt > 0) & (vote_cnt / len(gene_lists[label]) >= vote_rate)
+            total_count *= vote_array
+            out[label] = (np.where(total_count != 0, 1, total_count), total_count)
+        return out
 
     def _genes_to_pattern(self, gene_list: List[str], vote_rate: float):
         """SPFinder.py:459-489 on the CSC staging: per gene the int16 grid scaled to sum 100, accumulated;
@@ -382,7 +429,8 @@ class SPFinder:
                            mode: str = "vote") -> None:
         """SPFinder.py:491-524: mixture of the voted pattern image, fitted on the device."""
         if mode == "vote":
-            _, total_count = self._genes_to_pattern(gene_list, vote_rate)
+            done = self._patterns_on_device({"custom": list(gene_list)}, vote_rate)
+            _, total_count = done["custom"] if done is not None else self._genes_to_pattern(gene_list, vote_rate)
             # SPFinder.py:516-517: GaussianMixture(n_components).fit -> sklearn's default max_iter = 100
             self.custom_pattern = _fit_image(np.round(total_count).astype(np.int32), n_components, self.seed, self.device,
                                              max_iter=100)

@@ -177,3 +177,86 @@ extern "C" int stm_stage_csr_columns(const int64_t* indptr, const int32_t* indic
   else rc = use_smem ? run(stage_rows_kernel<true, false, true>) : run(stage_rows_kernel<true, false, false>);
   return rc;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pattern vote: the accumulation loop of SPFinder._genes_to_pattern (STMiner/SPFinder.py:459-489) for ALL labels at once.
+// For every gene g of label l (its int16-truncated counts w_gs, AlgUtils.py:35):  total_l[s] += w_gs * 100 / sum_s w_gs  and
+// votes_l[s] += 1 for every spot with w_gs != 0.  Spot-major (CSR) input: one warp per spot, lane k takes the row's entries
+// k, k + 32, ... in order and keeps a private accumulator per label; a fixed shuffle tree then combines the lanes — the
+// floating-point result is the same on every run (no atomics on the sums).  The per-gene totals are exact integer atomics.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace stm {
+namespace {
+
+constexpr int PAT_THREADS = 128;      // 4 warps = 4 spots per CTA
+constexpr int PAT_MAX_LABELS = 64;
+
+__global__ void __launch_bounds__(256) pattern_gene_sums_kernel(const int64_t* indptr, const int32_t* indices, const float* data,
+                                                                int n_obs, const int32_t* col_label, unsigned long long* gene_sum) {
+  const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n_obs) return;
+  for (int64_t e = indptr[row] + lane; e < indptr[row + 1]; e += 32) {
+    const int c = indices[e];
+    if (col_label[c] < 0) continue;
+    const int w = trunc_wrap_i16(data[e]);
+    if (w != 0) atomicAdd(&gene_sum[c], (unsigned long long)(long long)w);      // two's complement: exact for negative counts too
+  }
+}
+
+__global__ void __launch_bounds__(PAT_THREADS) pattern_vote_kernel(const int64_t* indptr, const int32_t* indices, const float* data,
+                                                                   int n_obs, const int32_t* col_label, int n_labels,
+                                                                   const long long* gene_sum, double* out_total, int32_t* out_votes) {
+  extern __shared__ double s_acc[];                       // [warps][n_labels][32] sums, then votes as int
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (PAT_THREADS / 32) + warp;
+  double* acc = s_acc + (size_t)warp * n_labels * 32;
+  int* vot = reinterpret_cast<int*>(s_acc + (size_t)(PAT_THREADS / 32) * n_labels * 32) + (size_t)warp * n_labels * 32;
+  for (int l = 0; l < n_labels; ++l) { acc[l * 32 + lane] = 0.0; vot[l * 32 + lane] = 0; }
+  __syncwarp();
+  if (row < n_obs) {
+    for (int64_t e = indptr[row] + lane; e < indptr[row + 1]; e += 32) {
+      const int c = indices[e];
+      const int l = col_label[c];
+      if (l < 0) continue;
+      const int w = trunc_wrap_i16(data[e]);
+      if (w == 0) continue;
+      const long long gs = gene_sum[c];
+      if (gs != 0) acc[l * 32 + lane] += (double)w * (100.0 / (double)gs);      // scale_array: exp * (100 / sum), 0 if sum == 0
+      vot[l * 32 + lane] += 1;
+    }
+  }
+  __syncwarp();
+  if (row < n_obs) {
+    for (int l = 0; l < n_labels; ++l) {
+      double v = acc[l * 32 + lane];
+      int k = vot[l * 32 + lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(FULL_MASK, v, o); k += __shfl_xor_sync(FULL_MASK, k, o); }
+      if (lane == 0) { out_total[(size_t)l * n_obs + row] = v; out_votes[(size_t)l * n_obs + row] = k; }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace stm
+
+extern "C" int stm_pattern_vote(const int64_t* indptr, const int32_t* indices, const float* data, int32_t n_obs, int32_t n_var,
+                                const int32_t* col_label, int32_t n_labels, int64_t* gene_sum,
+                                double* out_total, int32_t* out_votes, void* stream) {
+  using namespace stm;
+  STM_CHECK_ARG(n_obs >= 0 && n_var >= 0 && n_labels >= 0, "negative size");
+  STM_CHECK_ARG(n_labels <= PAT_MAX_LABELS, "at most 64 labels per call");
+  if (n_obs == 0 || n_labels == 0) return STM_OK;
+  STM_CHECK_ARG(indptr && indices && data && col_label && gene_sum && out_total && out_votes, "null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  STM_CHECK_CUDA(cudaMemsetAsync(gene_sum, 0, sizeof(int64_t) * (size_t)n_var, st));
+  pattern_gene_sums_kernel<<<(n_obs + 7) / 8, 256, 0, st>>>(indptr, indices, data, n_obs, col_label,
+                                                            reinterpret_cast<unsigned long long*>(gene_sum));
+  STM_CHECK_CUDA(cudaGetLastError());
+  const size_t smem = (size_t)(PAT_THREADS / 32) * n_labels * 32 * (sizeof(double) + sizeof(int));
+  STM_CHECK_CUDA(cudaFuncSetAttribute(pattern_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pattern_vote_kernel<<<(n_obs + PAT_THREADS / 32 - 1) / (PAT_THREADS / 32), PAT_THREADS, smem, st>>>(
+      indptr, indices, data, n_obs, col_label, n_labels, reinterpret_cast<const long long*>(gene_sum), out_total, out_votes);
+  STM_CHECK_CUDA(cudaGetLastError());
+  return STM_OK;
+}

@@ -454,3 +454,28 @@ def stage_csr_on_device(X, x, y, genes, columns=None, device=None) -> DeviceSpot
     dsm.h2d_bytes = int(X.indptr.nbytes + X.nnz * 8 + col_map.nbytes + row_order.nbytes + 2 * spot_x.nbytes)
     dsm._keepalive = (d_indptr, d_indices, d_data, d_map, d_order, ws)
     return dsm
+
+
+def pattern_vote_on_device(X, n_var: int, col_label: np.ndarray, n_labels: int, device=None):
+    """``stm_pattern_vote`` on a canonical CSR matrix: (total[n_labels, n_obs] float64, votes[n_labels, n_obs] int32) — the
+    accumulation of ``_genes_to_pattern`` (SPFinder.py:459-489) for every label in one pass (csrc/staging.cu)."""
+    import torch
+    from . import _lib
+    _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else "cuda")
+    if not X.has_canonical_format:
+        X = X.copy()
+        X.sum_duplicates()
+    n_obs = X.shape[0]
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+    with torch.cuda.device(dev):
+        d_indptr, d_indices = up(X.indptr.astype(np.int64, copy=False)), up(X.indices.astype(np.int32, copy=False))
+        d_data, d_label = up(X.data.astype(np.float32, copy=False)), up(np.asarray(col_label, dtype=np.int32))
+        gsum = torch.empty(max(n_var, 1), dtype=torch.int64, device=dev)
+        total = torch.empty((n_labels, n_obs), dtype=torch.float64, device=dev)
+        votes = torch.empty((n_labels, n_obs), dtype=torch.int32, device=dev)
+        st = lib.stm_pattern_vote(_lib.ptr(d_indptr), _lib.ptr(d_indices), _lib.ptr(d_data), n_obs, n_var, _lib.ptr(d_label),
+                                  int(n_labels), _lib.ptr(gsum), _lib.ptr(total), _lib.ptr(votes), _lib.current_stream_ptr())
+        _lib.check(st, "stm_pattern_vote")
+        return total.cpu().numpy(), votes.cpu().numpy()

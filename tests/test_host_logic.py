@@ -100,6 +100,23 @@ def test_preprocess_filters_and_normalises_in_place():
     assert sp._highly_variable_genes == list(sp.adata.var_names)
 
 
+def test_normalize_total_exclude_highly_expressed():
+    """scanpy 1.10 ``normalize_total(exclude_highly_expressed=True)`` (SPFinder.py:417-420): genes holding more than 5 % of
+    some cell's counts stay out of the size factors; dense restatement of scanpy's rule as the check."""
+    from stminer_b200.Simulate import simulate_adata
+    a = simulate_adata("T", seed=4)
+    X0 = a.X.toarray().astype(float)
+    sp = SPFinder(a)
+    sp.preprocess(normalize=True, exclude_highly_expressed=True, log1p=False, min_cells=1, min_genes=1, n_top_genes=-1)
+    cpc = X0.sum(1)
+    sub = (X0 > cpc[:, None] * 0.05).sum(0) == 0
+    assert 0 < sub.sum() < X0.shape[1]
+    c2 = X0[:, sub].sum(1)
+    c2 = c2 / np.median(c2[c2 > 0])
+    c2[c2 == 0] = 1
+    np.testing.assert_allclose(sp.adata.X.toarray(), X0 / c2[:, None], rtol=1e-12, atol=1e-12)
+
+
 def test_get_genes_csr_array_percentile_clip():
     """SPFinder.py:220-249: values clipped at the vmax percentile over ALL spots (only if that percentile > 0)."""
     adata, X, xy = _adata(seed=4)

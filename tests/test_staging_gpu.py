@@ -80,3 +80,30 @@ def test_unsupported_inputs_take_the_host_path(cuda_device):
     assert not device_staging_supported(a.X.astype(np.float64), x, y, None)       # values that float32 may not hold
     assert not device_staging_supported(a.X, x, y, [1, 2, 1])                     # a gene asked for twice
     assert not device_staging_supported(a.X, np.zeros_like(x), y * 0, None)       # observations sharing a spot
+
+
+def test_pattern_vote_on_device_matches_host_loop(cuda_device):
+    """get_pattern_array (SPFinder.py:441-489): all labels in one pass of the vote kernel == the host restatement of the
+    reference's per-label loop (tests/test_host_logic.py pins that one against a dense re-computation); the AnnData rows
+    are shuffled and carry floats that truncate to 0, negatives and int16 wraps."""
+    import pandas as pd
+    from stminer_b200 import SPFinder
+    a = _random_adata(23, 31, 60, 0.25, seed=5, big_values=True)
+    sp = SPFinder(a)
+    genes = list(a.var_names)
+    rng = np.random.default_rng(0)
+    lab = rng.integers(0, 4, len(genes))
+    sp.genes_labels = pd.DataFrame({"gene_id": genes, "labels": lab})
+    for vote_rate in (0.0, 0.3):
+        sp.patterns_matrix_dict, sp.patterns_binary_matrix_dict = {}, {}
+        sp.get_pattern_array(vote_rate=vote_rate)
+        assert set(sp.patterns_matrix_dict) == set(lab.tolist())
+        for label in set(lab.tolist()):
+            gl = [g for g, l in zip(genes, lab) if l == label]
+            binary, total = sp._genes_to_pattern(gl, vote_rate)
+            np.testing.assert_allclose(sp.patterns_matrix_dict[label], total, rtol=1e-12, atol=1e-12)
+            np.testing.assert_array_equal(sp.patterns_binary_matrix_dict[label], binary)
+    done = sp._patterns_on_device({"a": genes[:10], "b": genes[5:15]}, 0.0)
+    assert done is None                                     # a gene in two lists: host path
+    sp.get_custom_pattern(genes[:20], n_components=4, vote_rate=0.1)
+    assert sp.custom_pattern.means_.shape == (4, 2)
