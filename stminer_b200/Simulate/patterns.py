@@ -164,6 +164,50 @@ def simulate_long_genes(n_genes: int, seed: int = 0, shape: Tuple[int, int] = (1
                       ["long_%d" % i for i in range(len(targets))])
 
 
+def simulate_long_genes_device(n_genes: int, seed: int = 0, shape: Tuple[int, int] = (1000, 1000), nnz_lo: float = 1e3,
+                               nnz_hi: float = 5e5, device=None):
+    """``simulate_long_genes`` generated ON the device with torch (the full BASELINE configs[3] gene count — thousands of
+    genes of up to 5e5 spots — takes minutes in numpy): same model (blob-mixture intensity, support = the ``nnz_g`` cells
+    with the largest ``intensity x Exp(1)``, counts 1 + Poisson(intensity)), torch's generator instead of numpy's.
+    Returns a ``DeviceSpotMatrix`` (8 B / value: a million spots do not fit the compact encoding)."""
+    import torch
+    from ..staging import DeviceSpotMatrix, _StagedHost
+    dev = torch.device(device if device is not None else "cuda")
+    R, C = shape
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    rng = np.random.default_rng(seed)
+    targets = np.minimum(np.exp(rng.uniform(np.log(nnz_lo), np.log(nnz_hi), size=n_genes)).astype(np.int64), R * C)
+    rr = torch.arange(R, dtype=torch.float32, device=dev)[:, None]
+    cc = torch.arange(C, dtype=torch.float32, device=dev)[None, :]
+    col_ptr = np.concatenate([[0], np.cumsum(targets)]).astype(np.int64)
+    row_idx = torch.empty(int(col_ptr[-1]), dtype=torch.int32, device=dev)
+    val = torch.empty(int(col_ptr[-1]), dtype=torch.float32, device=dev)
+    for g, n in enumerate(targets.tolist()):
+        lam = torch.full((R, C), 0.05, dtype=torch.float32, device=dev)
+        for _b in range(int(rng.integers(2, 6))):
+            cx, cy = rng.uniform(0.1, 0.9) * R, rng.uniform(0.1, 0.9) * C
+            sx, sy = rng.uniform(0.05, 0.25) * R, rng.uniform(0.05, 0.25) * C
+            rho = rng.uniform(-0.7, 0.7)
+            dx, dy = (rr - cx) / sx, (cc - cy) / sy
+            lam += float(rng.uniform(1.0, 4.0)) * torch.exp(-0.5 * (dx * dx - 2 * rho * dx * dy + dy * dy) / (1 - rho * rho))
+        score = (lam * torch.empty((R, C), dtype=torch.float32, device=dev).exponential_(generator=gen)).ravel()
+        idx = torch.sort(torch.topk(score, n, sorted=False).indices).values
+        a, b = int(col_ptr[g]), int(col_ptr[g + 1])
+        row_idx[a:b] = idx.to(torch.int32)
+        val[a:b] = 1.0 + torch.poisson(lam.ravel()[idx], generator=gen)
+    sx_all = (np.arange(R * C) // C).astype(np.int32); sy_all = (np.arange(R * C) % C).astype(np.int32)
+    dsm = DeviceSpotMatrix.__new__(DeviceSpotMatrix)
+    dsm.host = _StagedHost(col_ptr, ["long_%d" % i for i in range(n_genes)], sx_all, sy_all, False)
+    dsm.device, dsm.compact, dsm._plans = dev, False, {}
+    up = lambda a, k=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+    dsm.col_ptr, dsm.row_idx, dsm.val = up(col_ptr), row_idx, val
+    dsm.spot_x, dsm.spot_y = up(sx_all), up(sy_all)
+    dsm._up = up
+    dsm.h2d_bytes = 0
+    return dsm
+
+
 def simulate_adata(config: str = "T", seed: int = 0, **kw):
     """Same data as an AnnData-like object (float values, not truncated) for the SPFinder façade."""
     from ..adata_lite import AnnDataLite
