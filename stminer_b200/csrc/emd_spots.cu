@@ -146,6 +146,17 @@ struct EmdArgs {
   double* out_cost; int32_t* out_status; int64_t* out_iters;
 };
 
+// -DSTM_EMD_CHECK: bounds checks on every index the refinement / tree build computes (compute-sanitizer is not available on
+// the pool): a violation prints its site and traps.
+#ifdef STM_EMD_CHECK
+#define EMD_CHECK(cond, what)                                                                              \
+  do {                                                                                                     \
+    if (!(cond)) { printf("[emd check] %s failed at line %d (block %d thread %d)\n", what, __LINE__, blockIdx.x, threadIdx.x); __trap(); } \
+  } while (0)
+#else
+#define EMD_CHECK(cond, what)
+#endif
+
 __device__ __forceinline__ long long shfl_xor_ll(long long v, int o) {
   return __shfl_xor_sync(FULL_MASK, v, o);
 }
@@ -561,7 +572,11 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       for (int v = tid; v <= n; v += EMD_THREADS) soff16[v] = (idx_t)deg32[v];
       for (int j = tid; j <= m; j += EMD_THREADS) tf16[j] = (idx_t)sc.tfirst[j];
       __syncthreads();
-      for (int e = tid; e < Ef; e += EMD_THREADS) sadj16[atomicAdd(&deg32[sc.fI[e]], 1)] = (idx_t)sc.fJ[e];
+      for (int e = tid; e < Ef; e += EMD_THREADS) {
+        const int at = atomicAdd(&deg32[sc.fI[e]], 1);
+        EMD_CHECK(at >= 0 && at < Ef && sc.fI[e] < n && sc.fJ[e] < m, "source adjacency slot");
+        sadj16[at] = (idx_t)sc.fJ[e];
+      }
       for (int v = tid; v < N; v += EMD_THREADS) s_parent[v] = UNVIS16;
       __syncthreads();
       for (int v = tid; v < n; v += EMD_THREADS) {      // lists in increasing target order (deterministic layout)
@@ -587,6 +602,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           stk[sp++] = (idx_t)s0;
           while (sp > 0) {
             const int v = stk[--sp];
+            EMD_CHECK(cnt < N && v < N, "preorder position");
             s_order[cnt] = (idx_t)v; s_pos[v] = (idx_t)cnt; ++cnt;
             const int pv = s_parent[v];
             const int xy = s_xy[v], xv = (xy << 16) >> 16, yv = xy >> 16;
@@ -1195,7 +1211,11 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       for (int k = tid; k <= nS; k += EMD_THREADS) sc.curS[k] = sc.offS[k];
       for (int k = tid; k <= nT; k += EMD_THREADS) sc.curT[k] = sc.offT[k];
       __syncthreads();
-      for (int e = tid; e < Ec; e += EMD_THREADS) sc.lstS[atomicAdd(&sc.curS[sc.aI[e]], 1)] = e;
+      for (int e = tid; e < Ec; e += EMD_THREADS) {
+        const int at = atomicAdd(&sc.curS[sc.aI[e]], 1);
+        EMD_CHECK(at >= 0 && at < Ec && sc.aI[e] < nS && sc.aJ[e] < nT, "coarse arc list slot");
+        sc.lstS[at] = e;
+      }
       __syncthreads();
       for (int I = tid; I < nS; I += EMD_THREADS) {      // arcs of I by increasing target
         const int a = sc.offS[I], b = sc.offS[I + 1];
@@ -1219,7 +1239,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
             int np = pass == 0 ? 0 : sc.pcFirst[r];
             while (rb > 0 && a < a_end) {
               const long long f = ra < rb ? ra : rb;
-              if (f > 0) { if (pass == 1) { sc.pI[np] = a; sc.pF[np] = f; } ++np; }
+              if (f > 0) { if (pass == 1) { EMD_CHECK(np < 2 * cap, "piece index"); sc.pI[np] = a; sc.pF[np] = f; } ++np; }
               ra -= f; rb -= f;
               if (ra == 0) { ++a; ra = a < a_end ? fs[a] : 0; }
             }
@@ -1257,7 +1277,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
               long long ra = sc.pF[pz];
               while (ra > 0 && b < b_end) {
                 const long long f = ra < rb ? ra : rb;
-                if (f > 0) { if (pass == 1) { sc.fI[E] = sc.pI[pz]; sc.fJ[E] = b; sc.fF[E] = f; } ++E; }
+                if (f > 0) { if (pass == 1) { EMD_CHECK(E < cap, "fine arc index"); sc.fI[E] = sc.pI[pz]; sc.fJ[E] = b; sc.fF[E] = f; } ++E; }
                 ra -= f; rb -= f;
                 if (rb == 0) { ++b; rb = b < b_end ? ft[b] : 0; if (pass == 1 && b < b_end) sc.tfirst[b] = E; }
               }
@@ -1269,7 +1289,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
         __syncthreads();
         if (pass == 0) cta_prefix_inplace<EMD_THREADS>(sc.aoff, nT + 1, s_ws);
       }
-      if (tid == 0) { const int Eall = sc.aoff[nT]; sc.tfirst[mf] = Eall; s_i[8] = Eall; }
+      if (tid == 0) { const int Eall = sc.aoff[nT]; EMD_CHECK(Eall <= cap && Eall < s_lv[lev - 1] + p.src_hdr[lev - 1], "forest size"); sc.tfirst[mf] = Eall; s_i[8] = Eall; }
       __syncthreads();
     }
 #ifdef STM_EMD_PROFILE
