@@ -72,6 +72,11 @@ constexpr int KM_LMAX = 6;                // greedy k-means++ candidates: 2 + fl
 #ifndef STM_EM_PREFETCH
 #define STM_EM_PREFETCH 0     // load the next step's spots before computing the current one (manual software pipelining)
 #endif
+#ifndef STM_EM_PAR_SMEM
+#define STM_EM_PAR_SMEM 0     // 1 = the E-step coefficients of a lane's components are re-read from shared memory (one LDS.64 per
+                              // pair and coefficient, shared by the spots in flight) instead of living in 30 registers — room for
+                              // a third spot in flight (STM_EM_S_LARGE=3)
+#endif
 #ifndef STM_EM_NOMAX
 #define STM_EM_NOMAX 0        // 1 = E-step without the per-spot max over the components: the log-density offsets are shifted by their
                               // maximum over the components once per iteration (an upper bound of every log density), so ex2 cannot
@@ -382,7 +387,8 @@ __device__ __forceinline__ void em_sweep(const Src& src, int i_begin, int i_end,
 template <int KT, int GS, int S, int T, typename Src>
 __device__ __forceinline__ void em_sweep_packed(const Src& src, int i_begin, int i_end, int grp, int sub,
                                                 const f2 (&pp)[(KT / 2) > 0 ? (KT / 2) : 1][6], const float (&ps)[6],
-                                                f2 (&ap)[(KT / 2) > 0 ? (KT / 2) : 1][6], float (&as)[6], double& ll) {
+                                                f2 (&ap)[(KT / 2) > 0 ? (KT / 2) : 1][6], float (&as)[6], double& ll,
+                                                [[maybe_unused]] unsigned pp_saddr = 0, [[maybe_unused]] unsigned ps_saddr = 0) {
   constexpr int NG = T / GS;
   constexpr int NP = KT / 2, R = KT % 2;
   constexpr int NPA = NP > 0 ? NP : 1;
@@ -489,6 +495,60 @@ __device__ __forceinline__ void em_sweep_packed(const Src& src, int i_begin, int
         sum[s] = sm2; m[s] = mx;
       }
       if (!(w[s] > 0.f)) sum[s] = 1.f;       // padding lanes (weight 0): keep rcp finite
+    }
+#elif STM_EM_PAR_SMEM
+    // coefficients from shared memory, pair-major: six LDS.64 per pair serve all spots in flight
+#pragma unroll
+    for (int s = 0; s < S; ++s) m[s] = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      f2 c[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(c[k].x), "=f"(c[k].y) : "r"(pp_saddr + 8u * (unsigned)(q * 6 + k)));
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const f2 xx = f2_make(x[s], x[s]), yy = f2_make(y[s], y[s]);
+        t0p[s][q] = f2_fma(xx, c[0], c[1]);
+        t1p[s][q] = f2_fma(xx, c[2], f2_fma(yy, c[3], c[4]));
+        lpp[s][q] = f2_sub(c[5], f2_fma(t0p[s][q], t0p[s][q], f2_mul(t1p[s][q], t1p[s][q])));
+        m[s] = fmaxf(m[s], fmaxf(lpp[s][q].x, lpp[s][q].y));
+      }
+    }
+    if constexpr (R == 1) {
+      float c[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c[k]) : "r"(ps_saddr + 4u * (unsigned)k));
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        t0s[s] = fmaf(x[s], c[0], c[1]);
+        t1s[s] = fmaf(x[s], c[2], fmaf(y[s], c[3], c[4]));
+        lps[s] = fmaf(-t0s[s], t0s[s], fmaf(-t1s[s], t1s[s], c[5]));
+        m[s] = fmaxf(m[s], lps[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int o = 1; o < GS; o <<= 1) m[s] = fmaxf(m[s], __shfl_xor_sync(FULL_MASK, m[s], o));
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const f2 mm = f2_make(m[s], m[s]);
+      f2 sp = f2_make(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        const f2 d = f2_sub(lpp[s][q], mm);
+        lpp[s][q] = f2_make(ex2_approx(d.x), ex2_approx(d.y));
+        sp = f2_add(sp, lpp[s][q]);
+      }
+      sum[s] = sp.x + sp.y;
+      if constexpr (R == 1) { lps[s] = ex2_approx(lps[s] - m[s]); sum[s] += lps[s]; }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int o = 1; o < GS; o <<= 1) sum[s] += __shfl_xor_sync(FULL_MASK, sum[s], o);
     }
 #else
 #pragma unroll
@@ -709,6 +769,17 @@ __device__ __noinline__ double em_chunk(const Src src, int c0, int c1, double* s
   constexpr int NP = KT / 2, NPA = NP > 0 ? NP : 1;
   f2 pp[NPA][6];
   float ps[6];
+#if STM_EM_PAR_SMEM
+#pragma unroll
+  for (int q = 0; q < NPA; ++q) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) pp[q][c] = f2_make(0.f, 0.f);      // unused: the sweep reads the coefficients from shared memory
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) ps[c] = 0.f;
+  const unsigned pp_saddr = (unsigned)__cvta_generic_to_shared(reinterpret_cast<const float2*>(s_f + L::F_PP) + (sub * NP) * 6);
+  const unsigned ps_saddr = (unsigned)__cvta_generic_to_shared(s_par + 8 * (sub * KT + KT - 1));
+#else
 #pragma unroll
   for (int q = 0; q < NP; ++q) {
     const float2* qa = reinterpret_cast<const float2*>(s_f + L::F_PP) + (sub * NP + q) * 6;
@@ -717,6 +788,8 @@ __device__ __noinline__ double em_chunk(const Src src, int c0, int c1, double* s
   }
 #pragma unroll
   for (int c = 0; c < 6; ++c) ps[c] = s_par[8 * (sub * KT + KT - 1) + c];
+  const unsigned pp_saddr = 0, ps_saddr = 0;
+#endif
   f2 ap[NPA][6];
   float as[6];
 #pragma unroll
@@ -726,7 +799,7 @@ __device__ __noinline__ double em_chunk(const Src src, int c0, int c1, double* s
   }
 #pragma unroll
   for (int c = 0; c < 6; ++c) as[c] = 0.f;
-  em_sweep_packed<KT, GS, S, T>(src, c0, c1, grp, sub, pp, ps, ap, as, ll);
+  em_sweep_packed<KT, GS, S, T>(src, c0, c1, grp, sub, pp, ps, ap, as, ll, pp_saddr, ps_saddr);
 #pragma unroll
   for (int q = 0; q < NP; ++q) {
 #pragma unroll
