@@ -200,6 +200,26 @@ int stm_emd_spots_batched_wide(const int32_t* src_x, const int32_t* src_y, const
                                double* out_cost, int32_t* out_status, int64_t* out_iters, void* stream);
 
 /*
+ * Lloyd iterations of KMeans on the device, all restarts at once (one CTA per restart), float64.
+ *
+ * Replaces: the KMeans half of cluster()   STMiner/Algorithm/algorithm.py:57
+ *           (sklearn.cluster.KMeans(n_clusters, random_state=0, max_iter=1000, n_init=20).fit -> _kmeans_single_lloyd,
+ *            scikit-learn cluster/_kmeans.py; the k-means++ start centres of every restart come from the caller, who draws
+ *            them exactly as KMeans.fit does)
+ *
+ *   X[n,d] row-major, mean-centred as KMeans.fit centres it; centers_init[n_runs,k,d]; k, d <= 64
+ *   tol = 1e-4 * mean(var(X, axis=0)) (KMeans' _tolerance); stop on unchanged labels or squared centre shift <= tol
+ *   out_centers[n_runs,k,d], out_labels[n_runs,n] int32, out_inertia[n_runs], out_n_iter[n_runs],
+ *   out_status[n_runs]: 0 ok, 1 a cluster became empty (scikit-learn relocates it; not restated here)
+ *   workspace: stm_kmeans_workspace_bytes(n, n_runs) bytes
+ */
+int64_t stm_kmeans_workspace_bytes(int32_t n, int32_t n_runs);
+int stm_kmeans_lloyd(const double* X, int32_t n, int32_t d, int32_t k, const double* centers_init, int32_t n_runs,
+                     int32_t max_iter, double tol, void* workspace, int64_t workspace_bytes,
+                     double* out_centers, int32_t* out_labels, double* out_inertia, int32_t* out_n_iter,
+                     int32_t* out_status, void* stream);
+
+/*
  * Device-side staging: spot-by-gene CSR matrix -> the gene-major (CSC) arrays stm_gmm_fit_batched reads.
  *
  * Replaces the per-gene host staging of the reference's fit path: get_exp_array / _preprocess

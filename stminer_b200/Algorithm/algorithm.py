@@ -102,13 +102,89 @@ def mds_fit_transform(dissimilarities, n_components: int = 2, n_init: int = 4, m
     return best[0].cpu().numpy(), best[1], best[2]
 
 
+class KMeansResult:
+    """What ``cluster`` hands back as its fit result: the attributes of a fitted ``sklearn.cluster.KMeans`` that callers
+    of the reference read (``labels_``, ``cluster_centers_``, ``inertia_``, ``n_iter_``)."""
+
+    def __init__(self, labels, centers, inertia, n_iter, n_clusters):
+        self.labels_, self.cluster_centers_, self.inertia_, self.n_iter_ = labels, centers, inertia, n_iter
+        self.n_clusters = n_clusters
+
+    def predict(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        d2 = ((X[:, None, :] - self.cluster_centers_[None]) ** 2).sum(axis=2)
+        return np.argmin(d2, axis=1).astype(np.int32)
+
+
+def kmeans_fit(X, n_clusters: int, n_init: int = 20, max_iter: int = 1000, tol: float = 1e-4, random_state=0, device=None):
+    """``KMeans(n_clusters, random_state, max_iter, n_init).fit(X)`` (algorithm.py:57) with the Lloyd iterations of all
+    restarts on the device (``stm_kmeans_lloyd``).  The start centres are drawn exactly as ``KMeans.fit`` draws them —
+    scikit-learn's own k-means++ on the mean-centred data, one shared RandomState consumed restart after restart — and the
+    best restart is chosen by KMeans' rule (lower inertia and not the same clustering), so the labels are those of
+    scikit-learn (tests compare them).  A restart in which a cluster becomes empty (scikit-learn relocates it to the
+    farthest point) is not restated: the whole fit is then handed to scikit-learn."""
+    from sklearn.cluster import KMeans, kmeans_plusplus
+    from sklearn.utils import check_random_state
+    from sklearn.utils.extmath import row_norms
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    n, d = X.shape
+    if n_clusters > 64 or d > 64 or n < n_clusters:
+        return KMeans(n_clusters=n_clusters, random_state=random_state, max_iter=max_iter, n_init=n_init, tol=tol).fit(X)
+    rs = check_random_state(random_state)
+    tol_abs = float(np.mean(np.var(X, axis=0)) * tol)
+    mean = X.mean(axis=0)
+    Xc = X - mean
+    xsn = row_norms(Xc, squared=True)
+    inits = np.stack([kmeans_plusplus(Xc, n_clusters, x_squared_norms=xsn, random_state=rs)[0] for _ in range(n_init)])
+    dev = torch.device(device if device is not None else "cuda")
+    with torch.cuda.device(dev):
+        dX = torch.from_numpy(Xc).to(dev)
+        dI = torch.from_numpy(np.ascontiguousarray(inits, dtype=np.float64)).to(dev)
+        ws_bytes = int(lib.stm_kmeans_workspace_bytes(n, n_init))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        oc = torch.empty((n_init, n_clusters, d), dtype=torch.float64, device=dev)
+        ol = torch.empty((n_init, n), dtype=torch.int32, device=dev)
+        oi = torch.empty(n_init, dtype=torch.float64, device=dev)
+        on = torch.empty(n_init, dtype=torch.int32, device=dev)
+        os_ = torch.empty(n_init, dtype=torch.int32, device=dev)
+        st = lib.stm_kmeans_lloyd(_lib.ptr(dX), n, d, int(n_clusters), _lib.ptr(dI), int(n_init), int(max_iter), tol_abs,
+                                  _lib.ptr(ws), ws_bytes, _lib.ptr(oc), _lib.ptr(ol), _lib.ptr(oi), _lib.ptr(on), _lib.ptr(os_),
+                                  _lib.current_stream_ptr())
+        _lib.check(st, "stm_kmeans_lloyd")
+        centers, labels, inertia = oc.cpu().numpy(), ol.cpu().numpy(), oi.cpu().numpy()
+        n_iter, status = on.cpu().numpy(), os_.cpu().numpy()
+    if (status != 0).any():
+        import logging
+        logging.getLogger(__name__).warning("a KMeans restart emptied a cluster; fitting with scikit-learn on the host")
+        return KMeans(n_clusters=n_clusters, random_state=random_state, max_iter=max_iter, n_init=n_init, tol=tol).fit(X)
+    best = None
+    for r in range(n_init):                 # KMeans.fit: lower inertia AND a different clustering replaces the best
+        if best is None or (inertia[r] < inertia[best] and not _same_clustering(labels[r], labels[best], n_clusters)):
+            best = r
+    return KMeansResult(labels[best].astype(np.int32), centers[best] + mean, float(inertia[best]), int(n_iter[best]), n_clusters)
+
+
+def _same_clustering(a, b, n_clusters) -> bool:
+    """sklearn's ``_is_same_clustering``: equal up to a permutation of the labels."""
+    mapping = np.full(n_clusters, -1, dtype=np.int64)
+    for x, y in zip(a.tolist(), b.tolist()):
+        if mapping[x] == -1:
+            mapping[x] = y
+        elif mapping[x] != y:
+            return False
+    return True
+
+
 def cluster(distance_array: pd.DataFrame, mds_components: int = 20, n_clusters: int = 10, method: str = "kmeans",
             device=None):
     """Drop-in for ``cluster`` (algorithm.py:29-61): MDS on the precomputed distances, then KMeans
     (``random_state=0, max_iter=1000, n_init=20``) or spectral clustering; returns
     ``(DataFrame[gene_id, labels], fit_result, embedding)``.  The MDS (SMACOF, O(G^2 d) per iteration) runs on the
     device with the semantics of the scikit-learn version the reference pins; it is unseeded in the reference too
-    (``np.random.seed`` fixes it).  KMeans on the G x d embedding stays scikit-learn on the host."""
+    (``np.random.seed`` fixes it).  KMeans: scikit-learn's k-means++ starts on the host, the Lloyd iterations of the 20
+    restarts on the device (``kmeans_fit``)."""
     from sklearn.cluster import KMeans, SpectralClustering
     if method not in ("kmeans", "spectral"):
         raise ValueError("method should be kmeans or spectral")
@@ -116,7 +192,7 @@ def cluster(distance_array: pd.DataFrame, mds_components: int = 20, n_clusters: 
     embedding_position, _, _ = mds_fit_transform(np.asarray(distance_array, dtype=np.float64), mds_components,
                                                  device=device)
     if method == "kmeans":
-        fit_result = KMeans(n_clusters=n_clusters, random_state=0, max_iter=1000, n_init=20).fit(embedding_position)
+        fit_result = kmeans_fit(embedding_position, n_clusters, n_init=20, max_iter=1000, random_state=0, device=device)
     else:
         fit_result = SpectralClustering(n_clusters=n_clusters, random_state=0, affinity="rbf").fit(embedding_position)
     result = pd.DataFrame(dict(gene_id=list(index), labels=list(fit_result.labels_)))

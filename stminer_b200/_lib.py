@@ -67,6 +67,9 @@ SIGNATURES = {
     "stm_stage_csr_columns": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_uint32, _P, C.c_int64, C.c_int64,
                                         _P, _P, _P, _P]),
     "stm_pattern_vote": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, _P]),
+    "stm_kmeans_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "stm_kmeans_lloyd": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, C.c_double, _P, C.c_int64,
+                                   _P, _P, _P, _P, _P, _P]),
     "stm_mds_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "stm_mds_smacof": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_double, C.c_int32, _P, C.c_int64,
                                  _P, _P, _P, _P]),

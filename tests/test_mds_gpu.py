@@ -73,3 +73,20 @@ def test_cluster_labels_match_reference_path(cuda_device):
     assert list(res["gene_id"]) == names
     with pytest.raises(ValueError):
         cluster(df, method="nope")
+
+
+@pytest.mark.parametrize("n,d,k,seed", [(500, 20, 6, 0), (2000, 20, 10, 1), (300, 10, 3, 2), (1200, 5, 8, 3), (64, 20, 2, 4)])
+def test_device_kmeans_matches_sklearn(cuda_device, n, d, k, seed):
+    """cluster()'s KMeans(n_clusters, random_state=0, max_iter=1000, n_init=20) (algorithm.py:57): same labels, centres and
+    inertia as scikit-learn from the same k-means++ draws — blobs with overlap, like an MDS embedding of gene distances."""
+    from sklearn.cluster import KMeans
+    from stminer_b200.Algorithm.algorithm import kmeans_fit
+    rng = np.random.default_rng(seed)
+    centres = rng.normal(0, 1.0, (k + 2, d))
+    X = centres[rng.integers(0, k + 2, n)] + rng.normal(0, 0.6, (n, d))
+    ref = KMeans(n_clusters=k, random_state=0, max_iter=1000, n_init=20).fit(X.copy())
+    got = kmeans_fit(X, k, n_init=20, max_iter=1000, random_state=0)
+    np.testing.assert_array_equal(got.labels_, ref.labels_)
+    np.testing.assert_allclose(got.cluster_centers_, ref.cluster_centers_, rtol=1e-10, atol=1e-12)
+    assert abs(got.inertia_ - ref.inertia_) <= 1e-10 * ref.inertia_
+    assert got.n_iter_ == ref.n_iter_
