@@ -239,3 +239,19 @@ def test_emd_visium_size_matches_independent_lp_golden(cuda_device):
             # from the artificial star (the start of POT, which the reference calls with numItermax=200000) the 16k-node
             # problem is still sub-optimal after 200,000 pivots: status 1 and a larger cost, as POT would return
             assert status_s[0] == 1 and cost_s[0] > cost[0]
+
+
+def test_emd_multiscale_edge_cases(cuda_device):
+    """Supports the reference's CSR images never produce but the API accepts: duplicate coordinates, targets outside the
+    source's bounding box, masses whose integer image is 0, single spots, a single row of cells, coordinates beyond the
+    range of the Morton keys (star fallback) — optimum of the independent LP, pivots of the oracle."""
+    from stminer_b200.Algorithm.distance import emd_batched
+    from tests.test_oracle_emd import _edge_problems
+    for name, (src, tgt) in _edge_problems().items():
+        cost, status, iters = emd_batched(src, [tgt], block_size=300, return_iters=True)
+        c, st, it, lev = eo.emd_multiscale(*src, *tgt, block_size=300)
+        assert status[0] == st == 0, (name, status)
+        assert iters[0] == it, (name, iters[0], it, lev[:6])
+        assert abs(cost[0] - c) <= 1e-12 * max(1.0, c), (name, cost[0], c)
+        ref = eo.emd_linprog(*src, *tgt)
+        assert abs(cost[0] - ref) <= 1e-8 * max(1.0, ref), (name, cost[0], ref)

@@ -85,3 +85,36 @@ def test_oracle_matches_visium_size_lp_golden():
         ref = float(z[p + "cost"])
         assert status == 0
         assert abs(cost - ref) <= 1e-7 * ref, (c, cost, ref)
+
+
+def _edge_problems():
+    rng = np.random.default_rng(11)
+    out = {}
+    # duplicate coordinates on both sides (a general support, not a CSR image): cells of the hierarchy with > 4 children
+    s = rng.integers(0, 36, 90); t = rng.integers(0, 36, 70)
+    out["duplicates"] = ((s // 6, s % 6, rng.random(90) + 0.05), (t // 6, t % 6, rng.random(70) + 0.05))
+    # targets outside the source's bounding box, left / below its corner (negative coordinates relative to it)
+    s = rng.permutation(100)[:60]; t = rng.permutation(100)[:40]
+    out["outside"] = ((s // 10 + 20, s % 10 + 30, rng.random(60) + 0.1), (t // 10, t % 10 + 25, rng.random(40) + 0.1))
+    # masses so small that their integer image is 0 (a node without any arc in the refined forest)
+    s = rng.permutation(144)[:80]; t = rng.permutation(144)[:50]
+    sm = rng.random(80) + 0.1; tm = rng.random(50) + 0.1
+    sm[3] = 1e-22; tm[7] = 1e-22; tm[8] = 1e-25
+    out["tiny_mass"] = ((s // 12, s % 12, sm), (t // 12, t % 12, tm))
+    # one source spot, one target spot, and a single row of cells
+    out["one_to_many"] = ((np.array([4]), np.array([5]), np.array([2.0])), (t // 12, t % 12, tm.copy()))
+    out["line"] = ((np.arange(70), np.zeros(70, dtype=int), rng.random(70) + 0.1), (np.arange(0, 70, 2), np.zeros(35, dtype=int), rng.random(35) + 0.1))
+    # a target too far left of the source's corner for the Morton keys (< -16384): the solver starts from the star
+    out["far"] = ((s // 12, s % 12, sm.copy()), (t // 12 - 20000, t % 12, tm.copy()))
+    return out
+
+
+@pytest.mark.parametrize("name", list(_edge_problems()))
+def test_multiscale_edge_cases_match_lp(name):
+    src, tgt = _edge_problems()[name]
+    cost, status, pivots, lev = eo.emd_multiscale(*src, *tgt)
+    assert status == 0
+    ref = eo.emd_linprog(*src, *tgt)
+    assert abs(cost - ref) <= 1e-8 * max(1.0, ref), (name, cost, ref)
+    star = eo.emd_network_simplex(*src, *tgt)[0]
+    assert abs(cost - star) <= 1e-11 * max(1.0, star)
