@@ -194,7 +194,7 @@ def run_reference(args, rank, world):
         per_step, args.workload, cores)
     line = {"impl": "reference", "metric": "genes_per_sec_gmm_fit", "value": value, "unit": "genes/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, sm, 1),
             "cpu_baseline": {"value": value, "unit": "genes/s", "cores": cores, "kind": "port", "sample": sample},
