@@ -181,3 +181,38 @@ def test_failed_emd_genes_are_skipped_not_nan(cuda_device, monkeypatch):
     gd = sp.global_distance
     assert keys[1] not in set(gd["Gene"]) and keys[2] not in set(gd["Gene"]) and len(gd) == len(keys) - 2
     assert np.isfinite(gd["Distance"]).all() and np.isfinite(gd["z-score"]).all()
+
+
+def test_svg_ranking_at_stereoseq_bin50_scale(cuda_device):
+    """spatial_high_variable_genes on Stereo-seq bin50-shaped data (200 x 200 bins; the per-spot total image has 35,000+
+    spots, far beyond one CTA's shared memory): every gene gets a finite exact distance from the global-memory-tree
+    kernel — in round 1 all of them came back as status 3 / NaN — and one of them is checked against the CPU oracle."""
+    from scipy import sparse
+    from scipy.sparse import csr_matrix
+    from stminer_b200 import SPFinder
+    from stminer_b200.adata_lite import AnnDataLite
+    from stminer_b200.Simulate import simulate_spot_matrix
+    sm = simulate_spot_matrix("S50", seed=0, n_templates=3, replicas=2, truncate_int16=False)
+    Xc = sparse.csc_matrix((sm.val, sm.row_idx, sm.col_ptr), shape=(sm.n_spots, sm.n_genes))
+    rng = np.random.default_rng(0)
+    keep = rng.random(Xc.nnz) < 0.08                 # sparse genes, as most real genes are ...
+    keep[Xc.indptr[0]:Xc.indptr[2]] = True           # ... and two dense ones, so that the total image covers the slide
+    Xc.data = Xc.data * keep
+    Xc.eliminate_zeros()
+    adata = AnnDataLite(Xc.tocsr(), obs=pd.DataFrame({"x": sm.spot_x.astype(int), "y": sm.spot_y.astype(int)}),
+                        var=pd.DataFrame(index=sm.genes), obsm={})
+    sp = SPFinder(adata)
+    genes = list(sm.genes[2:])
+    sp.get_genes_csr_array(min_cells=50, normalize=False, gene_list=genes)
+    sp.spatial_high_variable_genes()
+    gd = sp.global_distance
+    assert set(gd["Gene"]) == set(genes)
+    assert np.isfinite(gd["Distance"]).all() and (gd["Distance"] > 0).all() and np.isfinite(gd["z-score"]).all()
+    data = np.array(sp.adata.X.sum(axis=1)).flatten()
+    glob = csr_matrix((data, (sp.adata.obs["x"].values, sp.adata.obs["y"].values)))
+    src = eo.csr_to_problem(glob)
+    assert len(src[0]) > 30000
+    g = genes[-1]
+    cost, status, _, _ = eo.emd_multiscale(*src, *eo.csr_to_problem(sp.csr_dict[g]))
+    got = float(gd.set_index("Gene").loc[g, "Distance"])
+    assert status == 0 and abs(got - cost) <= 1e-9 * cost, (got, cost)
