@@ -41,7 +41,10 @@ constexpr int EMD_MAXPATH_S = 2048;     // longest cycle path kept, shared-memor
 constexpr int EMD_MAXPATH_G = 8192;     // global-memory tree
 constexpr int EMD_SCAN_CH_G = 8;        // global tree: up to 30 * 8 * threads nodes
 constexpr int EMD_ROWS_G = 64;          // most target rows of a pricing block of the global-tree kernel
-constexpr int EMD_ROWS_MIN_G = 4;       // and the fewest (when the target has that many)
+#ifndef STM_EMD_ROWS_MIN_G
+#define STM_EMD_ROWS_MIN_G 4
+#endif
+constexpr int EMD_ROWS_MIN_G = STM_EMD_ROWS_MIN_G;       // and the fewest (when the target has that many)
 constexpr int EMD_RG_G = 8;             // sources per thread and tile in its pricing
 constexpr int EMD_GLOBAL_THREADS = 512;
 constexpr int64_t EMD_GLOBAL_ALLOC_NODES = 9000;
