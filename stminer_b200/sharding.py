@@ -172,12 +172,13 @@ def pack_fit_result(res, K: int):
 
 
 def unpack_fit_rows(rows: np.ndarray, K: int) -> dict:
-    """Inverse of ``pack_fit_result`` on a host array [G, 7K + 4]."""
+    """Inverse of ``pack_fit_result`` on a host array [G, 7K + 4]; every field is a fresh array (``rows`` may be a
+    buffer that the next call reuses)."""
     G = rows.shape[0]
-    return dict(weights=np.ascontiguousarray(rows[:, :K]), means=np.ascontiguousarray(rows[:, K:3 * K]).reshape(G, K, 2),
-                covariances=np.ascontiguousarray(rows[:, 3 * K:7 * K]).reshape(G, K, 2, 2),
+    return dict(weights=rows[:, :K].copy(), means=rows[:, K:3 * K].copy().reshape(G, K, 2),
+                covariances=rows[:, 3 * K:7 * K].copy().reshape(G, K, 2, 2),
                 n_iter=rows[:, 7 * K].astype(np.int32), converged=rows[:, 7 * K + 1].astype(np.int32),
-                lower_bound=np.ascontiguousarray(rows[:, 7 * K + 2]), status=rows[:, 7 * K + 3].astype(np.int32))
+                lower_bound=rows[:, 7 * K + 2].copy(), status=rows[:, 7 * K + 3].astype(np.int32))
 
 
 _PINNED = {}
@@ -216,7 +217,7 @@ def gather_fit_rows(packed, owned_idx: List[np.ndarray], group=None):
         h = _pinned_like(ordered)
         h.copy_(ordered, non_blocking=True)
         torch.cuda.current_stream(buf.device).synchronize()
-        return h.numpy().copy()
+        return h.numpy()        # a view of the cached page-locked buffer: unpack_fit_rows copies every field out of it
     h = buf.numpy()
     out = np.empty((G, packed.shape[1]), dtype=h.dtype)
     for r in range(world):
