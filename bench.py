@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--pairs-genes", type=int, default=4000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="genes in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--emd-genes", type=int, default=1184, help="Visium-size spot-EMD problems in the emd leg (0 = skip)")
+    ap.add_argument("--emd-genes", type=int, default=2000, help="Visium-size spot-EMD problems in the emd leg (0 = skip)")
     ap.add_argument("--s10-genes", type=int, default=2072, help="long (Stereo-seq bin10-shaped) genes in the s10 leg (0 = skip)")
     ap.add_argument("--no-mds", action="store_true", help="skip the MDS (cluster_gene) leg")
     ap.add_argument("--no-adata", action="store_true", help="skip the fit_gmms(adata) end-to-end leg")
