@@ -780,10 +780,13 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
             const int rr0 = gidx < groups ? gidx : rows;       // lanes beyond the last row group sit the block out
             int j = j0 + gidx;
             while (j >= m) j -= m;
+            int bjrow = 0;                                     // the target row of the thread's (first) minimum
             for (int rr = rr0; rr < rows; rr += groups) {
               const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
+              int rmin = INT_MAX;
 #pragma unroll
-              for (int r = 0; r < EMD_RMAX_T; ++r) brc = min(brc, sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj)));
+              for (int r = 0; r < EMD_RMAX_T; ++r) rmin = min(rmin, sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj)));
+              if (rmin < brc) { brc = rmin; bjrow = j; }
               j += groups;
               while (j >= m) j -= m;
             }
@@ -799,22 +802,16 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
             if (g_rc < 0) {
               // ---- level 2: its first position in block order (rows from the block start, sources ascending) ----
               unsigned myk = 0xffffffffu;
-              if (brc == g_rc) {
-                j = j0 + gidx;
-                while (j >= m) j -= m;
-                for (int rr = rr0; rr < rows && myk == 0xffffffffu; rr += groups) {
-                  const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
+              if (brc == g_rc) {      // this thread's first row holding its minimum: the arc is in that row (slots ascending)
+                j = bjrow;
+                const int txy = s_xy[n + j], nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16), bj = s_pi[n + j];
 #pragma unroll
-                  for (int r = 0; r < EMD_RMAX_T; ++r) {
-                    const int rc = sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj));
-                    if (rc == g_rc && myk == 0xffffffffu) {
-                      int k = j * n + i0 + r * teff - next_arc;
-                      if (k < 0) k += n_arcs;
-                      myk = (unsigned)k;
-                    }
+                for (int r = EMD_RMAX_T - 1; r >= 0; --r) {
+                  if (sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj)) == g_rc) {
+                    int k = j * n + i0 + r * teff - next_arc;
+                    if (k < 0) k += n_arcs;
+                    myk = (unsigned)k;            // the lowest slot is written last
                   }
-                  j += groups;
-                  while (j >= m) j -= m;
                 }
               }
               const unsigned w_k = __reduce_min_sync(FULL_MASK, myk);
