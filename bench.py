@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--s10-genes", type=int, default=2072, help="long (Stereo-seq bin10-shaped) genes in the s10 leg (0 = skip)")
     ap.add_argument("--no-mds", action="store_true", help="skip the MDS (cluster_gene) leg")
     ap.add_argument("--no-adata", action="store_true", help="skip the fit_gmms(adata) end-to-end leg")
+    ap.add_argument("--emd50-genes", type=int, default=8, help="Stereo-seq bin50-size spot-EMD problems (0 = skip)")
     return ap.parse_args()
 
 
@@ -414,6 +415,33 @@ def run_ours(args, rank, world, local_rank):
                               "staging alone (the host staging it replaces took 4.5 s)"}
         del dsm_a, adata, Xr
 
+    # ---- spot EMD at Stereo-seq bin50 size: the per-spot total image of the S50 set (40,000 bins) against sparse genes ----
+    emd50 = None
+    if rank == 0 and world == 1 and args.emd50_genes > 0:
+        from stminer_b200.Algorithm.distance import emd_batched as _emd
+        tot50 = np.zeros(sm.n_spots)
+        np.add.at(tot50, sm.row_idx.astype(np.int64), sm.val.astype(np.float64))
+        k50 = tot50 > 0
+        src50 = (sm.spot_x[k50], sm.spot_y[k50], tot50[k50])
+        rng50 = np.random.default_rng(0)
+        tg50 = []
+        for gi in range(args.emd50_genes):               # every 100th gene (one per pattern), thinned to ~2,000 bins
+            g_ = (gi * 100) % G
+            a_, b_ = int(sm.col_ptr[g_]), int(sm.col_ptr[g_ + 1])
+            pick = np.sort(rng50.permutation(b_ - a_)[:min(b_ - a_, 2000)]) + a_
+            r_ = sm.row_idx[pick].astype(np.int64)
+            tg50.append((sm.spot_x[r_], sm.spot_y[r_], sm.val[pick].astype(np.float64)))
+        torch.cuda.synchronize()
+        t_5 = time.perf_counter()
+        c50, s50_, i50 = _emd(src50, tg50, device=dev, return_iters=True)
+        torch.cuda.synchronize()
+        t_5 = time.perf_counter() - t_5
+        emd50 = {"metric": "spot_emd_bin50_seconds", "problems": len(tg50), "source_bins": int(k50.sum()),
+                 "mean_target_bins": float(np.mean([len(t[0]) for t in tg50])), "seconds": t_5,
+                 "optimal": int((s50_ == 0).sum()), "mean_pivots": float(i50.mean()),
+                 "note": "global-memory-tree kernel (beyond one CTA's shared memory), one CTA per problem, all in flight "
+                         "together; dense bin50 genes (26,000 bins) take 55 s each (profiles/r2_tuning_log.txt)"}
+
     # ---- the step after the distance matrix: cluster() = SMACOF MDS (4 restarts, 20 components) on the G x G matrix ----
     mds = None
     if rank == 0 and world == 1 and not args.no_mds and Gp >= 64:
@@ -516,6 +544,7 @@ def run_ours(args, rank, world, local_rank):
                 "bucket_counts_cluster16_8_4_2_large_medium_small_rank0": buckets.tolist(), "wall_ms_per_step": 1e3 * t_wall / args.steps},
         "e2e_from_adata": from_adata,
         "emd": emd,
+        "emd_bin50": emd50,
         "mds": mds,
         "s10": s10,
         "clocks": clocks,
