@@ -57,6 +57,9 @@ constexpr int EMD_BIAS = 16384;       // Morton keys take coordinates relative t
                              // threads) while every barrier-delimited serial phase is cheaper with 16 warps: 116 vs 111 problems/s
 #endif
 // sources per thread kept in registers by the whole-row pricing path: 5,120 sources per CTA for the big kernel
+#ifndef STM_EMD_BLOCK_ARCS
+#define STM_EMD_BLOCK_ARCS 32768   // arcs per pricing block of the one-CTA-per-SM kernel (whole target rows)
+#endif
 #ifndef STM_EMD_MINB_SMALL
 #define STM_EMD_MINB_SMALL 1   // CTAs per SM the 256-thread kernel is compiled for (register bound)
 #endif
@@ -700,7 +703,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     // fewer barriers per arc) win — 32 arcs per thread measured best on Visium-size problems
     // on the problem itself; coarse levels (few arcs in all) price a sixteenth of their arcs, at least 4,096
     int B = p.block_size > 0 ? p.block_size
-                             : max((int)sqrt((double)n_arcs), min(ONE_PER_SM ? 32768 : 32 * EMD_THREADS, max(4096, n_arcs / 16)));
+                             : max((int)sqrt((double)n_arcs), min(ONE_PER_SM ? STM_EMD_BLOCK_ARCS : 32 * EMD_THREADS, max(4096, n_arcs / 16)));
     if (!GLOBAL && p.block_size <= 0 && n <= EMD_RMAX_T * EMD_THREADS) B = max(1, (B + n / 2) / n) * n;   // whole target rows
     if (B < 10) B = 10;
     if (B > n_arcs) B = n_arcs;
