@@ -101,6 +101,35 @@ class GeneImageDict(Mapping):
         return out
 
 
+def _loess_quadratic(x: np.ndarray, y: np.ndarray, span: float = 0.3) -> np.ndarray:
+    """Local quadratic regression (tricube weights on the ``span`` fraction of nearest points), evaluated at every x —
+    the estimator of Cleveland's loess(degree=2, family="gaussian") without the kd-tree surface interpolation."""
+    n = len(x)
+    if n == 0:
+        return np.zeros(0)
+    q = int(min(n, max(3, np.ceil(span * n))))
+    order = np.argsort(x, kind="stable")
+    xs, ys = x[order], y[order]
+    fit = np.empty(n)
+    lo = 0
+    for i in range(n):                      # the q nearest neighbours of a sorted array form a sliding window
+        while lo + q < n and xs[lo + q] - xs[i] < xs[i] - xs[lo]:
+            lo += 1
+        xw, yw = xs[lo:lo + q], ys[lo:lo + q]
+        h = max(xs[i] - xw[0], xw[-1] - xs[i])
+        if h <= 0:
+            fit[i] = yw.mean()
+            continue
+        w = np.clip(1.0 - (np.abs(xw - xs[i]) / h) ** 3, 0.0, None) ** 3
+        dx = xw - xs[i]
+        A = np.stack([np.ones_like(dx), dx, dx * dx], axis=1) * np.sqrt(w)[:, None]
+        coef, *_ = np.linalg.lstsq(A, yw * np.sqrt(w), rcond=None)
+        fit[i] = coef[0]
+    out = np.empty(n)
+    out[order] = fit
+    return out
+
+
 def _n_nonzero(X, axis):
     if sparse.issparse(X):
         return np.asarray((X > 0).sum(axis=axis)).ravel()
@@ -211,18 +240,44 @@ class SPFinder:
                 a.X = np.log1p(a.X)
 
     def _seurat_v3_hvg(self, n_top_genes: int) -> List[str]:
-        """Variance-ranked stand-in for scanpy's ``seurat_v3`` flavour (its loess fit needs scikit-misc, absent
-        here; the ranking is consumed only when ``n_top_genes > 0``, SPFinder.py:386-387)."""
+        """Restatement of scanpy's ``highly_variable_genes(flavor="seurat_v3")`` (SPFinder.py:409-413; scanpy 1.10
+        ``_highly_variable_genes_seurat_v3``): log10(variance) regressed on log10(mean) by a local quadratic fit (span 0.3),
+        counts clipped at ``mean + sqrt(N) * regularised std``, genes ranked by the variance of the standardised counts.
+        scanpy takes the fit from scikit-misc's loess (Cleveland's Fortran code with a kd-tree-interpolated surface, not
+        in this image); here the local regression is evaluated exactly at every gene — the same estimator without the
+        interpolation error, so the ranking can differ in near-ties only.  Consumed only when ``n_top_genes > 0``."""
         X = self.adata.X
+        N = X.shape[0]
         if sparse.issparse(X):
-            mean = np.asarray(X.mean(axis=0)).ravel()
-            var = np.asarray(X.multiply(X).mean(axis=0)).ravel() - mean ** 2
+            Xc = X.tocsc().astype(np.float64)
+            mean = np.asarray(Xc.mean(axis=0)).ravel()
+            sq = np.asarray(Xc.multiply(Xc).sum(axis=0)).ravel()
         else:
-            mean, var = np.mean(X, axis=0), np.var(X, axis=0)
-        disp = var / np.maximum(mean, 1e-12)
-        order = np.argsort(-disp, kind="stable")[:n_top_genes]
+            Xc = np.asarray(X, dtype=np.float64)
+            mean = Xc.mean(axis=0)
+            sq = (Xc * Xc).sum(axis=0)
+        var = (sq - N * mean ** 2) / max(N - 1, 1)                     # ddof = 1, as scanpy's _get_mean_var
+        not_const = var > 0
+        est = np.zeros_like(var)
+        est[not_const] = _loess_quadratic(np.log10(mean[not_const]), np.log10(var[not_const]), span=0.3)
+        reg_std = np.sqrt(10.0 ** est)
+        clip = reg_std * np.sqrt(N) + mean
+        if sparse.issparse(Xc):                                        # sums of the clipped counts, column by column
+            d = Xc.data.copy()
+            col = np.repeat(np.arange(Xc.shape[1]), np.diff(Xc.indptr))
+            np.minimum(d, clip[col], out=d)
+            csum = np.bincount(col, weights=d, minlength=Xc.shape[1])
+            csq = np.bincount(col, weights=d * d, minlength=Xc.shape[1])
+        else:
+            d = np.minimum(Xc, clip[None, :])
+            csum, csq = d.sum(axis=0), (d * d).sum(axis=0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            norm_var = (1.0 / ((N - 1) * reg_std ** 2)) * (N * mean ** 2 + csq - 2.0 * csum * mean)
+        norm_var[~np.isfinite(norm_var)] = 0.0
+        order = np.argsort(-norm_var, kind="stable")[:n_top_genes]
         mask = np.zeros(self.adata.n_vars, dtype=bool); mask[order] = True
         self.adata.var["highly_variable"] = mask
+        self.adata.var["variances_norm"] = norm_var
         return list(self.adata.var.index[mask])
 
     # ------------------------------------------------------------------ spot-level EMD path

@@ -117,6 +117,35 @@ def test_normalize_total_exclude_highly_expressed():
     np.testing.assert_allclose(sp.adata.X.toarray(), X0 / c2[:, None], rtol=1e-12, atol=1e-12)
 
 
+def test_seurat_v3_hvg_restatement():
+    """highly_variable_genes(flavor="seurat_v3") (SPFinder.py:409-413) restated with an exactly evaluated local quadratic
+    fit: Poisson genes get a standardised variance of about 1, over-dispersed genes rank first, and the loess reproduces a
+    quadratic exactly."""
+    from scipy import sparse
+    from stminer_b200.adata_lite import AnnDataLite
+    from stminer_b200.SPFinder import _loess_quadratic
+    x = np.sort(np.random.default_rng(1).uniform(-2, 3, 300))
+    np.testing.assert_allclose(_loess_quadratic(x, 0.5 * x * x - x + 2.0), 0.5 * x * x - x + 2.0, rtol=1e-9, atol=1e-9)
+    rng = np.random.default_rng(0)
+    N, G = 1500, 400
+    mu = np.exp(rng.normal(0, 1.2, G))
+    X = rng.poisson(mu[None, :], (N, G)).astype(np.float32)
+    hv = rng.choice(G, 30, replace=False)
+    X[:, hv] = rng.negative_binomial(1.0, 1.0 / (1.0 + mu[hv][None, :]), (N, 30))
+    genes = ["g%d" % i for i in range(G)]
+    a = AnnDataLite(sparse.csr_matrix(X), obs=pd.DataFrame({"x": np.arange(N) // 50, "y": np.arange(N) % 50}),
+                    var=pd.DataFrame(index=genes), obsm={})
+    sp = SPFinder(a)
+    top = sp._seurat_v3_hvg(30)
+    assert len(set(top) & {genes[i] for i in hv}) >= 26
+    nv = sp.adata.var["variances_norm"].values
+    assert 0.85 < np.median(np.delete(nv, hv)) < 1.15
+    assert int(sp.adata.var["highly_variable"].sum()) == 30
+    # the dense path gives the same ranking
+    b = AnnDataLite(X.copy(), obs=a.obs.copy(), var=pd.DataFrame(index=genes), obsm={})
+    assert SPFinder(b)._seurat_v3_hvg(30) == top
+
+
 def test_get_genes_csr_array_percentile_clip():
     """SPFinder.py:220-249: values clipped at the vmax percentile over ALL spots (only if that percentile > 0)."""
     adata, X, xy = _adata(seed=4)
