@@ -170,9 +170,14 @@ static int net_from_forest(Net* g, const int32_t* ai, const int32_t* aj, const i
  * kept, like POT), 3 (internal failure).  *iters is incremented by the number of pivots.
  *
  * cand_threads = 0: plain block search (one pivot per pricing pass).
- * cand_threads = T > 0: candidate list, the way a CUDA kernel with T threads could price — arc offset k of a block
- * belongs to class (k mod T) / 32 (the warp that evaluates it); the pass keeps the best arc of every class, and
- * "minor" pivots then re-price only those T/32 candidates until none is negative (LEMON's candidate-list idea).
+ * cand_threads = T > 0: CANDIDATE LIST, the way the register-resident pricing path of the CUDA kernel with T threads
+ * works (emd_spots.cu; it applies when the block is a whole number of target rows, B % n == 0, and the level has at most
+ * R * T sources, R = 5 for T = 256 and ceil(5120 / T) otherwise — emd_rmax there).  The kernel's threads form
+ * groups = T / teff row groups of teff = roundup32(ceil(n / R)) threads; the arc (i, j) with j the r-th row of the block
+ * belongs to thread (class)  (r mod groups) * teff + (i mod teff).  A pricing pass (a "major" iteration) that finds a
+ * negative block keeps every class's first most-negative arc of that block; the following "minor" iterations re-price
+ * only these <= T candidates (those no longer negative are dropped), enter the most negative one (ties: lowest class)
+ * and fall back to the block search where the last pass stopped once none is negative (LEMON's candidate-list idea).
  */
 static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_threads, int64_t* iters) {
   const int n = g->n, m = g->m, N = g->N;
@@ -187,41 +192,47 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
   if (B > n_arcs) B = n_arcs;
   int64_t next_arc = 0, it = *iters;
   int status = 0;
-  const int n_cls = cand_threads > 0 ? cand_threads / 32 : 0;
-  int64_t cand_e[64];
-  int n_cand = 0;
+  const int T = cand_threads > 0 ? cand_threads : 0;
+  const int R = T == 256 ? 5 : T > 0 ? (5120 + T - 1) / T : 0;
+  const int use_cand = T > 0 && B % n == 0 && (int64_t)n <= (int64_t)R * T;
+  const int teff = use_cand ? ((((n + R - 1) / R) + 31) & ~31) : 1;
+  const int groups = use_cand ? T / teff : 1;
+  int64_t* cand_e = (int64_t*)malloc(sizeof(int64_t) * (T + 1));
+  int64_t* cls_rc = (int64_t*)malloc(sizeof(int64_t) * (T + 1));
+  int have_cand = 0;
   for (;;) {
     /* ---- entering arc ----------------------------------------------------------------------- */
     int64_t scanned = 0, best_e = -1, best_rc = 0;
-    if (n_cand > 0) {   /* minor iteration: re-price the candidates kept by the last pass */
-      for (int c = 0; c < n_cls; ++c) {
+    if (have_cand) {   /* minor iteration: re-price the candidates kept by the last pass */
+      for (int c = 0; c < T; ++c) {
         const int64_t e = cand_e[c];
         if (e < 0) continue;
         const int j = (int)(e / n), i = (int)(e - (int64_t)j * n);
         const int64_t rc = arc_cost(g, i, j) + g->pi[i] - g->pi[n + j];
+        if (rc >= 0) { cand_e[c] = -1; continue; }
         if (rc < best_rc) { best_rc = rc; best_e = e; }   /* lowest class wins ties */
       }
-      if (best_e < 0) n_cand = 0;
+      if (best_e < 0) have_cand = 0;
     }
     while (best_e < 0 && scanned < n_arcs) {   /* major pass: block search over arcs e = j*n + i */
       int64_t cnt = B < n_arcs - scanned ? B : n_arcs - scanned;
-      int64_t cls_rc[64];
-      for (int c = 0; c < n_cls; ++c) { cand_e[c] = -1; cls_rc[c] = 0; }
+      if (use_cand) for (int c = 0; c < T; ++c) { cand_e[c] = -1; cls_rc[c] = 0; }
       best_e = -1; best_rc = 0;
       int j = (int)(next_arc / n), i = (int)(next_arc - (int64_t)j * n);
+      int r = 0;                                           /* row of the block (use_cand: blocks start on a row) */
       for (int64_t k = 0; k < cnt; ++k) {
         const int64_t rc = arc_cost(g, i, j) + g->pi[i] - g->pi[n + j];
         if (rc < best_rc) { best_rc = rc; best_e = (int64_t)j * n + i; }   /* first minimum in block order */
-        if (n_cls > 0) {
-          const int c = (int)((k % cand_threads) / 32);
-          if (rc < cls_rc[c]) { cls_rc[c] = rc; cand_e[c] = (int64_t)j * n + i; }
+        if (use_cand) {
+          const int c = (r % groups) * teff + i % teff;
+          if (rc < cls_rc[c]) { cls_rc[c] = rc; cand_e[c] = (int64_t)j * n + i; }   /* the class's first minimum */
         }
-        if (++i == n) { i = 0; if (++j == m) j = 0; }
+        if (++i == n) { i = 0; ++r; if (++j == m) j = 0; }
       }
       scanned += cnt;
       next_arc += cnt;
       if (next_arc >= n_arcs) next_arc -= n_arcs;
-      if (best_e >= 0) { n_cand = n_cls; break; }
+      if (best_e >= 0) { have_cand = use_cand; break; }
     }
     if (best_e < 0) break; /* optimal */
     if (it >= max_iter) { status = 1; break; }
@@ -294,7 +305,7 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
     for (int t = 0; t < lenY; ++t) g->size[pathY[t]] += s;
   }
   *iters = it;
-  free(pathA); free(pathB); free(P); free(S); free(F);
+  free(pathA); free(pathB); free(P); free(S); free(F); free(cand_e); free(cls_rc);
   return status;
 }
 
@@ -497,9 +508,9 @@ static int refine_level(const Net* gc, const Hier* hs, const Hier* ht, int lev /
  */
 int stm_oracle_emd_ms(const int32_t* sx, const int32_t* sy, const double* smass, int n,
                       const int32_t* tx, const int32_t* ty, const double* tmass, int m,
-                      int64_t max_iter, int64_t block_size, uint32_t flags, double* cost_out, int64_t* iters,
-                      int64_t* level_iters) {
-  if (flags & 1u) return stm_oracle_emd(sx, sy, smass, n, tx, ty, tmass, m, max_iter, block_size, 0, cost_out, iters);
+                      int64_t max_iter, int64_t block_size, uint32_t flags, int cand_threads, double* cost_out,
+                      int64_t* iters, int64_t* level_iters) {
+  if (flags & 1u) return stm_oracle_emd(sx, sy, smass, n, tx, ty, tmass, m, max_iter, block_size, cand_threads, cost_out, iters);
   *cost_out = 0.0;
   if (iters) *iters = 0;
   if (level_iters) memset(level_iters, 0, sizeof(int64_t) * (STM_EMD_MAXLEV + 1));
@@ -513,7 +524,7 @@ int stm_oracle_emd_ms(const int32_t* sx, const int32_t* sy, const double* smass,
     int ok = 1;
     for (int i = 0; i < n && ok; ++i) ok = sx[i] - x0 < 49152 && sy[i] - y0 < 49152;
     for (int j = 0; j < m && ok; ++j) ok = tx[j] - x0 >= -16384 && tx[j] - x0 < 49152 && ty[j] - y0 >= -16384 && ty[j] - y0 < 49152;
-    if (!ok) { free(si); free(ti); return stm_oracle_emd(sx, sy, smass, n, tx, ty, tmass, m, max_iter, block_size, 0, cost_out, iters); }
+    if (!ok) { free(si); free(ti); return stm_oracle_emd(sx, sy, smass, n, tx, ty, tmass, m, max_iter, block_size, cand_threads, cost_out, iters); }
   }
   /* number of levels: coarsen until the coarsest problem has at most STM_EMD_COARSEST_NODES nodes */
   Hier hs, ht;
@@ -546,7 +557,7 @@ int stm_oracle_emd_ms(const int32_t* sx, const int32_t* sy, const double* smass,
     /* max_iter (numItermax of the reference) bounds the pivots on the ORIGINAL problem, i.e. the finest level; the
        coarse levels only construct its start basis and always run to their optimum */
     int64_t it = 0;
-    status = net_run(&g, lev == 0 ? max_iter : INT64_MAX, B, 0, &it);
+    status = net_run(&g, lev == 0 ? max_iter : INT64_MAX, B, cand_threads, &it);
     if (level_iters) level_iters[lev] = it;
     it_total += it;
     if (lev == 0 || status != 0) cost = lev == 0 ? net_cost(&g) : 0.0;

@@ -32,7 +32,7 @@ def _lib():
                                        C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         lib.stm_oracle_emd_ms.restype = C.c_int
         lib.stm_oracle_emd_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                          C.c_int, C.c_int64, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+                                          C.c_int, C.c_int64, C.c_int64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -50,7 +50,8 @@ def csr_to_problem(img):
 
 def emd_network_simplex(sx, sy, smass, tx, ty, tmass, max_iter=200000, block_size=0, cand_threads=0):
     """(cost, status, pivots).  max_iter mirrors ``numItermax=200000`` (distance.py:201).  ``cand_threads`` = T
-    prices like the CUDA kernel with T threads (candidate list, see emd_oracle.c); 0 = plain block search."""
+    prices like the CUDA kernel with T threads per problem (candidate list on whole-row blocks, see emd_oracle.c;
+    T = ``stminer_b200.Algorithm.distance.emd_pricing_threads``); 0 = plain block search."""
     sx = np.ascontiguousarray(sx, dtype=np.int32); sy = np.ascontiguousarray(sy, dtype=np.int32)
     tx = np.ascontiguousarray(tx, dtype=np.int32); ty = np.ascontiguousarray(ty, dtype=np.int32)
     smass = np.ascontiguousarray(smass, dtype=np.float64); tmass = np.ascontiguousarray(tmass, dtype=np.float64)
@@ -61,7 +62,7 @@ def emd_network_simplex(sx, sy, smass, tx, ty, tmass, max_iter=200000, block_siz
     return cost.value, st, iters.value
 
 
-def emd_multiscale(sx, sy, smass, tx, ty, tmass, max_iter=200000, block_size=0, star=False):
+def emd_multiscale(sx, sy, smass, tx, ty, tmass, max_iter=200000, block_size=0, star=False, cand_threads=0):
     """(cost, status, total pivots, pivots per level [0] = finest) with the multiscale start basis the CUDA kernel uses
     by default (see emd_oracle.c); ``max_iter`` bounds the pivots of the finest level, i.e. of the original problem."""
     sx = np.ascontiguousarray(sx, dtype=np.int32); sy = np.ascontiguousarray(sy, dtype=np.int32)
@@ -71,7 +72,7 @@ def emd_multiscale(sx, sy, smass, tx, ty, tmass, max_iter=200000, block_size=0, 
     lev = np.zeros(16, dtype=np.int64)
     st = _lib().stm_oracle_emd_ms(sx.ctypes.data, sy.ctypes.data, smass.ctypes.data, len(sx),
                                   tx.ctypes.data, ty.ctypes.data, tmass.ctypes.data, len(tx),
-                                  int(max_iter), int(block_size), 1 if star else 0, C.byref(cost), C.byref(iters),
+                                  int(max_iter), int(block_size), 1 if star else 0, int(cand_threads), C.byref(cost), C.byref(iters),
                                   lev.ctypes.data)
     return cost.value, st, iters.value, lev
 

@@ -1,5 +1,5 @@
 """Spot-EMD timing on Visium-size problems: multiscale start (default) vs the star start.
-   python scripts/prof_emd.py [n_problems] [--star]"""
+   python scripts/prof_emd.py [n_problems] [--star] [--nocand]   (--nocand: also time the plain block search)"""
 import sys
 import time
 
@@ -30,5 +30,12 @@ for star in ([False, True] if "--star" in sys.argv else [False]):
     res[star] = cost
     print("%s start: %d problems in %.3f s = %.1f problems/s; mean pivots %.0f; status counts %s"
           % ("star" if star else "multiscale", len(tg), dt, len(tg) / dt, iters.mean(), np.bincount(status).tolist()))
+if "--nocand" in sys.argv:
+    t0 = time.perf_counter()
+    cost, status, iters = emd_batched(src, tg, return_iters=True, candidates=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print("plain block search (no candidate list): %d problems in %.3f s = %.1f problems/s; mean pivots %.0f; max rel diff %.3e"
+          % (len(tg), dt, len(tg) / dt, iters.mean(), np.max(np.abs(cost - res[False]) / res[False])))
 if len(res) == 2:
     print("max rel diff between the two starts: %.3e" % np.max(np.abs(res[True] - res[False]) / res[True]))

@@ -141,34 +141,13 @@ def csr_to_support(img):
     return (coo.row[keep].astype(np.int32), coo.col[keep].astype(np.int32), coo.data[keep].astype(np.float64))
 
 
-def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, device=None, return_iters: bool = False,
-                star_start: bool = False):
-    """Exact EMD between one source support ``(x, y, mass)`` and every target support of ``targets``.
-
-    Returns ``(cost[G] float64, status[G] int32)`` as numpy arrays (+ pivots with ``return_iters``).
-    ``max_iter`` mirrors ``numItermax=200000`` of the reference (distance.py:201): a problem that hits it
-    reports status 1 and the cost of its current basis, as POT does.  ``star_start`` selects the artificial star
-    POT starts from instead of the multiscale start basis (same optimum, about ten times the pivots).
-    """
-    torch = _lib.require_cuda()
-    lib = _lib.load()
-    device = torch.device(device if device is not None else "cuda")
-    G = len(targets)
-    sx, sy, sm = (np.ascontiguousarray(src[0], dtype=np.int32), np.ascontiguousarray(src[1], dtype=np.int32),
-                  np.ascontiguousarray(src[2], dtype=np.float64))
-    sizes = np.array([len(t[0]) for t in targets], dtype=np.int64)
-    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    cat = lambda k, dt: (np.concatenate([np.asarray(t[k], dtype=dt) for t in targets]) if G else np.zeros(0, dtype=dt))
-    tx, ty, tm = cat(0, np.int32), cat(1, np.int32), cat(2, np.float64)
-    if G == 0:
-        out = (np.zeros(0), np.zeros(0, dtype=np.int32))
-        return out + (np.zeros(0, dtype=np.int64),) if return_iters else out
-    if len(sx) == 0:
-        out = (np.zeros(G), np.full(G, 2, dtype=np.int32))
-        return out + (np.zeros(G, dtype=np.int64),) if return_iters else out
-    max_tgt = int(sizes.max())
-    # the default kernel keeps int32 potentials: it needs 2 * (span^2 + 1) * nodes < 2^31 for the bounding box of source
-    # and target together; problems beyond that (scattered coordinates, long thin tissues) go to the 64-bit variant
+def _emd_size_classes(lib, sx, sy, sizes, ptr, tx, ty):
+    """Masks over the targets of one source: (int32 kernel, 64-bit kernel, global-tree kernel); the rest keep status 3.
+    The default kernel keeps int32 potentials: it needs 2 * (span^2 + 1) * nodes < 2^31 for the bounding box of source and
+    target together; problems beyond that (scattered coordinates, long thin tissues) go to the 64-bit variant.  Beyond one
+    CTA's shared memory — e.g. a Stereo-seq bin50 slide with 40,000 source bins — the tree lives in the CTA's global
+    scratch."""
+    G = len(sizes)
     nz = sizes > 0
     first = ptr[:-1][nz]
     ext = {}
@@ -179,6 +158,64 @@ def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, devic
         ext[name] = hi - lo
     maxc = ext["x"] ** 2 + ext["y"] ** 2
     narrow = 2 * (maxc + 1) * (len(sx) + sizes + 1) + maxc < 2 ** 31 - 1
+    nodes = len(sx) + sizes + 1
+    cap_n, cap_w = int(lib.stm_emd_smem_node_capacity(0)), int(lib.stm_emd_smem_node_capacity(1))
+    cap_g = int(lib.stm_emd_global_node_capacity())
+    arcs_ok = len(sx) * sizes < 2 ** 31 - 1
+    small_n = narrow & (nodes <= cap_n)
+    small_w = ~narrow & (nodes <= cap_w)
+    large = ~small_n & ~small_w & (nodes <= cap_g) & arcs_ok
+    return small_n, small_w, large
+
+
+def _emd_pack(src, targets):
+    sx, sy, sm = (np.ascontiguousarray(src[0], dtype=np.int32), np.ascontiguousarray(src[1], dtype=np.int32),
+                  np.ascontiguousarray(src[2], dtype=np.float64))
+    G = len(targets)
+    sizes = np.array([len(t[0]) for t in targets], dtype=np.int64)
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    cat = lambda k, dt: (np.concatenate([np.asarray(t[k], dtype=dt) for t in targets]) if G else np.zeros(0, dtype=dt))
+    return sx, sy, sm, sizes, ptr, cat(0, np.int32), cat(1, np.int32), cat(2, np.float64)
+
+
+def emd_pricing_threads(src, targets) -> np.ndarray:
+    """Per target: threads per problem of the candidate-list pricing ``emd_batched(src, targets)`` solves it with
+    (512 or 256; 0 = plain block search: 64-bit and global-tree kernels) — what the CPU oracle takes as
+    ``cand_threads`` to follow the same pivots."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    sx, sy, sm, sizes, ptr, tx, ty, tm = _emd_pack(src, targets)
+    out = np.zeros(len(targets), dtype=np.int64)
+    if len(targets) == 0 or len(sx) == 0:
+        return out
+    small_n, _, _ = _emd_size_classes(lib, sx, sy, sizes, ptr, tx, ty)
+    if small_n.any():
+        out[small_n] = int(lib.stm_emd_pricing_threads(len(sx), int(sizes[small_n].max()), 0))
+    return out
+
+
+def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, device=None, return_iters: bool = False,
+                star_start: bool = False, candidates: bool = True):
+    """Exact EMD between one source support ``(x, y, mass)`` and every target support of ``targets``.
+
+    Returns ``(cost[G] float64, status[G] int32)`` as numpy arrays (+ pivots with ``return_iters``).
+    ``max_iter`` mirrors ``numItermax=200000`` of the reference (distance.py:201): a problem that hits it
+    reports status 1 and the cost of its current basis, as POT does.  ``star_start`` selects the artificial star
+    POT starts from instead of the multiscale start basis (same optimum, about ten times the pivots);
+    ``candidates=False`` prices by plain block search, one pricing pass per pivot (same optimum, more passes).
+    """
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    device = torch.device(device if device is not None else "cuda")
+    G = len(targets)
+    sx, sy, sm, sizes, ptr, tx, ty, tm = _emd_pack(src, targets)
+    if G == 0:
+        out = (np.zeros(0), np.zeros(0, dtype=np.int32))
+        return out + (np.zeros(0, dtype=np.int64),) if return_iters else out
+    if len(sx) == 0:
+        out = (np.zeros(G), np.full(G, 2, dtype=np.int32))
+        return out + (np.zeros(G, dtype=np.int64),) if return_iters else out
+    small_n, small_w, large = _emd_size_classes(lib, sx, sy, sizes, ptr, tx, ty)
     up = lambda a: torch.from_numpy(a).to(device)
     d = [up(a) for a in (sx, sy, sm, ptr, tx, ty, tm)]
     with torch.cuda.device(device):
@@ -186,15 +223,6 @@ def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, devic
         cost = torch.full((G,), float("nan"), dtype=torch.float64, device=device)
         status = torch.full((G,), 3, dtype=torch.int32, device=device)
         iters = torch.zeros(G, dtype=torch.int64, device=device)
-        # size classes: tree in shared memory (int32 / int64 potentials), or — beyond one CTA's shared memory, e.g. a
-        # Stereo-seq bin50 slide with 40,000 source bins — in the CTA's global scratch; problems beyond that keep status 3
-        nodes = len(sx) + sizes + 1
-        cap_n, cap_w = int(lib.stm_emd_smem_node_capacity(0)), int(lib.stm_emd_smem_node_capacity(1))
-        cap_g = int(lib.stm_emd_global_node_capacity())
-        arcs_ok = len(sx) * sizes < 2 ** 31 - 1
-        small_n = narrow & (nodes <= cap_n)
-        small_w = ~narrow & (nodes <= cap_w)
-        large = ~small_n & ~small_w & (nodes <= cap_g) & arcs_ok
         keep = []
         for wide, sel, big in ((False, np.flatnonzero(small_n), False), (True, np.flatnonzero(small_w), False),
                                (True, np.flatnonzero(large), True)):
@@ -214,7 +242,8 @@ def emd_batched(src, targets, max_iter: int = 200000, block_size: int = 0, devic
             fn = lib.stm_emd_spots_batched_wide if wide else lib.stm_emd_spots_batched
             st = fn(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), len(sx), _lib.ptr(d[3]),
                     _lib.ptr(d[4]), _lib.ptr(d[5]), _lib.ptr(d[6]), len(sel), call_max_tgt, _lib.ptr(d_order),
-                    int(max_iter), int(block_size), _lib.STM_EMD_STAR_START if star_start else 0,
+                    int(max_iter), int(block_size),
+                    (_lib.STM_EMD_STAR_START if star_start else 0) | (0 if candidates else _lib.STM_EMD_NO_CANDIDATES),
                     _lib.ptr(ws), ws_bytes, n_ctas,
                     _lib.ptr(cost), _lib.ptr(status), _lib.ptr(iters), _lib.current_stream_ptr())
             _lib.check(st, "stm_emd_spots_batched_wide" if wide else "stm_emd_spots_batched")

@@ -25,6 +25,7 @@ STM_FIT_DEVICE_INIT = 2
 STM_FIT_COMPACT_INPUT = 4
 STM_FIT_NO_CLUSTERS = 8
 STM_EMD_STAR_START = 1
+STM_EMD_NO_CANDIDATES = 2
 STM_FIT_N_BUCKETS = 7     # cluster x16 / x8 / x4 / x2, then one CTA per gene: large / medium / small
 
 
@@ -62,6 +63,7 @@ SIGNATURES = {
                                              C.c_int64, C.c_int32, C.c_uint32, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "stm_emd_smem_node_capacity": (C.c_int32, [C.c_int32]),
     "stm_emd_global_node_capacity": (C.c_int32, []),
+    "stm_emd_pricing_threads": (C.c_int32, [C.c_int32, C.c_int64, C.c_int32]),
     "stm_stage_blocks": (C.c_int32, [C.c_int32]),
     "stm_stage_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "stm_stage_csr_columns": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_uint32, _P, C.c_int64, C.c_int64,
