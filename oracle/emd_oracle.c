@@ -43,6 +43,7 @@
 #define STM_EMD_SCALE 1125899906842624.0 /* 2^50 */
 #define STM_EMD_MAXLEV 11
 #define STM_EMD_COARSEST_NODES 64
+#define STM_EMD_GROW 3   /* a pricing block after k empty ones is 2^min(k, 3) times as long (candidate-list pricing) */
 
 typedef struct {
   int n, m, N, root;
@@ -173,11 +174,12 @@ static int net_from_forest(Net* g, const int32_t* ai, const int32_t* aj, const i
  * cand_threads = T > 0: CANDIDATE LIST, the way the register-resident pricing path of the CUDA kernel with T threads
  * works (emd_spots.cu; it applies when the block is a whole number of target rows, B % n == 0, and the level has at most
  * R * T sources, R = 5 for T = 256 and ceil(5120 / T) otherwise — emd_rmax there).  The kernel's threads form
- * groups = T / teff row groups of teff = roundup32(ceil(n / R)) threads; the arc (i, j) with j the r-th row of the block
+ * groups = T / teff row groups of teff = max(32, ceil(n / R)) rounded up to a power of two threads; the arc (i, j) with j the r-th row of the block
  * belongs to thread (class)  (r mod groups) * teff + (i mod teff).  A pricing pass (a "major" iteration) that finds a
  * negative block keeps every class's first most-negative arc of that block; the following "minor" iterations re-price
  * only these <= T candidates (those no longer negative are dropped), enter the most negative one (ties: lowest class)
  * and fall back to the block search where the last pass stopped once none is negative (LEMON's candidate-list idea).
+ * Within a pass, the block that follows k blocks without a negative arc is 2^min(k, STM_EMD_GROW) times B long.
  */
 static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_threads, int64_t* iters) {
   const int n = g->n, m = g->m, N = g->N;
@@ -195,7 +197,8 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
   const int T = cand_threads > 0 ? cand_threads : 0;
   const int R = T == 256 ? 5 : T > 0 ? (5120 + T - 1) / T : 0;
   const int use_cand = T > 0 && B % n == 0 && (int64_t)n <= (int64_t)R * T;
-  const int teff = use_cand ? ((((n + R - 1) / R) + 31) & ~31) : 1;
+  int teff = 32;
+  while (use_cand && teff < (n + R - 1) / R) teff <<= 1;
   const int groups = use_cand ? T / teff : 1;
   int64_t* cand_e = (int64_t*)malloc(sizeof(int64_t) * (T + 1));
   int64_t* cls_rc = (int64_t*)malloc(sizeof(int64_t) * (T + 1));
@@ -214,8 +217,13 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
       }
       if (best_e < 0) have_cand = 0;
     }
+    int empty = 0;                             /* consecutive blocks of this pass without a negative arc */
     while (best_e < 0 && scanned < n_arcs) {   /* major pass: block search over arcs e = j*n + i */
-      int64_t cnt = B < n_arcs - scanned ? B : n_arcs - scanned;
+      /* with the candidate list, a block that follows k empty ones is 2^min(k, STM_EMD_GROW) times as long (the kernel
+         amortises its per-block work over the long fruitless scans near the optimum) */
+      const int64_t Bk = use_cand ? B << (empty < STM_EMD_GROW ? empty : STM_EMD_GROW) : B;
+      int64_t cnt = Bk < n_arcs - scanned ? Bk : n_arcs - scanned;
+      ++empty;
       if (use_cand) for (int c = 0; c < T; ++c) { cand_e[c] = -1; cls_rc[c] = 0; }
       best_e = -1; best_rc = 0;
       int j = (int)(next_arc / n), i = (int)(next_arc - (int64_t)j * n);

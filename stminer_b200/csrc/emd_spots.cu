@@ -37,7 +37,9 @@ namespace stm {
 namespace {
 
 constexpr int EMD_PREP_THREADS = 1024;
+constexpr int EMD_GROW = 3;             // a pricing block after k empty ones is 2^min(k, 3) times as long (candidate-list pricing)
 constexpr int EMD_MAXPATH_S = 2048;     // longest cycle path kept, shared-memory tree
+static_assert(2 * EMD_MAXPATH_S <= 0x1fff, "the leaving-arc key keeps 13 bits for the position on the cycle");
 constexpr int EMD_MAXPATH_G = 8192;     // global-memory tree
 constexpr int EMD_SCAN_CH_G = 8;        // global tree: up to 30 * 8 * threads nodes
 constexpr int EMD_ROWS_G = 64;          // most target rows of a pricing block of the global-tree kernel
@@ -413,7 +415,6 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
   __shared__ int s_ws[EMD_WARPS];          // block scans of the hierarchy / refinement code
   __shared__ int s_lv[EMD_LV];             // node counts of the target hierarchy
   __shared__ long long s_wrc64[WIDE ? 2 * EMD_WARPS : 1];   // per-warp reduced costs of the WIDE pricing arg-min
-  __shared__ long long s_delta;
   __shared__ int s_row[GLOBAL ? 2 * EMD_ROWS_G : 1];          // the block's target rows: -2x, -2y
   __shared__ long long s_rowp[GLOBAL ? EMD_ROWS_G : 1];       // and potentials (global-tree pricing)
   __shared__ int s_cand[(WIDE || GLOBAL) ? 1 : EMD_THREADS];  // candidate list: every thread's best arc (j << 16 | i) of the last pass
@@ -716,6 +717,8 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     const bool whole_rows = !WIDE && B % n == 0 && n <= EMD_RMAX_T * EMD_THREADS;   // n_arcs and every block start are multiples of n
     const bool whole_rows_g = GLOBAL && B % n == 0 && B / n <= EMD_ROWS_G;
     int next_arc = 0;
+    int next_row = 0;                               // next_arc / n while the blocks are whole rows
+    const int rows_B = whole_rows ? B / n : 0;
     long long it = 0;
     unsigned round = 0;
     // Candidate list (register-resident whole-row pricing only): a pricing pass that finds a negative block leaves every
@@ -745,7 +748,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       c_t0 = clock64();
 #endif
       // ---- entering arc: block search over arcs e = j*n + i ----------------------------------------
-      int scanned = 0, best_e = -1;
+      int scanned = 0, best_e = -1, cand_j = -1;
       pi_t best_rc = 0;
       if constexpr (!WIDE && !GLOBAL) {
         if (have_cand) {
@@ -771,7 +774,8 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           if (m_rc < 0) {
             const int cw = s_cand[m_t];                            // its owner kept it (only dropped entries are rewritten)
             best_rc = m_rc;
-            best_e = (cw >> 16) * n + (cw & 0xffff);
+            cand_j = cw >> 16;
+            best_e = cand_j * n + (cw & 0xffff);
 #ifdef STM_EMD_PROFILE
             ++n_minor;
 #endif
@@ -780,8 +784,14 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           }
         }
       }
+      int empty = 0;                       // consecutive blocks of this pass without a negative arc
       while (best_e < 0 && scanned < n_arcs) {
-        const int cnt = min(B, n_arcs - scanned);
+        // with the candidate list, the block after k empty ones is 2^min(k, EMD_GROW) times as long: near the optimum most
+        // blocks hold no negative arc, and the per-block work (sources into registers, reduction, barrier) is paid less often
+        const int grow = cand_on ? min(empty, EMD_GROW) : 0;
+        const int Bk = B << grow;
+        const int cnt = min(Bk, n_arcs - scanned);
+        ++empty;
         // The block is arcs [next_arc, next_arc + cnt) of the j-major arc order (wrapping): a few target rows,
         // each a contiguous range of sources.  Per row the target's terms stay in registers and the inner loop is
         // two shared loads, two IMADs and a compare per arc.
@@ -805,10 +815,14 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
             // unpacking, the loop — is amortised over as many arcs as possible) and the groups share the block's rows
             // (rows gidx, gidx + groups, ...), so the small coarse levels of the multiscale start use all lanes too.
             int sx[EMD_RMAX_T], sy[EMD_RMAX_T], sp[EMD_RMAX_T];
-            const int teff = (((n + EMD_RMAX_T - 1) / EMD_RMAX_T) + 31) & ~31;
-            const int groups = EMD_THREADS / teff;
-            const int gidx = tid / teff;
-            const int i0 = tid - gidx * teff;
+            // teff = the power of two >= max(32, ceil(n / slots)): group and lane indices by shifts (the block loop runs
+            // thousands of times per problem: no integer division on its path)
+            const int tq = (n + EMD_RMAX_T - 1) / EMD_RMAX_T;
+            const int tsh = tq <= 32 ? 5 : 32 - __clz(tq - 1);
+            const int teff = 1 << tsh;
+            const int groups = EMD_THREADS >> tsh;
+            const int gidx = tid >> tsh;
+            const int i0 = tid & (teff - 1);
 #pragma unroll
             for (int r = 0; r < EMD_RMAX_T; ++r) {
               const int i = i0 + r * teff;
@@ -819,8 +833,8 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
             }
             // The scan only tracks the thread's minimum (an add, two IMADs and a share of a 3-input min per arc); the
             // arc that attains the block minimum is located afterwards by the few threads whose minimum equals it.
-            const int j0 = next_arc / n;
-            const int rows = cnt / n;
+            const int j0 = next_row;
+            const int rows = cnt == Bk ? rows_B << grow : cnt / n;   // (the division: last block of a full sweep only)
             const int rr0 = gidx < groups ? gidx : rows;       // lanes beyond the last row group sit the block out
             int j = j0 + gidx;
             while (j >= m) j -= m;
@@ -1027,6 +1041,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
         scanned += cnt;
         next_arc += cnt;
         if (next_arc >= n_arcs) next_arc -= n_arcs;
+        if (whole_rows) { next_row += cnt == Bk ? rows_B << grow : cnt / n; if (next_row >= m) next_row -= m; }
         if (g_rc < 0) {
           best_rc = g_rc;
           best_e = start + (int)g_k;
@@ -1041,7 +1056,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       if (best_e < 0) break;                      // optimal
       if (it >= level_max_iter) { status = 1; break; }
       ++it;
-      const int ej = best_e / n, ei = best_e - ej * n;
+      const int ej = cand_j >= 0 ? cand_j : best_e / n, ei = best_e - ej * n;
       const int u_i = ei, u_j = n + ej;
       // ---- cycle: the two tree paths from the entering arc's endpoints up to their join node -----------------
       // A node v is an ancestor of u iff pos[v] <= pos[u] < pos[v] + size[v].  Instead of chasing parent pointers from
@@ -1101,41 +1116,72 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           rb = cta_excl_scan<EMD_THREADS>(cntB, s_ws, &nB);
         }
         if (tid == 0) { s_i[1] = nA; s_i[2] = nB; }
+        // ---- leaving arc, found while the paths are written: min flow over the arcs traversed against their direction;
+        //      ties by the strongly-feasible rule (i side: closest to i; j side wins and takes the one closest to the join)
+        //      = lexicographic (flow ascending, sequence number descending), sequence = lenA - 1 - a on path A (index a),
+        //      lenA + b on path B.  Every thread looks at the entries it writes, the warps combine by shuffles and the
+        //      per-warp results meet in shared memory behind the barrier the paths need anyway.
+        long long dmin = LLONG_MAX;
+        int dseq = -1;
         if (nA <= EMD_MAXPATH && nB <= EMD_MAXPATH) {
 #pragma unroll
           for (int c = 0; c < SCAN_CH; ++c) {
-            for (unsigned mm = mA[c]; mm; mm &= mm - 1) s_pathA[nA - 1 - ra++] = s_order[x0 + 32 * c + __ffs(mm) - 1];
-            for (unsigned mm = mB[c]; mm; mm &= mm - 1) s_pathB[nB - 1 - rb++] = s_order[x0 + 32 * c + __ffs(mm) - 1];
+            for (unsigned mm = mA[c]; mm; mm &= mm - 1) {
+              const int v = s_order[x0 + 32 * c + __ffs(mm) - 1];
+              s_pathA[nA - 1 - ra] = (idx_t)v;
+              if (v < n) { const long long f = FL(v); if (f < dmin || (f == dmin && ra > dseq)) { dmin = f; dseq = ra; } }
+              ++ra;
+            }
+            for (unsigned mm = mB[c]; mm; mm &= mm - 1) {
+              const int v = s_order[x0 + 32 * c + __ffs(mm) - 1];
+              s_pathB[nB - 1 - rb] = (idx_t)v;
+              const int sq = nA + nB - 1 - rb;
+              if (v >= n) { const long long f = FL(v); if (f < dmin || (f == dmin && sq > dseq)) { dmin = f; dseq = sq; } }
+              ++rb;
+            }
           }
+        }
+        if constexpr (!GLOBAL) {
+          // flows are < 2^50 + 1 and sequence numbers < 2 * EMD_MAXPATH_S = 2^12: one 64-bit key (flow, 8191 - sequence),
+          // minimised by two 32-bit REDUX steps (high word, then low word among the lanes that hold the minimum)
+          const unsigned long long key = dseq < 0 ? ~0ull : ((unsigned long long)dmin << 13) | (unsigned)(0x1fff - dseq);
+          const unsigned kh = (unsigned)(key >> 32), kl = (unsigned)key;
+          const unsigned mh = __reduce_min_sync(FULL_MASK, kh);
+          const unsigned ml = __reduce_min_sync(FULL_MASK, kh == mh ? kl : 0xffffffffu);
+          if (lane == 0) s_ll[warp] = (long long)(((unsigned long long)mh << 32) | ml);
+        } else {
+          for (int o = 16; o > 0; o >>= 1) {
+            const long long od = shfl_xor_ll(dmin, o);
+            const int os = __shfl_xor_sync(FULL_MASK, dseq, o);
+            if (od < dmin || (od == dmin && os > dseq)) { dmin = od; dseq = os; }
+          }
+          if (lane == 0) { s_ll[warp] = dmin; s_ll[EMD_WARPS + warp] = dseq; }
         }
       }
       __syncthreads();
       const int lenA = s_i[1], lenB = s_i[2];
       PROF_T(c_walk)
       if (lenA > EMD_MAXPATH || lenB > EMD_MAXPATH) { status = 4; break; }
-      // ---- leaving arc (warp 0): min flow over arcs traversed against their direction; ties resolved by
-      //      the strongly-feasible rule (i side: closest to i; j side wins and takes the one closest to the join)
-      if (warp == 0) {
-        long long dmin = LLONG_MAX;
-        int seq = -1;
-        for (int a = lane; a < lenA; a += 32) {
-          const int v = s_pathA[a];
-          if (v < n) { const long long f = FL(v); const int sq = lenA - 1 - a; if (f < dmin || (f == dmin && sq > seq)) { dmin = f; seq = sq; } }
-        }
-        for (int b = lane; b < lenB; b += 32) {
-          const int v = s_pathB[b];
-          if (v >= n) { const long long f = FL(v); const int sq = lenA + b; if (f < dmin || (f == dmin && sq > seq)) { dmin = f; seq = sq; } }
-        }
+      long long delta;
+      int seq;
+      if constexpr (!GLOBAL) {   // every warp combines the per-warp results: no second barrier
+        const unsigned long long key = lane < EMD_WARPS ? (unsigned long long)s_ll[lane] : ~0ull;
+        const unsigned kh = (unsigned)(key >> 32), kl = (unsigned)key;
+        const unsigned mh = __reduce_min_sync(FULL_MASK, kh);
+        const unsigned ml = __reduce_min_sync(FULL_MASK, kh == mh ? kl : 0xffffffffu);
+        const unsigned long long best = ((unsigned long long)mh << 32) | ml;
+        delta = (long long)(best >> 13);
+        seq = best == ~0ull ? -1 : 0x1fff - (int)(best & 0x1fffu);
+      } else {
+        long long dm = lane < EMD_WARPS ? s_ll[lane] : LLONG_MAX;
+        int ds = lane < EMD_WARPS ? (int)s_ll[EMD_WARPS + lane] : -1;
         for (int o = 16; o > 0; o >>= 1) {
-          const long long od = shfl_xor_ll(dmin, o);
-          const int os = __shfl_xor_sync(FULL_MASK, seq, o);
-          if (od < dmin || (od == dmin && os > seq)) { dmin = od; seq = os; }
+          const long long od = shfl_xor_ll(dm, o);
+          const int os = __shfl_xor_sync(FULL_MASK, ds, o);
+          if (od < dm || (od == dm && os > ds)) { dm = od; ds = os; }
         }
-        if (lane == 0) { s_delta = dmin; s_i[3] = seq; }
+        delta = dm; seq = ds;
       }
-      __syncthreads();
-      const long long delta = s_delta;
-      const int seq = s_i[3];
       PROF_T(c_leave)
       if (seq < 0) { status = 5; break; }        // unbounded: cannot happen for a transport LP
       const int side = seq >= lenA ? 1 : 0;
@@ -1150,8 +1196,21 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       const int ptr = pt < a0 ? pt : pt - s;
       const pi_t shift = side == 0 ? -best_rc : best_rc;
       // ---- flow update along the cycle + old flows / positions / sizes of the reversed path --------
-      for (int a = tid; a < lenA; a += EMD_THREADS) { const int v = s_pathA[a]; FL(v) += (v < n) ? -delta : delta; }
-      for (int b = tid; b < lenB; b += EMD_THREADS) { const int v = s_pathB[b]; FL(v) += (v >= n) ? -delta : delta; }
+      // side Y and the part of side X above the leaving arc in place; the new flows of pathX[0 .. k-1] move one node up the
+      // reversed path, so they wait in registers until everyone has read (the arc of pathX[k] leaves the basis)
+      constexpr int MAXT = (EMD_MAXPATH + EMD_THREADS - 1) / EMD_THREADS;
+      long long fo[MAXT];
+      for (int t = tid; t < lenY; t += EMD_THREADS) { const int v = pathY[t]; FL(v) += ((v < n) == (side == 1)) ? -delta : delta; }
+#pragma unroll
+      for (int r = 0; r < MAXT; ++r) {
+        const int t = tid + r * EMD_THREADS;
+        fo[r] = 0;
+        if (t < lenX) {
+          const int v = pathX[t];
+          const long long f = FL(v) + (((v < n) == (side == 0)) ? -delta : delta);
+          if (t > k) FL(v) = f; else fo[r] = f;
+        }
+      }
       for (int t = tid; t <= k; t += EMD_THREADS) { const int v = pathX[t]; s_P[t] = s_pos[v]; s_S[t] = s_size[v]; }
       // potential shift of the re-hung subtree (a contiguous preorder segment)
       for (int x = a0 + tid; x < a0 + s; x += EMD_THREADS) s_pi[s_order[x]] += shift;
@@ -1161,22 +1220,14 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       __syncthreads();
       // ---- reversed path: parents, flows, sizes (flows read before anyone overwrites them) ----------
       {
-        // every thread handles t = tid, tid + T, ...; two passes: read old flows, then write
-        constexpr int MAXT = (EMD_MAXPATH + EMD_THREADS - 1) / EMD_THREADS;
-        long long fo[MAXT];
-#pragma unroll
-        for (int r = 0; r < MAXT; ++r) {
-          const int t = tid + r * EMD_THREADS;
-          fo[r] = (t >= 1 && t <= k) ? FL(pathX[t - 1]) : 0;
-        }
-        __syncthreads();
 #pragma unroll
         for (int r = 0; r < MAXT; ++r) {
           const int t = tid + r * EMD_THREADS;
           if (t <= k) {
             const int v = pathX[t];
             if (t == 0) { s_parent[v] = (idx_t)t_in; FL(v) = delta; s_size[v] = (idx_t)s; }
-            else { s_parent[v] = pathX[t - 1]; FL(v) = fo[r]; s_size[v] = (idx_t)(s - s_S[t - 1]); }
+            else { s_parent[v] = pathX[t - 1]; s_size[v] = (idx_t)(s - s_S[t - 1]); }
+            if (t < k) FL(pathX[t + 1]) = fo[r];
           }
         }
       }
