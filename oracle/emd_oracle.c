@@ -43,6 +43,7 @@
 #define STM_EMD_SCALE 1125899906842624.0 /* 2^50 */
 #define STM_EMD_MAXLEV 11
 #define STM_EMD_COARSEST_NODES 64
+#define STM_EMD_GROW_G 4 /* the same for the global-tree kernel (cand_threads < 0): blocks of up to 64 target rows */
 #define STM_EMD_GROW 3   /* a pricing block after k empty ones is 2^min(k, 3) times as long (candidate-list pricing) */
 
 typedef struct {
@@ -180,6 +181,8 @@ static int net_from_forest(Net* g, const int32_t* ai, const int32_t* aj, const i
  * only these <= T candidates (those no longer negative are dropped), enter the most negative one (ties: lowest class)
  * and fall back to the block search where the last pass stopped once none is negative (LEMON's candidate-list idea).
  * Within a pass, the block that follows k blocks without a negative arc is 2^min(k, STM_EMD_GROW) times B long.
+ * cand_threads < 0: the pricing of the global-tree kernel (problems beyond one CTA's shared memory): plain block search
+ * whose blocks grow the same way (up to 2^STM_EMD_GROW_G times B and at most 64 target rows), no candidate list.
  */
 static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_threads, int64_t* iters) {
   const int n = g->n, m = g->m, N = g->N;
@@ -200,6 +203,7 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
   int teff = 32;
   while (use_cand && teff < (n + R - 1) / R) teff <<= 1;
   const int groups = use_cand ? T / teff : 1;
+  const int grow_g = cand_threads < 0 && B % n == 0 && B / n <= 64;   /* pricing of the global-tree kernel: growing blocks only */
   int64_t* cand_e = (int64_t*)malloc(sizeof(int64_t) * (T + 1));
   int64_t* cls_rc = (int64_t*)malloc(sizeof(int64_t) * (T + 1));
   int have_cand = 0;
@@ -221,7 +225,12 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
     while (best_e < 0 && scanned < n_arcs) {   /* major pass: block search over arcs e = j*n + i */
       /* with the candidate list, a block that follows k empty ones is 2^min(k, STM_EMD_GROW) times as long (the kernel
          amortises its per-block work over the long fruitless scans near the optimum) */
-      const int64_t Bk = use_cand ? B << (empty < STM_EMD_GROW ? empty : STM_EMD_GROW) : B;
+      int64_t Bk = use_cand ? B << (empty < STM_EMD_GROW ? empty : STM_EMD_GROW) : B;
+      if (grow_g) {   /* global-tree kernel: up to STM_EMD_GROW_G doublings while the block stays within 64 target rows */
+        int gsh = empty < STM_EMD_GROW_G ? empty : STM_EMD_GROW_G;
+        while (gsh > 0 && ((B / n) << gsh) > 64) --gsh;
+        Bk = B << gsh;
+      }
       int64_t cnt = Bk < n_arcs - scanned ? Bk : n_arcs - scanned;
       ++empty;
       if (use_cand) for (int c = 0; c < T; ++c) { cand_e[c] = -1; cls_rc[c] = 0; }
@@ -230,7 +239,8 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
       int r = 0;                                           /* row of the block (use_cand: blocks start on a row) */
       for (int64_t k = 0; k < cnt; ++k) {
         const int64_t rc = arc_cost(g, i, j) + g->pi[i] - g->pi[n + j];
-        if (rc < best_rc) { best_rc = rc; best_e = (int64_t)j * n + i; }   /* first minimum in block order */
+        /* first minimum in block order; the global-tree kernel's whole-row blocks: lowest source index, then first row */
+        if (rc < best_rc || (grow_g && rc == best_rc && rc < 0 && i < (int)(best_e % n))) { best_rc = rc; best_e = (int64_t)j * n + i; }
         if (use_cand) {
           const int c = (r % groups) * teff + i % teff;
           if (rc < cls_rc[c]) { cls_rc[c] = rc; cand_e[c] = (int64_t)j * n + i; }   /* the class's first minimum */

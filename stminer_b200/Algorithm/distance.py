@@ -180,17 +180,18 @@ def _emd_pack(src, targets):
 
 def emd_pricing_threads(src, targets) -> np.ndarray:
     """Per target: threads per problem of the candidate-list pricing ``emd_batched(src, targets)`` solves it with
-    (512 or 256; 0 = plain block search: 64-bit and global-tree kernels) — what the CPU oracle takes as
-    ``cand_threads`` to follow the same pivots."""
+    (512 or 256; 0 = plain block search: the 64-bit kernel; -1 = the global-tree kernel, whose blocks grow over fruitless
+    scans) — what the CPU oracle takes as ``cand_threads`` to follow the same pivots."""
     _lib.require_cuda()
     lib = _lib.load()
     sx, sy, sm, sizes, ptr, tx, ty, tm = _emd_pack(src, targets)
     out = np.zeros(len(targets), dtype=np.int64)
     if len(targets) == 0 or len(sx) == 0:
         return out
-    small_n, _, _ = _emd_size_classes(lib, sx, sy, sizes, ptr, tx, ty)
+    small_n, _, large = _emd_size_classes(lib, sx, sy, sizes, ptr, tx, ty)
     if small_n.any():
         out[small_n] = int(lib.stm_emd_pricing_threads(len(sx), int(sizes[small_n].max()), 0))
+    out[large] = -1
     return out
 
 

@@ -37,6 +37,7 @@ namespace stm {
 namespace {
 
 constexpr int EMD_PREP_THREADS = 1024;
+constexpr int EMD_GROW_G = 4;           // the same for the global-tree kernel (blocks of 4 .. 64 target rows)
 constexpr int EMD_GROW = 3;             // a pricing block after k empty ones is 2^min(k, 3) times as long (candidate-list pricing)
 constexpr int EMD_MAXPATH_S = 2048;     // longest cycle path kept, shared-memory tree
 static_assert(2 * EMD_MAXPATH_S <= 0x1fff, "the leaving-arc key keeps 13 bits for the position on the cycle");
@@ -727,6 +728,8 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     // (ties: lowest thread) and return to the block search where it stopped once none of them is negative.  Same
     // optimum, about 10 % fewer pivots and a third of the block scans on the coarse levels (oracle: cand_threads).
     const bool cand_on = !WIDE && !GLOBAL && whole_rows && !(p.flags & STM_EMD_NO_CANDIDATES);
+    const bool grow_g = GLOBAL && whole_rows_g && !(p.flags & STM_EMD_NO_CANDIDATES);
+    const int rows_Bg = whole_rows_g ? B / n : 0;
     bool have_cand = false;
     // numItermax of the reference bounds the pivots on the ORIGINAL problem (level 0); the coarse levels only construct
     // its start basis and run to their optimum
@@ -788,7 +791,12 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       while (best_e < 0 && scanned < n_arcs) {
         // with the candidate list, the block after k empty ones is 2^min(k, EMD_GROW) times as long: near the optimum most
         // blocks hold no negative arc, and the per-block work (sources into registers, reduction, barrier) is paid less often
-        const int grow = cand_on ? min(empty, EMD_GROW) : 0;
+        int grow = cand_on ? min(empty, EMD_GROW) : 0;
+        if constexpr (GLOBAL) {
+          // global-tree kernel: the sources stream from L2 once per block, so long blocks pay even more — up to
+          // EMD_ROWS_G target rows (what the block's row table in shared memory holds)
+          if (grow_g) { grow = min(empty, EMD_GROW_G); while (grow > 0 && (rows_Bg << grow) > EMD_ROWS_G) --grow; }
+        }
         const int Bk = B << grow;
         const int cnt = min(Bk, n_arcs - scanned);
         ++empty;
@@ -936,32 +944,35 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
               ++round;
             }
             if (g_rc < 0) {
-              unsigned myk = 0xffffffffu;                      // its first position in block order among this thread's arcs
+              // The entering arc among the arcs that attain the minimum: lowest source index first, then the first row of
+              // the block (a thread meets its sources tile by tile, so "first in block order" would need a second scan; this
+              // order costs nothing — first tile, first slot, first row — and the oracle resolves ties the same way).
+              unsigned mykey = 0xffffffffu;                    // source index * EMD_ROWS_G + row of the block
               if (trc == (long long)g_rc) {
-                for (int r2 = 0; r2 < rows && myk == 0xffffffffu; ++r2) {
-                  const long long nx2 = s_row[2 * r2], ny2 = s_row[2 * r2 + 1], bj = s_rowp[r2];
-                  int j = j0 + r2;
-                  while (j >= m) j -= m;
-#pragma unroll
-                  for (int r = 0; r < RG; ++r) {
-                    const int i = tbase + tid + r * EMD_THREADS;
-                    if (i < n && myk == 0xffffffffu) {
-                      const int xy = s_xy[i];
-                      const long long rc = ((xy << 16) >> 16) * nx2 + ((xy >> 16) * ny2 + ((long long)s_pi[i] - bj));
-                      if (rc == (long long)g_rc) {
-                        int k = j * n + i - next_arc;
-                        if (k < 0) k += n_arcs;
-                        myk = (unsigned)k;
-                      }
-                    }
+#pragma unroll 1
+                for (int r = 0; r < RG && mykey == 0xffffffffu; ++r) {
+                  const int i = tbase + tid + r * EMD_THREADS;
+                  if (i >= n) break;
+                  const int xy = s_xy[i];
+                  const long long sxi = (xy << 16) >> 16, syi = xy >> 16, spi = (long long)s_pi[i];
+                  for (int r2 = 0; r2 < rows; ++r2) {
+                    const long long rc = sxi * s_row[2 * r2] + (syi * s_row[2 * r2 + 1] + (spi - s_rowp[r2]));
+                    if (rc == (long long)g_rc) { mykey = (unsigned)i * EMD_ROWS_G + (unsigned)r2; break; }
                   }
                 }
               }
-              const unsigned w_k = __reduce_min_sync(FULL_MASK, myk);
+              const unsigned w_k = __reduce_min_sync(FULL_MASK, mykey);
               unsigned* wk = reinterpret_cast<unsigned*>(s_wkey + (round & 1) * EMD_WARPS);
               if (lane == 0) wk[warp] = w_k;
               __syncthreads();
-              g_k = __reduce_min_sync(FULL_MASK, lane < EMD_WARPS ? wk[lane] : 0xffffffffu);
+              const unsigned g_key = __reduce_min_sync(FULL_MASK, lane < EMD_WARPS ? wk[lane] : 0xffffffffu);
+              {
+                int j = j0 + (int)(g_key % EMD_ROWS_G);
+                while (j >= m) j -= m;
+                int k = j * n + (int)(g_key / EMD_ROWS_G) - next_arc;
+                if (k < 0) k += n_arcs;
+                g_k = (unsigned)k;
+              }
               ++round;
             } else {
               g_rc = PI_NONE;

@@ -82,13 +82,18 @@ def test_emd_beyond_one_cta_runs_with_the_tree_in_global_memory(cuda_device):
         tgs.append((t // 150, t % 150, rng.random(m) + 0.1))
     cost, status, iters = emd_batched(src, tgs, return_iters=True)
     costB, statusB, itersB = emd_batched(src, tgs, block_size=40000, return_iters=True)
-    T = emd_pricing_threads(src, tgs)          # 0 for the global-tree kernel, 512 for the target that fits shared memory
-    assert sorted(T.tolist()) == [0, 0, 512]
+    T = emd_pricing_threads(src, tgs)          # -1 for the global-tree kernel, 512 for the target that fits shared memory
+    assert sorted(T.tolist()) == [-1, -1, 512]
+    costR, statusR, itersR = emd_batched(src, tgs, block_size=8 * n, return_iters=True)      # whole target rows
     for g, t in enumerate(tgs):
         c, st, it, lev = eo.emd_multiscale(*src, *t, block_size=40000, cand_threads=int(T[g]))
         assert status[g] == statusB[g] == st == 0, (g, status, statusB)
         assert abs(cost[g] - c) <= 1e-11 * c and abs(costB[g] - c) <= 1e-11 * c, (g, cost[g], costB[g], c)
         assert itersB[g] == it, (g, itersB[g], it, lev[:8])
+        # blocks of whole target rows: the global-tree kernel lengthens them over fruitless scans, the oracle likewise
+        c2, st2, it2, lev2 = eo.emd_multiscale(*src, *t, block_size=8 * n, cand_threads=int(T[g]))
+        assert statusR[g] == st2 == 0 and itersR[g] == it2, (g, itersR[g], it2, lev2[:8])
+        assert abs(costR[g] - c) <= 1e-11 * c
 
 
 def test_emd_node_capacity_limit_reports_status_3(cuda_device):
