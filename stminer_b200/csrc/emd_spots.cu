@@ -42,7 +42,7 @@ constexpr int EMD_GROW = 3;             // a pricing block after k empty ones is
 constexpr int EMD_MAXPATH_S = 2048;     // longest cycle path kept, shared-memory tree
 static_assert(2 * EMD_MAXPATH_S <= 0x1fff, "the leaving-arc key keeps 13 bits for the position on the cycle");
 constexpr int EMD_MAXPATH_G = 8192;     // global-memory tree
-constexpr int EMD_SCAN_CH_G = 8;        // global tree: up to 30 * 8 * threads nodes
+constexpr int EMD_SCAN_CH_G = 8;        // global tree: node capacity 30 * 8 * threads (the workspace and the tests are sized for it)
 constexpr int EMD_ROWS_G = 64;          // most target rows of a pricing block of the global-tree kernel
 #ifndef STM_EMD_ROWS_MIN_G
 #define STM_EMD_ROWS_MIN_G 4
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
   constexpr int EMD_WARPS = EMD_THREADS / 32;
   constexpr int EMD_RMAX_T = emd_rmax(EMD_THREADS, ONE_PER_SM);
   constexpr int EMD_MAXPATH = GLOBAL ? EMD_MAXPATH_G : EMD_MAXPATH_S;
-  constexpr int SCAN_CH = GLOBAL ? EMD_SCAN_CH_G : 1;        // 32-position chunks of a thread's run in the cycle-path scan
+  constexpr int SCAN_CH = 1;        // 32-position chunks of a thread's run in the cycle-path scan (shared-memory kernels)
   using pi_t = typename std::conditional<WIDE, long long, int>::type;
   using idx_t = typename std::conditional<GLOBAL, uint32_t, unsigned short>::type;
   constexpr idx_t NONE16 = (idx_t)~(idx_t)0, UNVIS16 = (idx_t)(NONE16 - 1);
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     const int N0 = n0 + m0 + 1;
     // N + 1 <= cap: the tree build keeps N + 1 offsets in one node array; N <= 30 * threads: the cycle-path scan keeps one
     // bit per preorder position of a thread's run in a 32-bit mask
-    const bool fits = N0 + 1 <= cap && (GLOBAL || N0 < 65534) && N0 <= 30 * SCAN_CH * EMD_THREADS && (int64_t)n0 * m0 < 2147483647LL;
+    const bool fits = N0 + 1 <= cap && (GLOBAL || N0 < 65534) && (GLOBAL ? (int64_t)N0 <= EMD_GLOBAL_MAX_NODES : N0 <= 30 * SCAN_CH * EMD_THREADS) && (int64_t)n0 * m0 < 2147483647LL;
     const long long maxc0 = (long long)(xmax - xmin) * (xmax - xmin) + (long long)(ymax - ymin) * (ymax - ymin);
     const bool coords_ok = (xmax - ox) < 32768 && (ox - xmin) < 32768 && (ymax - oy) < 32768 && (oy - ymin) < 32768;
     const long long pi_limit = WIDE ? (1LL << 61) : 2147483647LL;
@@ -1074,7 +1074,31 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       // both endpoints (two lanes, ~180 cycles per step, everyone else waiting), every thread tests a run of consecutive
       // PREORDER POSITIONS: path A = ancestors-or-self of u_i that are not ancestors of u_j, path B the converse; along
       // a path the position decreases, so an ordered compaction (one block scan) yields both paths in walking order.
-      {
+      if constexpr (GLOBAL) {
+        // Global-tree kernel: the tree lives in L2, where that scan costs two loads per position of a 10^5-node preorder
+        // (~130k cycles).  Here two lanes climb instead — lane 0 of warp 0 from u_i (path A), lane 0 of warp 1 from u_j
+        // (path B): position, size, parent and flow of a node are loaded together, so a step costs one L2 round trip,
+        // ~40 steps per side.  The leaving arc is tracked on the way (same rule: smallest flow; on side A the first such
+        // arc met, on side B the last, B before A).
+        if (lane == 0 && warp < 2) {
+          const int other = warp == 0 ? u_j : u_i;
+          const int po = s_pos[other];
+          idx_t* const path = warp == 0 ? s_pathA : s_pathB;
+          int v = warp == 0 ? u_i : u_j, len = 0, didx = -1;
+          long long dmin = LLONG_MAX;
+          for (;;) {
+            const int pv = s_pos[v], sv = s_size[v], par = s_parent[v];
+            const long long f = FL(v);
+            if ((unsigned)(po - pv) < (unsigned)sv) break;          // v is an ancestor of the other endpoint: the join
+            if (len < EMD_MAXPATH) path[len] = (idx_t)v;
+            if (warp == 0 ? (v < n && f < dmin) : (v >= n && f <= dmin)) { dmin = f; didx = len; }
+            ++len;
+            v = par;
+          }
+          s_i[1 + warp] = len;
+          s_ll[warp] = dmin; s_ll[EMD_WARPS + warp] = didx;
+        }
+      } else {
         const int pu = s_pos[u_i], pw = s_pos[u_j];
         int per = (N + EMD_THREADS - 1) / EMD_THREADS;             // <= 30 * SCAN_CH for every problem that fits
         per += (2 - per) & 3;   // per = 2 (mod 4): a lane stride of per uint16 is an odd number of 4-byte words, so the
@@ -1083,7 +1107,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
         unsigned mA[SCAN_CH], mB[SCAN_CH];                         // one bit per position of the run, 32 per chunk
 #pragma unroll
         for (int c = 0; c < SCAN_CH; ++c) { mA[c] = 0u; mB[c] = 0u; }
-        constexpr int PER_UNROLL = GLOBAL ? 8 : 4;                 // independent load pairs in flight
+        constexpr int PER_UNROLL = 4;                              // independent load pairs in flight
         const int xlim = min(x1, max(pu, pw) + 1);                 // ancestors precede their descendants
 #pragma unroll
         for (int c = 0; c < SCAN_CH; ++c) {
@@ -1107,7 +1131,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
 #pragma unroll
         for (int c = 0; c < SCAN_CH; ++c) { cntA += __popc(mA[c]); cntB += __popc(mB[c]); }
         int nA, nB, ra, rb;                                        // totals; ranks in ascending position = distance from the join
-        if constexpr (!GLOBAL) {
+        {
           // exclusive block scan of the two counts, packed in one word
           const int cnt = cntA | (cntB << 16);
           int incl = cnt;
@@ -1122,9 +1146,6 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           const int before = __shfl_sync(FULL_MASK, wincl - wtot, warp) + incl - cnt;
           nA = total & 0xffff; nB = total >> 16;
           ra = before & 0xffff; rb = before >> 16;
-        } else {
-          ra = cta_excl_scan<EMD_THREADS>(cntA, s_ws, &nA);
-          rb = cta_excl_scan<EMD_THREADS>(cntB, s_ws, &nB);
         }
         if (tid == 0) { s_i[1] = nA; s_i[2] = nB; }
         // ---- leaving arc, found while the paths are written: min flow over the arcs traversed against their direction;
@@ -1152,7 +1173,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
             }
           }
         }
-        if constexpr (!GLOBAL) {
+        {
           // flows are < 2^50 + 1 and sequence numbers < 2 * EMD_MAXPATH_S = 2^12: one 64-bit key (flow, 8191 - sequence),
           // minimised by two 32-bit REDUX steps (high word, then low word among the lanes that hold the minimum)
           const unsigned long long key = dseq < 0 ? ~0ull : ((unsigned long long)dmin << 13) | (unsigned)(0x1fff - dseq);
@@ -1160,13 +1181,6 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           const unsigned mh = __reduce_min_sync(FULL_MASK, kh);
           const unsigned ml = __reduce_min_sync(FULL_MASK, kh == mh ? kl : 0xffffffffu);
           if (lane == 0) s_ll[warp] = (long long)(((unsigned long long)mh << 32) | ml);
-        } else {
-          for (int o = 16; o > 0; o >>= 1) {
-            const long long od = shfl_xor_ll(dmin, o);
-            const int os = __shfl_xor_sync(FULL_MASK, dseq, o);
-            if (od < dmin || (od == dmin && os > dseq)) { dmin = od; dseq = os; }
-          }
-          if (lane == 0) { s_ll[warp] = dmin; s_ll[EMD_WARPS + warp] = dseq; }
         }
       }
       __syncthreads();
@@ -1184,14 +1198,10 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
         delta = (long long)(best >> 13);
         seq = best == ~0ull ? -1 : 0x1fff - (int)(best & 0x1fffu);
       } else {
-        long long dm = lane < EMD_WARPS ? s_ll[lane] : LLONG_MAX;
-        int ds = lane < EMD_WARPS ? (int)s_ll[EMD_WARPS + lane] : -1;
-        for (int o = 16; o > 0; o >>= 1) {
-          const long long od = shfl_xor_ll(dm, o);
-          const int os = __shfl_xor_sync(FULL_MASK, ds, o);
-          if (od < dm || (od == dm && os > ds)) { dm = od; ds = os; }
-        }
-        delta = dm; seq = ds;
+        const long long fA = s_ll[0], fB = s_ll[1];
+        const int ia = (int)s_ll[EMD_WARPS], ib = (int)s_ll[EMD_WARPS + 1];
+        if (ib >= 0 && (ia < 0 || fB <= fA)) { delta = fB; seq = lenA + ib; }
+        else { delta = fA; seq = ia >= 0 ? lenA - 1 - ia : -1; }
       }
       PROF_T(c_leave)
       if (seq < 0) { status = 5; break; }        // unbounded: cannot happen for a transport LP
