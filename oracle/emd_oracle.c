@@ -41,7 +41,10 @@
 #include <string.h>
 
 #define STM_EMD_SCALE 1125899906842624.0 /* 2^50 */
-#define STM_EMD_MAXLEV 11
+#define STM_EMD_MAXLEV 23  /* bit levels 0 .. 23: cells up to 2^11 x 2^12 */
+#define STM_EMD_MAXUSE 16  /* levels in use per problem at most */
+#define STM_EMD_SKIP_NUM 4   /* a bit level that keeps more than 4/5 of the nodes of the level below is skipped */
+#define STM_EMD_SKIP_DEN 5
 #define STM_EMD_COARSEST_NODES 64
 #define STM_EMD_GROW_G 4 /* the same for the global-tree kernel (cand_threads < 0): blocks of up to 64 target rows */
 #define STM_EMD_GROW 3   /* a pricing block after k empty ones is 2^min(k, 3) times as long (candidate-list pricing) */
@@ -379,13 +382,14 @@ static int cmp_key(const void* a, const void* b) {
   return x < y ? -1 : x > y;
 }
 
-/* One side's hierarchy: level 0 = the points in Morton order (ties by input index); level l+1 = runs of level-l
- * nodes in the same (x >> (l+1), y >> (l+1)) cell.  x/y of level l are the cell coordinates u >> l (u = biased
- * coordinate), child[l][c] .. child[l][c+1] are the children (at level l-1) of node c of level l >= 1. */
+/* One side's hierarchy over BIT levels: level 0 = the points in Morton order (ties by input index); level b + 1 = runs of
+ * level-b nodes whose Morton codes agree after dropping one more bit — cells are halved along y first (odd b: 2^(b/2) wide,
+ * 2^(b/2 + 1) high), then along x.  x/y of level b are the cell coordinates (u_x >> b/2, u_y >> (b+1)/2) of the biased
+ * coordinates u; child[b][c] .. child[b][c+1] are the children (at level b-1) of node c of level b >= 1. */
 typedef struct {
   int L;
   int cnt[STM_EMD_MAXLEV + 1];
-  uint32_t* code[STM_EMD_MAXLEV + 1];   /* morton code of the level-0 cell >> 2l */
+  uint32_t* code[STM_EMD_MAXLEV + 1];   /* morton code of the level-0 cell >> b */
   int32_t* x[STM_EMD_MAXLEV + 1];
   int32_t* y[STM_EMD_MAXLEV + 1];
   int64_t* mass[STM_EMD_MAXLEV + 1];
@@ -412,11 +416,13 @@ static void hier_build(Hier* h, const int32_t* px, const int32_t* py, const int6
     h->child[l] = (int32_t*)malloc(sizeof(int32_t) * (pn + 1));
     int c = -1;
     for (int i = 0; i < pn; ++i) {
-      const uint32_t pc = h->code[l - 1][i] >> 2;
+      const uint32_t pc = h->code[l - 1][i] >> 1;
       if (c < 0 || pc != h->code[l][c]) {
         ++c;
         h->code[l][c] = pc; h->child[l][c] = i; h->mass[l][c] = 0;
-        h->x[l][c] = h->x[l - 1][i] >> 1; h->y[l][c] = h->y[l - 1][i] >> 1;   /* arithmetic shift = floor: cell coordinates */
+        /* odd level: the y bit goes (the Morton code holds y in the even bits); arithmetic shift = floor: cell coordinates */
+        h->x[l][c] = (l & 1) ? h->x[l - 1][i] : h->x[l - 1][i] >> 1;
+        h->y[l][c] = (l & 1) ? h->y[l - 1][i] >> 1 : h->y[l - 1][i];
       }
       h->mass[l][c] += h->mass[l - 1][i];
     }
@@ -438,7 +444,7 @@ static int cmp_arc_ij(const void* a, const void* b) {   /* arcs packed as (I << 
  * Stage 1, per coarse source I: north-west corner between its children (in order) and its arcs (by increasing J)
  * gives pieces (fine source, J, flow).  Stage 2, per coarse target J: north-west corner between its pieces (by
  * increasing I, then child order = increasing fine source) and its children gives the fine arcs. */
-static int refine_level(const Net* gc, const Hier* hs, const Hier* ht, int lev /* coarse level */,
+static int refine_level(const Net* gc, const Hier* hs, const Hier* ht, int lev /* coarse level */, int flev /* fine: lev - 1 or lev - 2 */,
                         int32_t** out_i, int32_t** out_j, int64_t** out_f) {
   const int nS = gc->n, nT = gc->m;
   /* coarse arcs sorted by (I, J) */
@@ -459,9 +465,12 @@ static int refine_level(const Net* gc, const Hier* hs, const Hier* ht, int lev /
     aF[e] = gc->parent[I] == J ? gc->flow[I] : gc->flow[J];   /* the arc is stored at its child end */
   }
   free(key);
-  const int32_t* cs = hs->child[lev]; const int32_t* ct = ht->child[lev];
-  const int64_t* fs = hs->mass[lev - 1]; const int64_t* ft = ht->mass[lev - 1];
-  const int nf = hs->cnt[lev - 1], mf = ht->cnt[lev - 1];
+  /* children at the fine level: directly, or through the skipped level in between (descendants stay contiguous) */
+  int32_t* cs = (int32_t*)malloc(sizeof(int32_t) * (nS + 1)); int32_t* ct = (int32_t*)malloc(sizeof(int32_t) * (nT + 1));
+  for (int I = 0; I <= nS; ++I) cs[I] = flev == lev - 1 ? hs->child[lev][I] : hs->child[lev - 1][hs->child[lev][I]];
+  for (int J = 0; J <= nT; ++J) ct[J] = flev == lev - 1 ? ht->child[lev][J] : ht->child[lev - 1][ht->child[lev][J]];
+  const int64_t* fs = hs->mass[flev]; const int64_t* ft = ht->mass[flev];
+  const int nf = hs->cnt[flev], mf = ht->cnt[flev];
   /* stage 1: pieces per arc (in arc order (I, J)); at most children(I) pieces per arc */
   const int maxp = nf + Ec + 1;
   int32_t* pc_i = (int32_t*)malloc(sizeof(int32_t) * maxp); int64_t* pc_f = (int64_t*)malloc(sizeof(int64_t) * maxp);
@@ -512,7 +521,7 @@ static int refine_level(const Net* gc, const Hier* hs, const Hier* ht, int lev /
       }
     }
   }
-  free(aI); free(aJ); free(aF); free(pc_i); free(pc_f); free(pc_first); free(toff); free(tlist); free(tcur);
+  free(aI); free(aJ); free(aF); free(pc_i); free(pc_f); free(pc_first); free(toff); free(tlist); free(tcur); free(cs); free(ct);
   (void)nf;
   *out_i = oi; *out_j = oj; *out_f = of;
   return E;
@@ -522,7 +531,7 @@ static int refine_level(const Net* gc, const Hier* hs, const Hier* ht, int lev /
  * Exact EMD with the multiscale start.  flags bit 0: star start (then identical to stm_oracle_emd).
  * block_size > 0: that block at every level (clamped to the level's arc count); <= 0: max(sqrt(n_l m_l),
  * min(n_l m_l, rows * n_l)) with rows = 7 — whole target rows, as the CUDA kernel prices.
- * level_iters (optional, STM_EMD_MAXLEV + 1 entries): pivots per level, [0] = finest.
+ * level_iters (optional, STM_EMD_MAXLEV + 1 entries): pivots per level in use, [0] = finest.
  */
 int stm_oracle_emd_ms(const int32_t* sx, const int32_t* sy, const double* smass, int n,
                       const int32_t* tx, const int32_t* ty, const double* tmass, int m,
@@ -548,17 +557,32 @@ int stm_oracle_emd_ms(const int32_t* sx, const int32_t* sy, const double* smass,
   Hier hs, ht;
   hier_build(&hs, sx, sy, si, n, x0, y0, STM_EMD_MAXLEV + 1);
   hier_build(&ht, tx, ty, ti, m, x0, y0, STM_EMD_MAXLEV + 1);
+  /* the bit levels in use, finest first: a level that keeps more than 4/5 of the nodes of the one below it is skipped (on
+     the Visium lattice, where (row + col) is even, halving along y merges nothing); never two in a row */
+  int seq[STM_EMD_MAXLEV + 1];
   int L = 1;
-  while (L <= STM_EMD_MAXLEV && hs.cnt[L - 1] + ht.cnt[L - 1] > STM_EMD_COARSEST_NODES) ++L;
+  seq[0] = 0;
+  for (int b = 0; hs.cnt[b] + ht.cnt[b] > STM_EMD_COARSEST_NODES && b + 1 <= STM_EMD_MAXLEV && L < STM_EMD_MAXUSE;) {
+    int nb = b + 1;
+    if (nb + 1 <= STM_EMD_MAXLEV &&
+        (int64_t)STM_EMD_SKIP_DEN * (hs.cnt[nb] + ht.cnt[nb]) > (int64_t)STM_EMD_SKIP_NUM * (hs.cnt[b] + ht.cnt[b])) nb = b + 2;
+    seq[L++] = nb;
+    b = nb;
+  }
   int status = 0;
   int64_t it_total = 0;
   int32_t *ai = 0, *aj = 0; int64_t* af = 0;
   int E = 0;
   double cost = 0.0;
-  for (int lev = L - 1; lev >= 0 && status == 0; --lev) {
+  for (int li = L - 1; li >= 0 && status == 0; --li) {
+    const int lev = seq[li];
     Net g;
     const int nl = hs.cnt[lev], ml = ht.cnt[lev];
-    net_alloc(&g, nl, ml, hs.x[lev], hs.y[lev], ht.x[lev], ht.y[lev]);
+    /* isotropic cost in units of the cell width: an odd level's cells are twice as high as wide */
+    int32_t* ys = (int32_t*)malloc(sizeof(int32_t) * (nl + 1)); int32_t* yt = (int32_t*)malloc(sizeof(int32_t) * (ml + 1));
+    for (int i = 0; i < nl; ++i) ys[i] = hs.y[lev][i] * (1 + (lev & 1));
+    for (int j = 0; j < ml; ++j) yt[j] = ht.y[lev][j] * (1 + (lev & 1));
+    net_alloc(&g, nl, ml, hs.x[lev], ys, ht.x[lev], yt);
     int ok = -1;
     if (ai) {
       ok = net_from_forest(&g, ai, aj, af, E);
@@ -575,12 +599,13 @@ int stm_oracle_emd_ms(const int32_t* sx, const int32_t* sy, const double* smass,
     /* max_iter (numItermax of the reference) bounds the pivots on the ORIGINAL problem, i.e. the finest level; the
        coarse levels only construct its start basis and always run to their optimum */
     int64_t it = 0;
-    status = net_run(&g, lev == 0 ? max_iter : INT64_MAX, B, cand_threads, &it);
-    if (level_iters) level_iters[lev] = it;
+    status = net_run(&g, li == 0 ? max_iter : INT64_MAX, B, cand_threads, &it);
+    if (level_iters) level_iters[li] = it;
     it_total += it;
-    if (lev == 0 || status != 0) cost = lev == 0 ? net_cost(&g) : 0.0;
-    else E = refine_level(&g, &hs, &ht, lev, &ai, &aj, &af);
+    if (li == 0 || status != 0) cost = li == 0 ? net_cost(&g) : 0.0;
+    else E = refine_level(&g, &hs, &ht, lev, seq[li - 1], &ai, &aj, &af);
     net_free(&g);
+    free(ys); free(yt);
   }
   if (ai) { free(ai); free(aj); free(af); }
   hier_free(&hs); hier_free(&ht);

@@ -69,7 +69,7 @@ def emd_multiscale(sx, sy, smass, tx, ty, tmass, max_iter=200000, block_size=0, 
     tx = np.ascontiguousarray(tx, dtype=np.int32); ty = np.ascontiguousarray(ty, dtype=np.int32)
     smass = np.ascontiguousarray(smass, dtype=np.float64); tmass = np.ascontiguousarray(tmass, dtype=np.float64)
     cost = C.c_double(0.0); iters = C.c_int64(0)
-    lev = np.zeros(16, dtype=np.int64)
+    lev = np.zeros(32, dtype=np.int64)
     st = _lib().stm_oracle_emd_ms(sx.ctypes.data, sy.ctypes.data, smass.ctypes.data, len(sx),
                                   tx.ctypes.data, ty.ctypes.data, tmass.ctypes.data, len(tx),
                                   int(max_iter), int(block_size), 1 if star else 0, int(cand_threads), C.byref(cost), C.byref(iters),

@@ -52,8 +52,10 @@ constexpr int EMD_RG_G = 8;             // sources per thread and tile in its pr
 constexpr int EMD_GLOBAL_THREADS = 512;
 constexpr int64_t EMD_GLOBAL_ALLOC_NODES = 9000;
 constexpr int64_t EMD_GLOBAL_MAX_NODES = 30LL * EMD_SCAN_CH_G * EMD_GLOBAL_THREADS;   // 122,880
-constexpr int EMD_LV = 12;            // hierarchy levels kept (level 0 = the problem itself)
-constexpr int EMD_COARSEST = 64;      // the coarsest level solved has at most this many nodes (or is level EMD_LV - 1)
+constexpr int EMD_LV = 24;            // BIT levels of the hierarchy kept per side (level 0 = the problem itself; level b = Morton code >> b)
+constexpr int EMD_LU = 16;            // levels in use per problem at most (a level that merges < 20 % of the nodes is skipped)
+constexpr int EMD_HDR_X0 = 32, EMD_HDR_Y0 = 33, EMD_HDR_OK = 34;   // src_hdr entries behind the EMD_LV node counts
+constexpr int EMD_COARSEST = 64;      // the coarsest level solved has at most this many nodes (or is the last level kept / in use)
 constexpr int EMD_BIAS = 16384;       // Morton keys take coordinates relative to the source's corner in [-16384, 32768)
 #ifndef STM_EMD_T_BIG
 #define STM_EMD_T_BIG 512    // CTA size of the one-CTA-per-SM kernel: the pricing scan is issue-bound (same time at 512 or 1,024
@@ -147,7 +149,7 @@ struct EmdArgs {
   int64_t max_iter; int32_t block_size; uint32_t flags;
   // source side, built once per batch by emd_prep_kernel
   int64_t* src_int;               // [n_src] integer source masses in input order (star start)
-  int32_t* src_hdr;               // [0, EMD_LV) node counts per level, [16] x0, [17] y0, [18] 1 = coordinates in range
+  int32_t* src_hdr;               // [0, EMD_LV) node counts per bit level, [32] x0, [33] y0, [34] 1 = coordinates in range
   EmdHier hs;
   char* cta_ws; int64_t cta_ws_bytes;   // per-CTA scratch slices
   unsigned int* counter;          // dynamic problem queue
@@ -275,8 +277,10 @@ __device__ void cta_prefix_inplace(int32_t* a, int len, int* s_ws) {
   __syncthreads();
 }
 
-// Levels 1 .. EMD_LV - 1 of one side from its level 0 (cnt0 nodes in Morton order, codes in codeA).  cnt[] receives the
-// node counts.  Whole CTA.
+// Bit levels 1 .. EMD_LV - 1 of one side from its level 0 (cnt0 nodes in Morton order, codes in codeA): level b = runs of
+// level b - 1 nodes whose codes agree after one more bit is dropped — cells are halved along y first (the code holds y in its
+// even bits), then along x; xy of level b = cell coordinates (u_x >> b/2, u_y >> (b+1)/2).  cnt[] receives the node counts.
+// Whole CTA.
 template <int T>
 __device__ void build_levels(const EmdHier h, int cnt0, uint32_t* codeA, uint32_t* codeB, int32_t* cnt, int* s_ws) {
   if (threadIdx.x == 0) cnt[0] = cnt0;
@@ -292,15 +296,15 @@ __device__ void build_levels(const EmdHier h, int cnt0, uint32_t* codeA, uint32_
     const int per = (pn + T - 1) / T;
     const int b = min(pn, (int)threadIdx.x * per), e = min(pn, b + per);
     int heads = 0;
-    for (int i = b; i < e; ++i) heads += (i == 0 || (cin[i] >> 2) != (cin[i - 1] >> 2)) ? 1 : 0;
+    for (int i = b; i < e; ++i) heads += (i == 0 || (cin[i] >> 1) != (cin[i - 1] >> 1)) ? 1 : 0;
     int total = 0;
     int c = cta_excl_scan<T>(heads, s_ws, &total);
     for (int i = b; i < e; ++i) {
-      if (i == 0 || (cin[i] >> 2) != (cin[i - 1] >> 2)) {
+      if (i == 0 || (cin[i] >> 1) != (cin[i - 1] >> 1)) {
         const int xy = pxy[i];
-        const int x = ((xy << 16) >> 16) >> 1, y = (xy >> 16) >> 1;          // arithmetic shifts: cell coordinates
+        const int x = ((xy << 16) >> 16) >> ((l & 1) ^ 1), y = (xy >> 16) >> (l & 1);   // arithmetic shifts: cell coordinates
         cxy[c] = (x & 0xffff) | (y << 16);
-        cout[c] = cin[i] >> 2;
+        cout[c] = cin[i] >> 1;
         cch[c] = i;
         ++c;
       }
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(EMD_PREP_THREADS) emd_prep_kernel(const int32_
   __syncthreads();
   x0 = s_box[0]; x1 = s_box[1]; y0 = s_box[2]; y1 = s_box[3];
   const bool ok = (long long)x1 - x0 < 32768 && (long long)y1 - y0 < 32768;
-  if (tid == 0) { hdr[16] = x0; hdr[17] = y0; hdr[18] = ok ? 1 : 0; }
+  if (tid == 0) { hdr[EMD_HDR_X0] = x0; hdr[EMD_HDR_Y0] = y0; hdr[EMD_HDR_OK] = ok ? 1 : 0; }
   if (!ok) { if (tid < EMD_LV) hdr[tid] = 0; return; }
   for (int i = tid; i < P; i += T)
     sortbuf[i] = i < n ? ((unsigned long long)morton16((uint32_t)(src_x[i] - x0 + EMD_BIAS), (uint32_t)(src_y[i] - y0 + EMD_BIAS)) << 32) | (unsigned)i
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
   __shared__ int s_i[16];
   __shared__ int s_wsum[EMD_WARPS];
   __shared__ int s_ws[EMD_WARPS];          // block scans of the hierarchy / refinement code
-  __shared__ int s_lv[EMD_LV];             // node counts of the target hierarchy
+  __shared__ int s_lv[EMD_LU];             // levels in use, finest first: bit level << 20 | node count of the target side
   __shared__ long long s_wrc64[WIDE ? 2 * EMD_WARPS : 1];   // per-warp reduced costs of the WIDE pricing arg-min
   __shared__ int s_row[GLOBAL ? 2 * EMD_ROWS_G : 1];          // the block's target rows: -2x, -2y
   __shared__ long long s_rowp[GLOBAL ? EMD_ROWS_G : 1];       // and potentials (global-tree pricing)
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
   int64_t* flow;
   { EMD_SCRATCH(sc0); flow = sc0.flow; }
   auto FL = [&](int v) -> long long& { return v < fcap ? s_flow[v] : *reinterpret_cast<long long*>(flow + v); };
-  const bool hier_ok = p.src_hdr[18] != 0;
+  const bool hier_ok = p.src_hdr[EMD_HDR_OK] != 0;
 
   for (;;) {
     __syncthreads();
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       continue;
     }
     // ---- bounding box (relative to the source's corner), capacity checks ------------------------------------
-    const int ox = hier_ok ? p.src_hdr[16] : p.src_x[0], oy = hier_ok ? p.src_hdr[17] : p.src_y[0];
+    const int ox = hier_ok ? p.src_hdr[EMD_HDR_X0] : p.src_x[0], oy = hier_ok ? p.src_hdr[EMD_HDR_Y0] : p.src_y[0];
     int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
     int txmin = INT_MAX, tymin = INT_MAX, txmax = INT_MIN, tymax = INT_MIN;
     for (int v = tid; v < n0 + m0; v += EMD_THREADS) {
@@ -513,22 +517,35 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       }
       __syncthreads();
       build_levels<EMD_THREADS>(sc.ht, m0, sc.codeA, sc.codeB, sc.tcnt, s_ws);
-      if (tid < EMD_LV) s_lv[tid] = sc.tcnt[tid];
+      // the bit levels in use: coarsen until at most EMD_COARSEST nodes are left; a level that keeps more than 4/5 of the
+      // nodes of the one below it is skipped (on the Visium lattice halving along y merges nothing), never two in a row
+      if (tid == 0) {
+        int b = 0, Lc = 1;
+        s_lv[0] = sc.tcnt[0];
+        while (p.src_hdr[b] + sc.tcnt[b] > EMD_COARSEST && b + 1 < EMD_LV && Lc < EMD_LU) {
+          int nb = b + 1;
+          if (nb + 1 < EMD_LV && 5LL * (p.src_hdr[nb] + sc.tcnt[nb]) > 4LL * (p.src_hdr[b] + sc.tcnt[b])) nb = b + 2;
+          s_lv[Lc++] = (nb << 20) | sc.tcnt[nb];
+          b = nb;
+        }
+        s_i[10] = Lc;
+      }
       __syncthreads();
-      while (L < EMD_LV && p.src_hdr[L - 1] + s_lv[L - 1] > EMD_COARSEST) ++L;
+      L = s_i[10];
     }
 
 #ifdef STM_EMD_PROFILE
     if (tid == 0 && g < 2) printf("[emd prof] g=%d hierarchy %lld cycles, %d levels\n", g, (long long)(clock64() - c_h0), L);
 #endif
-    for (int lev = L - 1; lev >= 0; --lev) {
+    for (int li = L - 1; li >= 0; --li) {
 #ifdef STM_EMD_PROFILE
     const long long c_l0 = clock64();
 #endif
+    const int lev = star ? 0 : s_lv[li] >> 20;          // bit level
     n = star ? n0 : p.src_hdr[lev];
-    m = star ? m0 : s_lv[lev];
+    m = star ? m0 : s_lv[li] & 0xfffff;
     N = n + m + 1; root = n + m;
-    const bool from_forest = !star && lev < L - 1;
+    const bool from_forest = !star && li < L - 1;
     const int Ef = from_forest ? s_i[8] : 0;
     // ---- stage the level's coordinates, its bounding box -------------------------------------------------------
     {
@@ -543,6 +560,8 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           xy = ((x - ox) & 0xffff) | ((y - oy) << 16);
         } else {
           xy = v < n ? hsx[v] : htx[v - n];
+          // an odd level's cells are twice as high as wide: y in units of the cell width keeps the cost isotropic
+          if (lev & 1) xy = (xy & 0xffff) | (((xy >> 16) * 2) << 16);
         }
         s_xy[v] = xy;
         const int x = (xy << 16) >> 16, y = xy >> 16;
@@ -733,7 +752,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     bool have_cand = false;
     // numItermax of the reference bounds the pivots on the ORIGINAL problem (level 0); the coarse levels only construct
     // its start basis and run to their optimum
-    const long long level_max_iter = lev == 0 ? p.max_iter : LLONG_MAX;
+    const long long level_max_iter = li == 0 ? p.max_iter : LLONG_MAX;
     __syncthreads();
 #ifdef STM_EMD_PROFILE
     const long long c_l1 = clock64();
@@ -1293,18 +1312,26 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     const long long c_l2 = clock64();
 #endif
     if (status != 0) break;
-    if (lev > 0) {
+    if (li > 0) {
       EMD_SCRATCH(sc);
       // ---- refinement: this level's optimum -> feasible forest of level lev - 1 --------------------------------
       // Stage 1, per coarse source I: north-west corner between its children (in order) and its arcs (by increasing
       // target) gives pieces (fine source, arc, flow).  Stage 2, per coarse target J: north-west corner between the
       // pieces of its arcs (by increasing source) and its children gives the fine arcs, grouped by fine target.
       const int nS = n, nT = m;
-      const int32_t* cs = p.hs.child + (size_t)lev * (p.hs.stride + 1);
-      const int32_t* ct = sc.ht.child + (size_t)lev * (sc.ht.stride + 1);
-      const int64_t* fs = p.hs.mass + (size_t)(lev - 1) * p.hs.stride;
-      const int64_t* ft = sc.ht.mass + (size_t)(lev - 1) * sc.ht.stride;
-      const int mf = s_lv[lev - 1];
+      // the finer level in use is one or two bit levels below; across a skipped level the child ranges compose (descendants
+      // stay contiguous in Morton order)
+      const int flev = s_lv[li - 1] >> 20;
+      const bool two = lev - flev == 2;
+      const int32_t* cs2 = p.hs.child + (size_t)lev * (p.hs.stride + 1);
+      const int32_t* ct2 = sc.ht.child + (size_t)lev * (sc.ht.stride + 1);
+      const int32_t* cs1 = p.hs.child + (size_t)(lev - 1) * (p.hs.stride + 1);
+      const int32_t* ct1 = sc.ht.child + (size_t)(lev - 1) * (sc.ht.stride + 1);
+      auto CS = [&](int I) { const int c = cs2[I]; return two ? cs1[c] : c; };
+      auto CT = [&](int J) { const int c = ct2[J]; return two ? ct1[c] : c; };
+      const int64_t* fs = p.hs.mass + (size_t)flev * p.hs.stride;
+      const int64_t* ft = sc.ht.mass + (size_t)flev * sc.ht.stride;
+      const int mf = s_lv[li - 1] & 0xfffff;
       int Ec = 0;
       {   // real tree arcs with positive flow, compacted in node order
         const int per = (nS + nT + EMD_THREADS - 1) / EMD_THREADS;
@@ -1351,8 +1378,8 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       // stage 1: count, offsets, write
       for (int pass = 0; pass < 2; ++pass) {
         for (int I = tid; I < nS; I += EMD_THREADS) {
-          int a = cs[I];
-          const int a_end = cs[I + 1];
+          int a = CS(I);
+          const int a_end = CS(I + 1);
           long long ra = a < a_end ? fs[a] : 0;
           for (int r = sc.offS[I]; r < sc.offS[I + 1]; ++r) {
             long long rb = sc.aF[sc.lstS[r]];
@@ -1386,8 +1413,8 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       // stage 2: count, offsets, write
       for (int pass = 0; pass < 2; ++pass) {
         for (int J = tid; J < nT; J += EMD_THREADS) {
-          int b = ct[J];
-          const int b_end = ct[J + 1];
+          int b = CT(J);
+          const int b_end = CT(J + 1);
           long long rb = b < b_end ? ft[b] : 0;
           int E = pass == 0 ? 0 : sc.aoff[J];
           if (pass == 1 && b < b_end) sc.tfirst[b] = E;
@@ -1409,7 +1436,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
         __syncthreads();
         if (pass == 0) cta_prefix_inplace<EMD_THREADS>(sc.aoff, nT + 1, s_ws);
       }
-      if (tid == 0) { const int Eall = sc.aoff[nT]; EMD_CHECK(Eall <= cap && Eall < s_lv[lev - 1] + p.src_hdr[lev - 1], "forest size"); sc.tfirst[mf] = Eall; s_i[8] = Eall; }
+      if (tid == 0) { const int Eall = sc.aoff[nT]; EMD_CHECK(Eall <= cap && Eall < mf + p.src_hdr[flev], "forest size"); sc.tfirst[mf] = Eall; s_i[8] = Eall; }
       __syncthreads();
     }
 #ifdef STM_EMD_PROFILE
