@@ -158,7 +158,7 @@ int stm_gmm_dist_one_vs_all(const double* qw, const double* qmu, const double* q
  *   max_tgt      largest target support in the batch; order[G] optional processing order (largest first)
  *   max_iter     pivot limit on the problem itself (reference: numItermax=200000); block_size: arcs priced per block
  *                search step, 0 = about 32 arcs per thread rounded to whole target rows (LEMON/POT use sqrt(n*m))
- *   flags        0 = multiscale start basis: the grid is coarsened by 2 x 2 cells level by level, the coarsest problem
+ *   flags        0 = multiscale start basis: the grid is coarsened one Morton bit (half a cell) per level, the coarsest problem
  *                is solved from the artificial star and every finer level starts from the refinement of the coarser
  *                optimum; the finest level is the problem itself, solved to optimality by the same simplex, with about
  *                ten times fewer pivots (max_iter applies to that level; out_iters counts all levels).

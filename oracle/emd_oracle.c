@@ -22,7 +22,8 @@
  * Two start bases (the LP optimum — the value the reference returns — does not depend on the start):
  *   - STAR  (stm_oracle_emd, or flags & 1): the artificial star POT/LEMON start from;
  *   - MULTISCALE (stm_oracle_emd_ms, default of the CUDA kernel): the nodes are sorted along the Morton curve, the
- *     grid is coarsened by 2 x 2 cells level by level, the coarsest problem is solved from the star and every
+ *     grid is coarsened one Morton bit per level (cells halved along y, then x; levels that merge < 20 % of the nodes
+ *     are skipped), the coarsest problem is solved from the star and every
  *     finer level starts from the refinement of the coarser optimum (two north-west-corner passes: the flow of a
  *     coarse arc is dealt to the children of its source cell, then to the children of its target cell).  The
  *     finest level is the original problem, solved to optimality by the same simplex — about ten times fewer pivots.

@@ -15,14 +15,15 @@
 //     potential shift of the re-hung subtree and preorder re-numbering are all data-parallel over the CTA;
 //   * arc flows (int64) live in shared memory as far as it reaches, the rest in a per-CTA global slice;
 //   * MULTISCALE START (default): the LP optimum does not depend on the start basis, the number of pivots does — by
-//     a factor of ten.  Sources and targets are sorted along the Morton curve, the grid is coarsened by 2 x 2 cells
-//     level by level (a level's nodes are runs of the finer level's nodes), the coarsest problem (<= 64 nodes) is
+//     a factor of ten.  Sources and targets are sorted along the Morton curve and the grid is coarsened one Morton bit
+//     at a time — cells are halved along y, then along x, ... (a level's nodes are runs of the finer level's nodes; a
+//     level that merges < 20 % of the nodes is skipped) —, the coarsest problem (<= 64 nodes) is
 //     solved from the artificial star, and every finer level starts from the REFINEMENT of the coarser optimum:
 //     two north-west-corner passes deal the flow of each coarse arc first to the children of its source cell, then
 //     to the children of its target cell — a feasible forest with positive flows, completed to a strongly
 //     feasible spanning tree by hanging each component's first source under the root with a zero-flow
 //     artificial arc.  The finest level is the original problem, solved to optimality by the same simplex.
-//     Visium-size problems (4,992 x 3,000): ~6.5k pivots on the original problem + ~9k cheaper ones on the coarse
+//     Visium-size problems (4,992 x 3,000): ~6k pivots on the original problem + ~8k cheaper ones on the coarse
 //     levels instead of ~90k from the star.  STM_EMD_STAR_START selects the star (POT's start; same pivot sequence
 //     as oracle/emd_oracle.c::stm_oracle_emd for the same block size).
 #include <limits.h>
