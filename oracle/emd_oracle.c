@@ -185,8 +185,9 @@ static int net_from_forest(Net* g, const int32_t* ai, const int32_t* aj, const i
  * only these <= T candidates (those no longer negative are dropped), enter the most negative one (ties: lowest class)
  * and fall back to the block search where the last pass stopped once none is negative (LEMON's candidate-list idea).
  * Within a pass, the block that follows k blocks without a negative arc is 2^min(k, STM_EMD_GROW) times B long.
- * cand_threads < 0: the pricing of the global-tree kernel (problems beyond one CTA's shared memory): plain block search
- * whose blocks grow the same way (up to 2^STM_EMD_GROW_G times B and at most 64 target rows), no candidate list.
+ * cand_threads < 0: the pricing of the global-tree kernel (problems beyond one CTA's shared memory) on blocks of at most
+ * 64 whole target rows: its 512 threads own the sources i = thread (mod 512); ties inside a block go to the lowest source
+ * index, then the first row; candidate list per thread as above; blocks grow up to 2^STM_EMD_GROW_G times B within 64 rows.
  */
 static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_threads, int64_t* iters) {
   const int n = g->n, m = g->m, N = g->N;
@@ -201,13 +202,13 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
   if (B > n_arcs) B = n_arcs;
   int64_t next_arc = 0, it = *iters;
   int status = 0;
-  const int T = cand_threads > 0 ? cand_threads : 0;
+  const int grow_g = cand_threads < 0 && B % n == 0 && B / n <= 64;   /* whole-row pricing of the global-tree kernel */
+  const int T = cand_threads > 0 ? cand_threads : grow_g ? 512 : 0;      /* candidate classes */
   const int R = T == 256 ? 5 : T > 0 ? (5120 + T - 1) / T : 0;
-  const int use_cand = T > 0 && B % n == 0 && (int64_t)n <= (int64_t)R * T;
+  const int use_cand = cand_threads > 0 && B % n == 0 && (int64_t)n <= (int64_t)R * T;
   int teff = 32;
   while (use_cand && teff < (n + R - 1) / R) teff <<= 1;
   const int groups = use_cand ? T / teff : 1;
-  const int grow_g = cand_threads < 0 && B % n == 0 && B / n <= 64;   /* pricing of the global-tree kernel: growing blocks only */
   int64_t* cand_e = (int64_t*)malloc(sizeof(int64_t) * (T + 1));
   int64_t* cls_rc = (int64_t*)malloc(sizeof(int64_t) * (T + 1));
   int have_cand = 0;
@@ -237,7 +238,7 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
       }
       int64_t cnt = Bk < n_arcs - scanned ? Bk : n_arcs - scanned;
       ++empty;
-      if (use_cand) for (int c = 0; c < T; ++c) { cand_e[c] = -1; cls_rc[c] = 0; }
+      if (use_cand || grow_g) for (int c = 0; c < T; ++c) { cand_e[c] = -1; cls_rc[c] = 0; }
       best_e = -1; best_rc = 0;
       int j = (int)(next_arc / n), i = (int)(next_arc - (int64_t)j * n);
       int r = 0;                                           /* row of the block (use_cand: blocks start on a row) */
@@ -248,13 +249,16 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
         if (use_cand) {
           const int c = (r % groups) * teff + i % teff;
           if (rc < cls_rc[c]) { cls_rc[c] = rc; cand_e[c] = (int64_t)j * n + i; }   /* the class's first minimum */
+        } else if (grow_g) {   /* global-tree kernel: thread = source index mod 512; ties: lowest source, then first row */
+          const int c = i % T;
+          if (rc < cls_rc[c] || (rc == cls_rc[c] && rc < 0 && i < (int)(cand_e[c] % n))) { cls_rc[c] = rc; cand_e[c] = (int64_t)j * n + i; }
         }
         if (++i == n) { i = 0; ++r; if (++j == m) j = 0; }
       }
       scanned += cnt;
       next_arc += cnt;
       if (next_arc >= n_arcs) next_arc -= n_arcs;
-      if (best_e >= 0) { have_cand = use_cand; break; }
+      if (best_e >= 0) { have_cand = use_cand || grow_g; break; }
     }
     if (best_e < 0) break; /* optimal */
     if (it >= max_iter) { status = 1; break; }

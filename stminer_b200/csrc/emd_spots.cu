@@ -9,7 +9,10 @@
 //   * masses are scaled to integers (total 2^50), potentials are integers, so every comparison is exact
 //     and the pivot sequence is the one of the CPU oracle (oracle/emd_oracle.c) for the same block size;
 //   * pricing is a block search: the CTA evaluates a block of arcs in parallel and enters the most negative
-//     reduced cost of the first block that has one (LEMON's rule);
+//     reduced cost of the first block that has one (LEMON's rule).  On top of it (default, STM_EMD_NO_CANDIDATES turns
+//     it off): a CANDIDATE LIST — every thread keeps the best arc it saw in a successful block scan and the following
+//     "minor" iterations re-price only those <= 512 arcs until none is negative — and GROWING BLOCKS — the block after
+//     k fruitless ones is 2^min(k, 3) times as long.  Both belong to the pivot rule the oracle restates (cand_threads);
 //   * the spanning tree is stored as parent / preorder position / subtree size (uint16) in shared memory, a
 //     subtree being a contiguous segment of the preorder array — cycle paths, leaving-arc search, flow update,
 //     potential shift of the re-hung subtree and preorder re-numbering are all data-parallel over the CTA;
@@ -424,6 +427,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
   __shared__ int s_row[GLOBAL ? 2 * EMD_ROWS_G : 1];          // the block's target rows: -2x, -2y
   __shared__ long long s_rowp[GLOBAL ? EMD_ROWS_G : 1];       // and potentials (global-tree pricing)
   __shared__ int s_cand[(WIDE || GLOBAL) ? 1 : EMD_THREADS];  // candidate list: every thread's best arc (j << 16 | i) of the last pass
+  __shared__ int2 s_candg[GLOBAL ? EMD_THREADS : 1];          // the same for the global-tree kernel: (source, target), source < 0: none
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // the scratch pointers are recomputed where they are needed (hierarchy, tree build, refinement) so that they do not
@@ -807,6 +811,49 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           }
         }
       }
+      if constexpr (GLOBAL) {
+        if (have_cand) {
+          // ---- minor iteration of the global-tree kernel: the same rule with 64-bit reduced costs ----------------
+          const int2 c = s_candg[tid];
+          long long rc = 0;
+          if (c.x >= 0) {
+            const int sxy = s_xy[c.x], txy = s_xy[n + c.y];
+            const long long nx2 = -2 * ((txy << 16) >> 16), ny2 = -2 * (txy >> 16);
+            rc = ((sxy << 16) >> 16) * nx2 + ((sxy >> 16) * ny2 + ((long long)s_pi[c.x] - (long long)s_pi[n + c.y]));
+            if (rc >= 0) { s_candg[tid].x = -1; rc = 0; }          // no longer a candidate
+          }
+          long long r64 = rc;
+          unsigned t32 = rc < 0 ? (unsigned)tid : 0xffffffffu;      // ties: lowest thread
+          for (int o = 16; o > 0; o >>= 1) {
+            const long long orc = shfl_xor_ll(r64, o);
+            const unsigned ot = __shfl_xor_sync(FULL_MASK, t32, o);
+            if (orc < r64 || (orc == r64 && ot < t32)) { r64 = orc; t32 = ot; }
+          }
+          long long* wr = s_wrc64 + (round & 1) * EMD_WARPS;
+          unsigned* wk = reinterpret_cast<unsigned*>(s_wkey + (round & 1) * EMD_WARPS);
+          if (lane == 0) { wr[warp] = r64; wk[warp] = t32; }
+          __syncthreads();
+          r64 = lane < EMD_WARPS ? wr[lane] : 0;
+          t32 = lane < EMD_WARPS ? wk[lane] : 0xffffffffu;
+          for (int o = 16; o > 0; o >>= 1) {
+            const long long orc = shfl_xor_ll(r64, o);
+            const unsigned ot = __shfl_xor_sync(FULL_MASK, t32, o);
+            if (orc < r64 || (orc == r64 && ot < t32)) { r64 = orc; t32 = ot; }
+          }
+          ++round;
+          if (r64 < 0) {
+            const int2 cw = s_candg[t32];                          // its owner kept it
+            best_rc = (pi_t)r64;
+            cand_j = cw.y;
+            best_e = cw.y * n + cw.x;
+#ifdef STM_EMD_PROFILE
+            ++n_minor;
+#endif
+          } else {
+            have_cand = false;
+          }
+        }
+      }
       int empty = 0;                       // consecutive blocks of this pass without a negative arc
       while (best_e < 0 && scanned < n_arcs) {
         // with the candidate list, the block after k empty ones is 2^min(k, EMD_GROW) times as long: near the optimum most
@@ -967,20 +1014,31 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
               // The entering arc among the arcs that attain the minimum: lowest source index first, then the first row of
               // the block (a thread meets its sources tile by tile, so "first in block order" would need a second scan; this
               // order costs nothing — first tile, first slot, first row — and the oracle resolves ties the same way).
+              // Every thread with a negative minimum locates it the same way: its candidate for the minor iterations.
               unsigned mykey = 0xffffffffu;                    // source index * EMD_ROWS_G + row of the block
-              if (trc == (long long)g_rc) {
+              int2 mycand = make_int2(-1, 0);
+              if (trc < 0 && (grow_g || trc == (long long)g_rc)) {
+                bool found = false;
 #pragma unroll 1
-                for (int r = 0; r < RG && mykey == 0xffffffffu; ++r) {
+                for (int r = 0; r < RG && !found; ++r) {
                   const int i = tbase + tid + r * EMD_THREADS;
                   if (i >= n) break;
                   const int xy = s_xy[i];
                   const long long sxi = (xy << 16) >> 16, syi = xy >> 16, spi = (long long)s_pi[i];
                   for (int r2 = 0; r2 < rows; ++r2) {
                     const long long rc = sxi * s_row[2 * r2] + (syi * s_row[2 * r2 + 1] + (spi - s_rowp[r2]));
-                    if (rc == (long long)g_rc) { mykey = (unsigned)i * EMD_ROWS_G + (unsigned)r2; break; }
+                    if (rc == trc) {
+                      int j = j0 + r2;
+                      while (j >= m) j -= m;
+                      mycand = make_int2(i, j);
+                      if (trc == (long long)g_rc) mykey = (unsigned)i * EMD_ROWS_G + (unsigned)r2;
+                      found = true;
+                      break;
+                    }
                   }
                 }
               }
+              if (grow_g) { s_candg[tid] = mycand; have_cand = true; }
               const unsigned w_k = __reduce_min_sync(FULL_MASK, mykey);
               unsigned* wk = reinterpret_cast<unsigned*>(s_wkey + (round & 1) * EMD_WARPS);
               if (lane == 0) wk[warp] = w_k;
@@ -1563,7 +1621,7 @@ int emd_launch(bool wide, const int32_t* src_x, const int32_t* src_y, const doub
     // ---- the batch does not fit a CTA's shared memory: tree in the CTA's global scratch (one CTA per SM) ----
     a.cap_nodes = (int32_t)ws_cap;
     const int64_t paths = 4 * (int64_t)EMD_MAXPATH_G * 4 + 64;
-    int64_t fcap_g = ((int64_t)max_optin - 4096 - paths) / 8;
+    int64_t fcap_g = ((int64_t)max_optin - 8192 - paths) / 8;       // static shared memory incl. the candidate list
     fcap_g = std::max<int64_t>(0, std::min<int64_t>(fcap_g, ws_cap)) & ~1LL;
     a.flow_smem_nodes = (int32_t)fcap_g;
     const size_t smem_g = (size_t)fcap_g * 8 + (size_t)paths;
