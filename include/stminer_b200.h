@@ -192,7 +192,8 @@ int64_t stm_emd_workspace_bytes(int32_t n_src, int64_t max_tgt, int32_t n_ctas);
 int32_t stm_emd_smem_node_capacity(int32_t wide);
 int32_t stm_emd_global_node_capacity(void);
 /* Threads per problem of the candidate-list pricing for a batch of this size: 512 (one CTA per SM), 256 (small
- * problems), 0 = plain block search (64-bit and global-tree kernels).  The CPU oracle takes it as cand_threads. */
+ * problems), 0 = plain block search (the 64-bit shared-memory kernel), -1 = the global-tree kernel (512 threads, sources
+ * dealt by index mod 512, ties to the lowest source index).  The CPU oracle takes the value as cand_threads. */
 int32_t stm_emd_pricing_threads(int32_t n_src, int64_t max_tgt, int32_t wide);
 int stm_emd_spots_batched(const int32_t* src_x, const int32_t* src_y, const double* src_mass, int32_t n_src,
                           const int64_t* tgt_ptr, const int32_t* tgt_x, const int32_t* tgt_y,

@@ -1692,7 +1692,7 @@ extern "C" int32_t stm_emd_pricing_threads(int32_t n_src, int64_t max_tgt, int32
   if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
   const int64_t ws_cap = stm::emd_ws_cap(n_src, max_tgt);
   const int64_t max_cap = (((int64_t)max_optin - 4096 - (int64_t)stm::emd_smem_bytes(0)) / (int64_t)stm::emd_node_bytes(false)) & ~7LL;
-  if (ws_cap > max_cap) return 0;                                   // global-tree kernel: plain block search
+  if (ws_cap > max_cap) return -1;                                  // global-tree kernel (its own candidate classes and tie rule)
   return stm::emd_smem_bytes(ws_cap, 0, false) * 2 + 2048 > (size_t)max_optin ? STM_EMD_T_BIG : 256;
 }
 
