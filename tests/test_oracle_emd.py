@@ -73,6 +73,11 @@ def test_multiscale_start_reaches_the_same_optimum(c, d):
     assert abs(cost - float(d["cost"])) <= 1e-9 * max(1.0, float(d["cost"]))
     cost2, status2, _, _ = eo.emd_multiscale(d["sx"], d["sy"], d["sm"], d["tx"], d["ty"], d["tm"], block_size=23)
     assert status2 == 0 and abs(cost2 - cost) <= 1e-11 * max(1.0, cost)
+    # the pivot rules of the CUDA kernels (candidate list + growing blocks for 256 / 512 threads per problem, the
+    # global-tree kernel's variant) change the pivots, never the optimum
+    for T in (256, 512, -1):
+        cost3, status3, _, _ = eo.emd_multiscale(d["sx"], d["sy"], d["sm"], d["tx"], d["ty"], d["tm"], cand_threads=T)
+        assert status3 == 0 and abs(cost3 - cost) <= 1e-11 * max(1.0, cost), T
 
 
 def test_oracle_matches_visium_size_lp_golden():
@@ -85,6 +90,11 @@ def test_oracle_matches_visium_size_lp_golden():
         ref = float(z[p + "cost"])
         assert status == 0
         assert abs(cost - ref) <= 1e-7 * ref, (c, cost, ref)
+        # with the pricing of the kernel that solves a problem of this size (fewer pivots, same optimum)
+        T = 512 if len(z[p + "sx"]) + len(z[p + "tx"]) < 11000 else -1
+        cost_c, status_c, pivots_c, _ = eo.emd_multiscale(z[p + "sx"], z[p + "sy"], z[p + "sm"], z[p + "tx"], z[p + "ty"], z[p + "tm"],
+                                                          cand_threads=T)
+        assert status_c == 0 and abs(cost_c - ref) <= 1e-7 * ref and pivots_c < pivots, (c, cost_c, ref, pivots_c, pivots)
 
 
 def _edge_problems():
