@@ -437,6 +437,27 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
   { EMD_SCRATCH(sc0); flow = sc0.flow; }
   auto FL = [&](int v) -> long long& { return v < fcap ? s_flow[v] : *reinterpret_cast<long long*>(flow + v); };
   const bool hier_ok = p.src_hdr[EMD_HDR_OK] != 0;
+  // CTA-wide lexicographic minimum of (64-bit value, 32-bit key) by shuffles: over the warp, then — through one shared entry
+  // per warp, double-buffered by `round`, one barrier — over the per-warp results; every thread gets the result
+  auto cta_lexmin64 = [&](long long& r64, unsigned& k32, unsigned& round) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long orc = shfl_xor_ll(r64, o);
+      const unsigned ok = __shfl_xor_sync(FULL_MASK, k32, o);
+      if (orc < r64 || (orc == r64 && ok < k32)) { r64 = orc; k32 = ok; }
+    }
+    long long* wr = s_wrc64 + (round & 1) * EMD_WARPS;
+    unsigned* wk = reinterpret_cast<unsigned*>(s_wkey + (round & 1) * EMD_WARPS);
+    if (lane == 0) { wr[warp] = r64; wk[warp] = k32; }
+    __syncthreads();
+    r64 = lane < EMD_WARPS ? wr[lane] : LLONG_MAX;
+    k32 = lane < EMD_WARPS ? wk[lane] : 0xffffffffu;
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long orc = shfl_xor_ll(r64, o);
+      const unsigned ok = __shfl_xor_sync(FULL_MASK, k32, o);
+      if (orc < r64 || (orc == r64 && ok < k32)) { r64 = orc; k32 = ok; }
+    }
+    ++round;
+  };
 
   for (;;) {
     __syncthreads();
@@ -824,23 +845,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           }
           long long r64 = rc;
           unsigned t32 = rc < 0 ? (unsigned)tid : 0xffffffffu;      // ties: lowest thread
-          for (int o = 16; o > 0; o >>= 1) {
-            const long long orc = shfl_xor_ll(r64, o);
-            const unsigned ot = __shfl_xor_sync(FULL_MASK, t32, o);
-            if (orc < r64 || (orc == r64 && ot < t32)) { r64 = orc; t32 = ot; }
-          }
-          long long* wr = s_wrc64 + (round & 1) * EMD_WARPS;
-          unsigned* wk = reinterpret_cast<unsigned*>(s_wkey + (round & 1) * EMD_WARPS);
-          if (lane == 0) { wr[warp] = r64; wk[warp] = t32; }
-          __syncthreads();
-          r64 = lane < EMD_WARPS ? wr[lane] : 0;
-          t32 = lane < EMD_WARPS ? wk[lane] : 0xffffffffu;
-          for (int o = 16; o > 0; o >>= 1) {
-            const long long orc = shfl_xor_ll(r64, o);
-            const unsigned ot = __shfl_xor_sync(FULL_MASK, t32, o);
-            if (orc < r64 || (orc == r64 && ot < t32)) { r64 = orc; t32 = ot; }
-          }
-          ++round;
+          cta_lexmin64(r64, t32, round);
           if (r64 < 0) {
             const int2 cw = s_candg[t32];                          // its owner kept it
             best_rc = (pi_t)r64;
@@ -1102,25 +1107,10 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
             // per-warp entries
             long long r64 = bi >= 0 ? (long long)brc : LLONG_MAX;
             unsigned k32 = bi >= 0 ? (unsigned)k : 0xffffffffu;
-            for (int o = 16; o > 0; o >>= 1) {
-              const long long orc = shfl_xor_ll(r64, o);
-              const unsigned ok = __shfl_xor_sync(FULL_MASK, k32, o);
-              if (orc < r64 || (orc == r64 && ok < k32)) { r64 = orc; k32 = ok; }
-            }
-            long long* wr = s_wrc64 + (round & 1) * EMD_WARPS;
-            unsigned* wk = reinterpret_cast<unsigned*>(s_wkey + (round & 1) * EMD_WARPS);
-            if (lane == 0) { wr[warp] = r64; wk[warp] = k32; }
-            __syncthreads();
-            r64 = lane < EMD_WARPS ? wr[lane] : LLONG_MAX;
-            k32 = lane < EMD_WARPS ? wk[lane] : 0xffffffffu;
-            for (int o = 16; o > 0; o >>= 1) {
-              const long long orc = shfl_xor_ll(r64, o);
-              const unsigned ok = __shfl_xor_sync(FULL_MASK, k32, o);
-              if (orc < r64 || (orc == r64 && ok < k32)) { r64 = orc; k32 = ok; }
-            }
+            cta_lexmin64(r64, k32, round);
             g_rc = (pi_t)r64; g_k = k32;
           }
-          ++round;
+          if constexpr (!WIDE) ++round;
           }
         }
 #ifdef STM_EMD_PROFILE
