@@ -188,6 +188,9 @@ static int net_from_forest(Net* g, const int32_t* ai, const int32_t* aj, const i
  * cand_threads < 0: the pricing of the global-tree kernel (problems beyond one CTA's shared memory) on blocks of at most
  * 64 whole target rows: its 512 threads own the sources i = thread (mod 512); ties inside a block go to the lowest source
  * index, then the first row; candidate list per thread as above; blocks grow up to 2^STM_EMD_GROW_G times B within 64 rows.
+ * That kernel searches on the LOW 32 BITS of the reduced costs (its potentials are 64-bit, the reduced costs fit 32 bits in
+ * practice): the selected arc is re-priced exactly — a non-negative value is a wrap artefact and switches the rest of the
+ * level to 64-bit pricing — and when the 32-bit search finds nothing, one 64-bit sweep over all arcs certifies the optimum.
  */
 static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_threads, int64_t* iters) {
   const int n = g->n, m = g->m, N = g->N;
@@ -212,6 +215,7 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
   int64_t* cand_e = (int64_t*)malloc(sizeof(int64_t) * (T + 1));
   int64_t* cls_rc = (int64_t*)malloc(sizeof(int64_t) * (T + 1));
   int have_cand = 0;
+  int wide_pr = 0;   /* global-tree kernel: 64-bit pricing for the rest of the level (wrap artefact seen, or the certificate) */
   for (;;) {
     /* ---- entering arc ----------------------------------------------------------------------- */
     int64_t scanned = 0, best_e = -1, best_rc = 0;
@@ -227,6 +231,7 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
       if (best_e < 0) have_cand = 0;
     }
     int empty = 0;                             /* consecutive blocks of this pass without a negative arc */
+  search:
     while (best_e < 0 && scanned < n_arcs) {   /* major pass: block search over arcs e = j*n + i */
       /* with the candidate list, a block that follows k empty ones is 2^min(k, STM_EMD_GROW) times as long (the kernel
          amortises its per-block work over the long fruitless scans near the optimum) */
@@ -243,7 +248,8 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
       int j = (int)(next_arc / n), i = (int)(next_arc - (int64_t)j * n);
       int r = 0;                                           /* row of the block (use_cand: blocks start on a row) */
       for (int64_t k = 0; k < cnt; ++k) {
-        const int64_t rc = arc_cost(g, i, j) + g->pi[i] - g->pi[n + j];
+        int64_t rc = arc_cost(g, i, j) + g->pi[i] - g->pi[n + j];
+        if (grow_g && !wide_pr) rc = (int64_t)(int32_t)(uint32_t)rc;   /* the global-tree kernel prices on the low 32 bits */
         /* first minimum in block order; the global-tree kernel's whole-row blocks: lowest source index, then first row */
         if (rc < best_rc || (grow_g && rc == best_rc && rc < 0 && i < (int)(best_e % n))) { best_rc = rc; best_e = (int64_t)j * n + i; }
         if (use_cand) {
@@ -255,10 +261,19 @@ static int net_run(Net* g, int64_t max_iter, int64_t block_size, int cand_thread
         }
         if (++i == n) { i = 0; ++r; if (++j == m) j = 0; }
       }
+      if (best_e >= 0 && grow_g && !wide_pr) {   /* the selected arc re-priced in 64 bits */
+        const int bj = (int)(best_e / n), bi = (int)(best_e - (int64_t)bj * n);
+        best_rc = arc_cost(g, bi, bj) + g->pi[bi] - g->pi[n + bj];
+        if (best_rc >= 0) { wide_pr = 1; --empty; best_e = -1; best_rc = 0; continue; }   /* wrap artefact: the block again, in 64 bits */
+      }
       scanned += cnt;
       next_arc += cnt;
       if (next_arc >= n_arcs) next_arc -= n_arcs;
       if (best_e >= 0) { have_cand = use_cand || grow_g; break; }
+    }
+    if (best_e < 0 && grow_g && !wide_pr) {      /* nothing negative in the low words: the certificate is a 64-bit sweep */
+      wide_pr = 1; scanned = 0; empty = 0;
+      goto search;
     }
     if (best_e < 0) break; /* optimal */
     if (it >= max_iter) { status = 1; break; }

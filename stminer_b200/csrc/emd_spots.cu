@@ -774,6 +774,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
     // optimum, about 10 % fewer pivots and a third of the block scans on the coarse levels (oracle: cand_threads).
     const bool cand_on = !WIDE && !GLOBAL && whole_rows && !(p.flags & STM_EMD_NO_CANDIDATES);
     const bool grow_g = GLOBAL && whole_rows_g && !(p.flags & STM_EMD_NO_CANDIDATES);
+    bool wide_pr = false;     // global-tree kernel: 64-bit pricing for the rest of the level (32-bit wrap artefact, or the final certificate)
     const int rows_Bg = whole_rows_g ? B / n : 0;
     bool have_cand = false;
     // numItermax of the reference bounds the pivots on the ORIGINAL problem (level 0); the coarse levels only construct
@@ -859,6 +860,9 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           }
         }
       }
+      bool certify;
+      do {
+      certify = false;
       int empty = 0;                       // consecutive blocks of this pass without a negative arc
       while (best_e < 0 && scanned < n_arcs) {
         // with the candidate list, the block after k empty ones is 2^min(k, EMD_GROW) times as long: near the optimum most
@@ -984,6 +988,92 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
               s_rowp[r] = s_pi[n + j];
             }
             __syncthreads();
+            bool redo = false;
+            if (grow_g && !wide_pr) {
+              // 32-BIT PRICING.  The potentials are 64-bit because (span^2 + 1) * nodes exceeds int32, yet a reduced cost —
+              // a difference of two potentials plus a cost — fits 32 bits on every arc anyone has seen: the scan works on the
+              // low words with wrapping arithmetic (exact whenever |rc| < 2^31; a third of the instructions of the 64-bit
+              // scan), the arc it selects is re-priced in 64 bits (a non-negative value there = a wrap artefact: the level
+              // goes on in 64 bits), and so is the whole arc set once the 32-bit search finds nothing (the certificate).
+              int trc = 0;
+              int tbase = -1;                                  // the tile in which this thread's minimum was first reached
+              for (int base = 0; base < n; base += RG * EMD_THREADS) {
+                if (base + tid >= n) break;                    // no source of this tile is this thread's
+                unsigned sx[RG], sy[RG], sp[RG];
+#pragma unroll
+                for (int r = 0; r < RG; ++r) {
+                  int i = base + tid + r * EMD_THREADS;
+                  if (i >= n) i = base + tid;                  // slots beyond n repeat the thread's own first source of the tile
+                  const int xy = s_xy[i];
+                  sx[r] = (unsigned)((xy << 16) >> 16); sy[r] = (unsigned)(xy >> 16);
+                  sp[r] = (unsigned)s_pi[i];
+                }
+                const int before = trc;
+                for (int r2 = 0; r2 < rows; ++r2) {
+                  const unsigned nx2 = (unsigned)s_row[2 * r2], ny2 = (unsigned)s_row[2 * r2 + 1], bj = (unsigned)s_rowp[r2];
+#pragma unroll
+                  for (int r = 0; r < RG; ++r) trc = min(trc, (int)(sx[r] * nx2 + (sy[r] * ny2 + (sp[r] - bj))));
+                }
+                if (trc < before) tbase = base;
+              }
+              int g32;
+              {
+                const int w_rc = __reduce_min_sync(FULL_MASK, trc);
+                int* wrc = reinterpret_cast<int*>(s_wkey + (round & 1) * EMD_WARPS);
+                if (lane == 0) wrc[warp] = w_rc;
+                __syncthreads();
+                g32 = __reduce_min_sync(FULL_MASK, lane < EMD_WARPS ? wrc[lane] : 0);
+                ++round;
+              }
+              if (g32 < 0) {
+                unsigned mykey = 0xffffffffu;                  // source index * EMD_ROWS_G + row of the block (ties: see below)
+                int2 mycand = make_int2(-1, 0);
+                if (trc < 0) {
+                  bool found = false;
+#pragma unroll 1
+                  for (int r = 0; r < RG && !found; ++r) {
+                    const int i = tbase + tid + r * EMD_THREADS;
+                    if (i >= n) break;
+                    const int xy = s_xy[i];
+                    const unsigned sxi = (unsigned)((xy << 16) >> 16), syi = (unsigned)(xy >> 16), spi = (unsigned)s_pi[i];
+                    for (int r2 = 0; r2 < rows; ++r2) {
+                      const int rc = (int)(sxi * (unsigned)s_row[2 * r2] + (syi * (unsigned)s_row[2 * r2 + 1] + (spi - (unsigned)s_rowp[r2])));
+                      if (rc == trc) {
+                        int j = j0 + r2;
+                        while (j >= m) j -= m;
+                        mycand = make_int2(i, j);
+                        if (trc == g32) mykey = (unsigned)i * EMD_ROWS_G + (unsigned)r2;
+                        found = true;
+                        break;
+                      }
+                    }
+                  }
+                }
+                s_candg[tid] = mycand; have_cand = true;
+                const unsigned w_k = __reduce_min_sync(FULL_MASK, mykey);
+                unsigned* wk = reinterpret_cast<unsigned*>(s_wkey + (round & 1) * EMD_WARPS);
+                if (lane == 0) wk[warp] = w_k;
+                __syncthreads();
+                const unsigned g_key = __reduce_min_sync(FULL_MASK, lane < EMD_WARPS ? wk[lane] : 0xffffffffu);
+                ++round;
+                int j = j0 + (int)(g_key % EMD_ROWS_G);
+                while (j >= m) j -= m;
+                const int ie = (int)(g_key / EMD_ROWS_G);
+                const int sxy = s_xy[ie], txy = s_xy[n + j];
+                const long long rc64 = (long long)((sxy << 16) >> 16) * (-2 * ((txy << 16) >> 16)) +
+                                       ((long long)(sxy >> 16) * (-2 * (txy >> 16)) + ((long long)s_pi[ie] - (long long)s_pi[n + j]));
+                if (rc64 < 0) {
+                  int k = j * n + ie - next_arc;
+                  if (k < 0) k += n_arcs;
+                  g_k = (unsigned)k;
+                  g_rc = (pi_t)rc64;
+                } else {                                        // wrap artefact: this block again, in 64 bits
+                  wide_pr = true; redo = true; have_cand = false;
+                }
+              } else {
+                g_rc = PI_NONE;
+              }
+            } else {
             long long trc = 0;
             int tbase = -1;                                    // the tile in which this thread's minimum was first reached
             for (int base = 0; base < n; base += RG * EMD_THREADS) {
@@ -1060,6 +1150,8 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
             } else {
               g_rc = PI_NONE;
             }
+            }
+            if (redo) { --empty; continue; }
           }
           }
           if (!fast_done) {
@@ -1128,6 +1220,11 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
           break;
         }
       }
+      if constexpr (GLOBAL) {
+        // nothing negative in the low words: the certificate of optimality is a sweep over all arcs in 64 bits
+        if (best_e < 0 && grow_g && !wide_pr) { wide_pr = true; scanned = 0; certify = true; }
+      }
+      } while (certify);
       PROF_T(c_price)
 #ifdef STM_EMD_PROFILE
       n_scanned += scanned;
