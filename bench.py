@@ -440,7 +440,7 @@ def run_ours(args, rank, world, local_rank):
                  "mean_target_bins": float(np.mean([len(t[0]) for t in tg50])), "seconds": t_5,
                  "optimal": int((s50_ == 0).sum()), "mean_pivots": float(i50.mean()),
                  "note": "global-memory-tree kernel (beyond one CTA's shared memory), one CTA per problem, all in flight "
-                         "together; 8 dense bin50 genes (26,000 bins each) in flight take 15.6 s (profiles/r2_tuning_log.txt)"}
+                         "together; 8 dense bin50 genes (26,000 bins each) in flight take 14.5 s (profiles/r2_tuning_log.txt)"}
 
     # ---- the step after the distance matrix: cluster() = SMACOF MDS (4 restarts, 20 components) on the G x G matrix ----
     mds = None

@@ -1398,11 +1398,28 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
         }
       }
       for (int t = tid; t <= k; t += EMD_THREADS) { const int v = pathX[t]; s_P[t] = s_pos[v]; s_S[t] = s_size[v]; }
-      // potential shift of the re-hung subtree (a contiguous preorder segment)
-      for (int x = a0 + tid; x < a0 + s; x += EMD_THREADS) s_pi[s_order[x]] += shift;
-      // affected preorder range
+      // potential shift of the re-hung subtree (a contiguous preorder segment), copy of the affected preorder range
       const int lo = pt < a0 ? pt + 1 : a0, hi = pt < a0 ? a0 + s : pt + 1;
-      for (int x = lo + tid; x < hi; x += EMD_THREADS) s_tmp[x] = s_order[x];
+      if constexpr (GLOBAL) {
+        // the tree lives in L2: one pass over the range (the subtree is part of it), four independent loads in flight
+        constexpr int UB = 4;
+        for (int x = lo + tid; x < hi; x += UB * EMD_THREADS) {
+          int o[UB];
+          pi_t pv[UB];
+#pragma unroll
+          for (int q = 0; q < UB; ++q) { const int xq = x + q * EMD_THREADS; o[q] = xq < hi ? (int)s_order[xq] : 0; }
+#pragma unroll
+          for (int q = 0; q < UB; ++q) { const int xq = x + q * EMD_THREADS; pv[q] = (xq >= a0 && xq < a0 + s) ? s_pi[o[q]] : 0; }
+#pragma unroll
+          for (int q = 0; q < UB; ++q) {
+            const int xq = x + q * EMD_THREADS;
+            if (xq < hi) { s_tmp[xq] = (idx_t)o[q]; if (xq >= a0 && xq < a0 + s) s_pi[o[q]] = pv[q] + shift; }
+          }
+        }
+      } else {
+        for (int x = a0 + tid; x < a0 + s; x += EMD_THREADS) s_pi[s_order[x]] += shift;
+        for (int x = lo + tid; x < hi; x += EMD_THREADS) s_tmp[x] = s_order[x];
+      }
       __syncthreads();
       // ---- reversed path: parents, flows, sizes (flows read before anyone overwrites them) ----------
       {
@@ -1420,8 +1437,16 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
       for (int t = k + 1 + tid; t < lenX; t += EMD_THREADS) s_size[pathX[t]] -= (idx_t)s;
       for (int t = tid; t < lenY; t += EMD_THREADS) s_size[pathY[t]] += (idx_t)s;
       // ---- preorder re-numbering of the affected range ------------------------------------------------
-      for (int x = lo + tid; x < hi; x += EMD_THREADS) {
-        const int v = s_tmp[x];
+      constexpr int UR = GLOBAL ? 4 : 1;         // global tree: four copied entries loaded before they are placed
+      for (int xb = lo + tid; xb < hi; xb += UR * EMD_THREADS) {
+        int vq[UR];
+#pragma unroll
+        for (int q = 0; q < UR; ++q) { const int xq = xb + q * EMD_THREADS; vq[q] = xq < hi ? (int)s_tmp[xq] : 0; }
+#pragma unroll
+        for (int q = 0; q < UR; ++q) {
+        const int x = xb + q * EMD_THREADS;
+        if (x >= hi) break;
+        const int v = vq[q];
         int f;
         if (x < a0 || x >= a0 + s) {
           const int xr = x < a0 ? x : x - s;
@@ -1439,6 +1464,7 @@ __global__ void __launch_bounds__(EMD_THREADS, ONE_PER_SM ? 1 : STM_EMD_MINB_SMA
         }
         s_order[f] = (idx_t)v;
         s_pos[v] = (idx_t)f;
+        }
       }
       __syncthreads();
       PROF_T(c_update)
