@@ -96,6 +96,31 @@ def test_emd_beyond_one_cta_runs_with_the_tree_in_global_memory(cuda_device):
         assert abs(costR[g] - c) <= 1e-11 * c
 
 
+def test_emd_global_tree_32bit_search_survives_wrapping_reduced_costs(cuda_device):
+    """The global-tree kernel searches on the low 32 bits of the reduced costs.  Targets whose integer mass is 0 hang on an
+    artificial arc with potential +BIG (~1e13 here), so the reduced costs of their arcs do not fit 32 bits: whatever the
+    wrapped search makes of them, the 64-bit re-pricing of the selected arc and the 64-bit certificate sweep keep the result
+    exact — same optimum and same pivots as the oracle's restatement (cand_threads = -1)."""
+    from stminer_b200.Algorithm.distance import emd_batched, emd_pricing_threads
+    rng = np.random.default_rng(5)
+    n, m = 9000, 4200
+    cells = rng.permutation(150 * 150)[:n]
+    src = (cells // 150, cells % 150, rng.random(n) + 0.1)
+    t = rng.permutation(150 * 150)[:m]
+    tm = rng.random(m) + 0.1
+    tm[[17, 2900, 4100]] = 1e-26                       # integer image 0: no arc in any refined forest
+    tgt = (t // 150, t % 150, tm)
+    assert emd_pricing_threads(src, [tgt]).tolist() == [-1]
+    cost, status, iters = emd_batched(src, [tgt], block_size=8 * n, return_iters=True)
+    c, st, it, lev = eo.emd_multiscale(*src, *tgt, block_size=8 * n, cand_threads=-1)
+    c0, st0, _, _ = eo.emd_multiscale(*src, *tgt)                                   # plain 64-bit block search
+    assert status[0] == st == st0 == 0
+    assert abs(cost[0] - c0) <= 1e-11 * c0 and abs(c - c0) <= 1e-11 * c0
+    assert iters[0] == it, (iters[0], it, lev[:8])
+    cost_d, status_d = emd_batched(src, [tgt])                                      # the kernel's default blocks
+    assert status_d[0] == 0 and abs(cost_d[0] - c0) <= 1e-11 * c0
+
+
 def test_emd_node_capacity_limit_reports_status_3(cuda_device):
     """Beyond the global-tree capacity (or 2^31 arcs) a problem is refused with status 3 and NaN, never a wrong value."""
     from stminer_b200 import _lib

@@ -128,3 +128,8 @@ def test_multiscale_edge_cases_match_lp(name):
     assert abs(cost - ref) <= 1e-8 * max(1.0, ref), (name, cost, ref)
     star = eo.emd_network_simplex(*src, *tgt)[0]
     assert abs(cost - star) <= 1e-11 * max(1.0, star)
+    # the global-tree kernel's rule searches on the low 32 bits of the reduced costs; nodes hanging on artificial arcs
+    # (potentials +-BIG: "tiny_mass") make those wrap, and the 64-bit re-pricing / certificate sweep must catch it
+    for T in (256, -1):
+        cost_t, status_t, _, _ = eo.emd_multiscale(*src, *tgt, cand_threads=T)
+        assert status_t == 0 and abs(cost_t - star) <= 1e-11 * max(1.0, star), (name, T, cost_t, star)
